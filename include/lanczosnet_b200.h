@@ -1,0 +1,153 @@
+/*
+ * lanczosnet_b200.h -- C ABI of liblanczosnet_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the LanczosNet spectral-convolution forward path of
+ * lrjconan/LanczosNetwork.  Conventions follow the reference's own native interface
+ * (operators/src/cuda/segment_reduction.h:8-12): the CUDA stream comes first, inputs are
+ * const device pointers to contiguous row-major buffers, dimensions are plain ints,
+ * outputs come last.  Differences, on purpose:
+ *   - every entry point returns an int status (0 = ok, <0 = argument error, >0 = cudaError_t)
+ *     instead of calling exit(-1) on a launch failure (segment_reduction.cu:28-36);
+ *   - the library owns no tensor memory and never synchronises; workspace is caller-provided;
+ *   - no global mutable state besides a thread-local error string (re-entrant under
+ *     nn.DataParallel's one-thread-per-device execution, runner/qm8_runner.py:291-292).
+ *
+ * All pointers are DEVICE pointers unless stated otherwise.  There is no CPU fallback.
+ */
+#ifndef LANCZOSNET_B200_H_
+#define LANCZOSNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lnb_stream_t; /* cudaStream_t */
+
+#define LNB_OK 0
+#define LNB_ERR_ARG (-1)
+#define LNB_ERR_UNSUPPORTED (-2)
+
+/* ABI version (bumped on any signature change) and last error text of the calling thread. */
+int lnb_abi_version(void);
+const char* lnb_last_error(void);
+/* Number of kernels this library has launched from the calling thread (bench.py's
+ * gpu_launches evidence). */
+int64_t lnb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * operators/segment_reduction  (replaces operators/src/cuda/segment_reduction.h:8-12 and the
+ * four python-visible names of operators/src/segment_reduction{,_cuda}.h:1-6)
+ * data [B, dim1, dim2] fp32, segment_ids [B, dim1] int64, output [B, num_segments, dim2].
+ * forward:  output[b, ids[b,c], :] += data[b, c, :]       (output pre-zeroed by the caller,
+ *                                                          operators/functions/unsorted_segment_sum.py:20-27)
+ * backward: grad_data[b, c, :] = grad_output[b, ids[b,c], :]
+ * data_shape = host pointer to {B, dim1, dim2} like the reference launcher.
+ * ------------------------------------------------------------------------------------- */
+int lnb_unsorted_segment_sum_forward(lnb_stream_t stream, const float* data,
+                                     const int64_t* segment_ids, const int* data_shape,
+                                     int num_segments, float* output);
+int lnb_unsorted_segment_sum_backward(lnb_stream_t stream, const float* grad_output,
+                                      const int64_t* segment_ids, const int* data_shape,
+                                      int num_segments, float* grad_data);
+
+/* ---------------------------------------------------------------------------------------
+ * Generic strided batched fp32 GEMM   C[b,z] = act( (A[b,z] * kscale[b,z]) @ B[b,z] + bias )
+ * (the torch.bmm / nn.Linear call sites of model/lanczos_net.py:112-121,167-181).
+ * Strides are in elements.  kscale (optional) multiplies column k of A; bias (optional) has
+ * N entries; relu != 0 applies max(.,0).  CUDA-core FFMA path for arbitrary shapes/strides.
+ * ------------------------------------------------------------------------------------- */
+typedef struct lnb_gemm_desc {
+  const float* A; int64_t a_sb, a_sz, a_sm, a_sk;
+  const float* B; int64_t b_sb, b_sz, b_sk, b_sn;
+  float* C;       int64_t c_sb, c_sz, c_sm, c_sn;
+  const float* kscale; int64_t s_sb, s_sz, s_sk;
+  const float* bias; int64_t bias_sz;   /* bias[z*bias_sz + n] */
+  int32_t batch, nz, M, N, K, relu;
+} lnb_gemm_desc;
+int lnb_batched_gemm(lnb_stream_t stream, const lnb_gemm_desc* desc /* host */);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense layer on 5th-gen tensor cores:  C[M,N] = act(A[M,K] @ W[N,K]^T + bias)
+ * (nn.Linear of model/lanczos_net.py:181 and the 4096-wide MLP of ada_lanczos_net.py:54-63).
+ * fp32 in/out; computed as 3xTF32 split products (hi*hi + hi*lo + lo*hi) with fp32 TMEM
+ * accumulation -> fp32-grade accuracy.  W_hi / W_lo are the tf32 split of W produced once by
+ * lnb_split_tf32.  Requirements: K % 32 == 0, N % 16 == 0 (N <= 256 per tile column block).
+ * ------------------------------------------------------------------------------------- */
+int lnb_split_tf32(lnb_stream_t stream, const float* x, int64_t n, float* hi, float* lo);
+int lnb_linear_tf32x3(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
+                      const float* bias, int M, int N, int K, int relu, float* C);
+
+/* ---------------------------------------------------------------------------------------
+ * Embedding rows (model/lanczos_net.py:154): out[r, :] = table[idx[r], :].
+ * ------------------------------------------------------------------------------------- */
+int lnb_embedding_rows(lnb_stream_t stream, const int64_t* idx, const float* table,
+                       int64_t rows, int num_embeddings, int dim, float* out);
+
+/* ---------------------------------------------------------------------------------------
+ * Ritz-value power table (model/lanczos_net.py:146-149): table[b,k,s] = D[b,k] ** powers[s],
+ * correctly rounded from a double-precision pow.  The per-layer filter MLP
+ * (model/lanczos_net.py:109-113) is then four lnb_batched_gemm / lnb_linear_tf32x3 calls over
+ * the B*K rows, batched over all layers at once because the input does not depend on the
+ * layer state.  powers: host pointer to S ints (S <= 32).
+ * ------------------------------------------------------------------------------------- */
+int lnb_ritz_power_table(lnb_stream_t stream, const float* D, int64_t rows, const int* powers,
+                         int S, float* table /* [rows, S] */);
+
+/* ---------------------------------------------------------------------------------------
+ * Readout (model/lanczos_net.py:185-194, ada_lanczos_net.py:350-361):
+ *   y[b,n,:] = (W_out state[b,n,:] + b_out) * sigmoid(w_att . state[b,n,:] + b_att)
+ *   score[b,:] = mean over n with mask[b,n] != 0 (mask == NULL -> all n)
+ * ------------------------------------------------------------------------------------- */
+int lnb_readout(lnb_stream_t stream, const float* state, const float* W_out, const float* b_out,
+                const float* w_att, const float* b_att, const uint8_t* mask, int B, int N, int H,
+                int P, float* score /* [B,P] */);
+
+/* ---------------------------------------------------------------------------------------
+ * Gaussian-kernel graph Laplacian (model/ada_lanczos_net.py:101-137, adjacency from :310-311):
+ *   adj = (L[b,i,j,0] != 0);  dist2 = |x_i - x_j|^2;  sigma2 = mean over all N^2 pairs;
+ *   A = exp(-dist2/sigma2) * adj;  d = (rowsum + [rowsum==0])^-1/2;  out = d_i A_ij d_j
+ * L has E1 channels innermost (dataset/qm8.py:262); only channel 0 is read.
+ * ------------------------------------------------------------------------------------- */
+int lnb_gaussian_laplacian(lnb_stream_t stream, const float* x, const float* L, int B, int N,
+                           int Dx, int E1, float* out /* [B,N,N] */);
+
+/* ---------------------------------------------------------------------------------------
+ * Batched K-step Lanczos tridiagonalisation with full double re-orthogonalisation and the
+ * reference's masking rules (model/ada_lanczos_net.py:139-247).  q1 is the raw start vector
+ * (the randn draw of :161); mask (uint8, may be NULL) zeroes padded nodes.
+ * Outputs: T [B,K,K] dense tridiagonal, Q [B,N,K], alpha [B,K], beta [B,K] (beta[b,K-1]=0),
+ * idx [B] int32 = number of retained Krylov directions (:208-211).
+ * ------------------------------------------------------------------------------------- */
+int lnb_lanczos_tridiag(lnb_stream_t stream, const float* A, const uint8_t* mask, const float* q1,
+                        int B, int N, int K, float* T, float* Q, float* alpha, float* beta,
+                        int32_t* idx);
+
+/* ---------------------------------------------------------------------------------------
+ * Ritz pairs of the Lanczos tridiagonal: implicit-shift QL on (alpha, beta) with the
+ * rotations applied to Q, so ritz_vec = Q S directly.  Ordered by descending |theta|
+ * (the reference's Ritz ordering, utils/data_helper.py:217-223); ties keep ascending index.
+ * status[b] = 0 ok, >0 = QL sweeps exhausted on that graph.
+ * ------------------------------------------------------------------------------------- */
+int lnb_tridiag_ritz(lnb_stream_t stream, const float* alpha, const float* beta, const float* Q,
+                     int B, int N, int K, float* theta /* [B,K] */, float* ritz_vec /* [B,N,K] */,
+                     int32_t* status /* [B] */);
+
+/* ---------------------------------------------------------------------------------------
+ * Powers of the tridiagonal for the learned filter (model/ada_lanczos_net.py:262-274):
+ *   out[b, r, s, c] = (T_b ** powers[s])[r, c]    (the MLP input layout r*S*K + s*K + c)
+ * powers: host pointer to S strictly increasing positive ints.
+ * ------------------------------------------------------------------------------------- */
+int lnb_tridiag_powers(lnb_stream_t stream, const float* T, int B, int K, const int* powers, int S,
+                       float* out /* [B,K,S,K] */);
+
+/* Symmetrised filter blocks (model/ada_lanczos_net.py:275-278):
+ *   G[b,s,r,c] = 0.5 * (Y[b, r*K*S + c*S + s] + Y[b, c*K*S + r*S + s])                     */
+int lnb_symmetrize_filters(lnb_stream_t stream, const float* Y, int B, int K, int S,
+                           float* G /* [B,S,K,K] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANCZOSNET_B200_H_ */

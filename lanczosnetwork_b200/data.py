@@ -1,0 +1,185 @@
+"""Host-side graph preparation for the hot path (numpy; no torch, no CUDA).
+
+Mirrors the parts of the reference that *feed* the spectral-convolution forward:
+
+  * ``get_laplacian(adj, 'L4')``      utils/data_helper.py:119-166 (L4 branch :155-156,
+                                      normalisation :92-116)
+  * ``get_graph_laplacian_eigs``      utils/data_helper.py:169-226 (dense eigh branch,
+                                      -|lambda| stable ordering :217-223)
+  * ``prepare_graph``                 dataset/get_qm8_data.py:60-90 / get_graph_data.py:52-92
+  * ``collate``                       dataset/qm8.py:57-90,220-291 (default branch)
+  * synthetic generators              dataset/get_graph_data.py:15-49 (G(n,p) regression set)
+                                      and a QM8-shaped molecule sampler
+
+All arithmetic follows the reference's fp64-then-cast-to-fp32 convention so the padded
+batch tensors are bit-identical to what the reference loader would hand the model.
+"""
+import numpy as np
+
+__all__ = [
+    'check_dist', 'get_laplacian', 'get_graph_laplacian_eigs', 'prepare_graph',
+    'collate', 'synthetic_molecule', 'synthetic_qm8_batch', 'synthetic_regression_graphs',
+]
+
+EPS = float(np.finfo(np.float32).eps)
+
+
+def check_dist(dist):
+  """utils/data_helper.py:9-14: diffusion distances must be ints or the string 'inf'."""
+  for dd in dist:
+    if not isinstance(dd, int) and dd != 'inf':
+      raise ValueError("Non-supported value of diffusion distance")
+  return dist
+
+
+def _normalize_sym(mat, exponent=0.5):
+  deg = mat.sum(axis=1)
+  with np.errstate(divide='ignore'):
+    scale = np.power(deg, -exponent)
+  scale[np.isinf(scale)] = 0.0
+  # same rounding as diag(s) @ M @ diag(s): fl(fl(s_i * m_ij) * s_j)
+  return (scale[:, None] * mat) * scale[None, :]
+
+
+def get_laplacian(adj, graph_laplacian_type='L4', alpha=0.5):
+  """Dense graph operators of utils/data_helper.py:119-166.  The hot path only consumes
+  'L4' (GCN renormalisation); L1/L2/L6 are provided because the same file defines them."""
+  adj = np.asarray(adj)
+  if not np.issubdtype(adj.dtype, np.floating):
+    adj = adj.astype(np.float64)
+  # NB: like the reference, arithmetic stays in the adjacency's dtype (the shipped
+  # preprocessors feed float64; eye() promotes the L4 / L2 sums to float64 either way)
+  if adj.ndim != 2 or adj.shape[0] != adj.shape[1]:
+    raise ValueError('adjacency must be square')
+  eye = np.eye(adj.shape[0])
+  if graph_laplacian_type == 'L1':
+    return np.diag(adj.sum(axis=1)) - adj
+  if graph_laplacian_type == 'L2':
+    return eye - _normalize_sym(adj)
+  if graph_laplacian_type == 'L4':
+    return _normalize_sym(eye + adj)
+  if graph_laplacian_type == 'L6':
+    return _normalize_sym(adj, exponent=alpha)
+  raise ValueError('Unsupported Graph Laplacian!')
+
+
+def get_graph_laplacian_eigs(adj, k=100, graph_laplacian_type='L4'):
+  """(eigs[:k], V[:, :k], L) with eigenpairs ordered by descending |lambda| (stable), the
+  dense-eigh branch of utils/data_helper.py:169-226."""
+  lap = get_laplacian(adj, graph_laplacian_type)
+  vals, vecs = np.linalg.eigh(lap)
+  order = np.argsort(-np.abs(vals), kind='mergesort')[:k]
+  return vals[order], vecs[:, order], lap
+
+
+def prepare_graph(adjs, node_feat, label=None):
+  """Per-graph record with the keys the collate step reads."""
+  adjs = np.asarray(adjs, dtype=np.float64)
+  if adjs.ndim == 2:
+    adjs = adjs[:, :, None]
+  D, V, L4 = get_graph_laplacian_eigs(adjs.sum(axis=2))
+  L_multi = np.stack([get_laplacian(adjs[:, :, e]) for e in range(adjs.shape[2])], axis=2)
+  rec = {'node_feat': np.asarray(node_feat), 'L_multi': L_multi, 'L_simple_4': L4,
+         'D_simple': D, 'V_simple': V}
+  if label is not None:
+    rec['label'] = np.asarray(label)
+  return rec
+
+
+def collate(samples, num_eigs):
+  """Zero-pad a list of ``prepare_graph`` records to the batch-max node count.
+
+  Returns numpy arrays: node_feat (B,N) int64 or (B,N,D) float32, node_mask (B,N) uint8,
+  L (B,N,N,E+1) float32 with channel 0 the simple-graph operator, D (B,K), V (B,N,K)."""
+  sizes = np.array([s['L_simple_4'].shape[0] for s in samples])
+  B, N = len(samples), int(sizes.max())
+  E = samples[0]['L_multi'].shape[2]
+  nf0 = np.asarray(samples[0]['node_feat'])
+  node_feat = (np.zeros((B, N), np.int64) if nf0.ndim == 1
+               else np.zeros((B, N, nf0.shape[1]), np.float32))
+  mask = (np.arange(N)[None, :] < sizes[:, None]).astype(np.uint8)
+  L = np.zeros((B, N, N, E + 1), np.float32)
+  D = np.zeros((B, num_eigs), np.float32)
+  V = np.zeros((B, N, num_eigs), np.float32)
+  for b, s in enumerate(samples):
+    n = int(sizes[b])
+    node_feat[b, :n] = s['node_feat']
+    L[b, :n, :n, 0] = s['L_simple_4']
+    L[b, :n, :n, 1:] = s['L_multi']
+    kk = min(num_eigs, s['D_simple'].shape[0])
+    D[b, :kk] = s['D_simple'][:kk]
+    V[b, :n, :kk] = s['V_simple'][:, :kk]
+  out = {'node_feat': node_feat, 'node_mask': mask, 'L': L, 'D': D, 'V': V}
+  if 'label' in samples[0]:
+    out['label'] = np.concatenate([np.asarray(s['label'], np.float32).reshape(1, -1)
+                                   for s in samples], axis=0)
+  return out
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs (no dataset can be downloaded; shapes follow the reference)
+# ----------------------------------------------------------------------------
+def synthetic_molecule(rng, num_nodes, num_bond_type=6, num_atom=70, max_degree=4,
+                       extra_edge_frac=0.3):
+  """Random connected, degree-capped, molecule-like multigraph.
+
+  A random spanning tree (each new atom bonds to a random earlier atom with free valence)
+  plus ~extra_edge_frac*n ring-closing bonds; every bond gets one of num_bond_type channels.
+  Returns (node_feat (n,) int64 in [0,num_atom), adjs (n,n,num_bond_type) float64)."""
+  n = int(num_nodes)
+  adjs = np.zeros((n, n, num_bond_type), np.float64)
+  deg = np.zeros(n, np.int64)
+  for v in range(1, n):
+    free = np.flatnonzero(deg[:v] < max_degree)
+    u = int(free[rng.randint(len(free))]) if len(free) else int(rng.randint(v))
+    c = int(rng.randint(num_bond_type))
+    adjs[u, v, c] = adjs[v, u, c] = 1.0
+    deg[u] += 1
+    deg[v] += 1
+  for _ in range(int(round(extra_edge_frac * n))):
+    u, v = int(rng.randint(n)), int(rng.randint(n))
+    if u == v or adjs[u, v].sum() > 0 or deg[u] >= max_degree or deg[v] >= max_degree:
+      continue
+    c = int(rng.randint(num_bond_type))
+    adjs[u, v, c] = adjs[v, u, c] = 1.0
+    deg[u] += 1
+    deg[v] += 1
+  node_feat = rng.randint(0, num_atom, size=n).astype(np.int64)
+  return node_feat, adjs
+
+
+def synthetic_qm8_sizes(rng, batch_size, min_nodes=3, max_nodes=26, mean_nodes=16.0):
+  sizes = np.clip(np.rint(rng.normal(mean_nodes, 4.5, size=batch_size)), min_nodes,
+                  max_nodes).astype(np.int64)
+  sizes[rng.randint(batch_size)] = max_nodes      # batch-max padding target N = max_nodes
+  return sizes
+
+
+def synthetic_qm8_batch(batch_size, seed=1234, num_eigs=20, num_bond_type=6, num_atom=70,
+                        num_label=16, max_nodes=26):
+  """QM8-shaped padded batch: n_b in [3,26], mean ~16."""
+  rng = np.random.RandomState(seed)
+  sizes = synthetic_qm8_sizes(rng, batch_size, max_nodes=max_nodes)
+  samples = []
+  for n in sizes:
+    nf, adjs = synthetic_molecule(rng, n, num_bond_type, num_atom)
+    samples.append(prepare_graph(adjs, nf, label=rng.randn(1, num_label)))
+  return collate(samples, num_eigs)
+
+
+def synthetic_regression_graphs(num_graphs=16, seed=123, min_num_nodes=20, max_num_nodes=100,
+                                node_emb_dim=10, graph_emb_dim=2, edge_prob=0.5):
+  """The reference's synthetic graph-regression set (dataset/get_graph_data.py:15-49):
+  X ~ randn(n,10), A = G(n, 0.5) with one edge type, Y ~ randn(1,2).  Same RNG call order
+  as the reference so identical seeds give identical graphs."""
+  import networkx as nx
+  rng = np.random.RandomState(seed)
+  sizes = rng.randint(min_num_nodes, high=max_num_nodes + 1, size=num_graphs)
+  out = []
+  for n in sizes:
+    X = rng.randn(n, node_emb_dim)
+    g = nx.fast_gnp_random_graph(int(n), edge_prob, seed=int(rng.randint(1000)))
+    A = np.asarray(nx.to_numpy_array(g), dtype=np.float64)[:, :, None]
+    Y = rng.randn(1, graph_emb_dim)
+    out.append(prepare_graph(A, X, label=Y))
+  return out

@@ -1,0 +1,73 @@
+"""Install the B200 drop-ins into an UNMODIFIED checkout of lrjconan/LanczosNetwork.
+
+    python -m lanczosnetwork_b200.dropin /path/to/LanczosNetwork -c config/qm8_lanczos_net.yaml -t
+
+What it does:
+  1. registers ``operators._ext`` / ``operators._ext.segment_reduction`` in ``sys.modules`` so
+     ``from model import *`` of the reference works without building its THC-era extension
+     (model/mpnn.py:6 -> operators/functions/unsorted_segment_sum.py:5);
+  2. rebinds ``LanczosNet`` / ``AdaLanczosNet`` / ``LanczosNetGeneral`` inside the runner
+     modules' globals, because the runners resolve the class with ``eval(name)`` in their own
+     namespace (runner/qm8_runner.py:59,288; runner/graph_runner.py:57,285);
+  3. runs the reference ``run_exp.main()`` unchanged.
+"""
+import importlib
+import os
+import sys
+
+from . import model as _models
+from .operators import _ext as _ext_pkg
+
+DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral')
+
+
+def register_native_op():
+  """Make ``operators._ext.segment_reduction`` importable under the reference's module path."""
+  sys.modules.setdefault('operators._ext', _ext_pkg)
+  sys.modules.setdefault('operators._ext.segment_reduction', _ext_pkg.segment_reduction)
+  ops_pkg = sys.modules.get('operators')
+  if ops_pkg is not None:
+    setattr(ops_pkg, '_ext', _ext_pkg)
+
+
+def patch_namespace(module):
+  """Rebind the three class names in ``module``'s globals to the B200 drop-ins."""
+  for name in DROPIN_CLASSES:
+    if hasattr(module, name):
+      setattr(module, name, getattr(_models, name))
+  return module
+
+
+def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.graph_runner')):
+  """Returns the list of patched modules.  ``reference_root`` is put on sys.path if given."""
+  if reference_root is not None:
+    reference_root = os.path.abspath(reference_root)
+    if reference_root not in sys.path:
+      sys.path.insert(0, reference_root)
+  register_native_op()
+  patched = []
+  ref_model = importlib.import_module('model')
+  patched.append(patch_namespace(ref_model))
+  for name in runner_modules:
+    try:
+      mod = importlib.import_module(name)
+    except ImportError:      # e.g. tensorboardX absent: that runner cannot be used anyway
+      continue
+    patched.append(patch_namespace(mod))
+  return patched
+
+
+def main(argv=None):
+  argv = list(sys.argv[1:] if argv is None else argv)
+  if not argv:
+    raise SystemExit(__doc__)
+  root = argv.pop(0)
+  install(root)
+  os.chdir(root)
+  sys.argv = ['run_exp.py'] + argv
+  run_exp = importlib.import_module('run_exp')
+  run_exp.main()
+
+
+if __name__ == '__main__':
+  main()

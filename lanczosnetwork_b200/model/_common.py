@@ -1,0 +1,130 @@
+"""Shared host-side scaffolding of the three drop-in modules.
+
+Parameter containers, names and initialisation mirror the reference so its checkpoints load
+unchanged (model/lanczos_net.py:15-93, utils/train_helper.py:14-32): ``embedding.weight``,
+``filter.{i}.{weight,bias}``, ``spectral_filter.{l}.{0,2,4,6}.{weight,bias}``,
+``att_func.0.{weight,bias}``.  The forward math lives in CUDA (lanczosnetwork_b200.ops).
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..data import check_dist
+from ..spectral_conv import WeightCache
+
+
+def _opt(obj, name, default):
+  return getattr(obj, name) if hasattr(obj, name) else default
+
+
+class SpectralNetBase(nn.Module):
+  """Common constructor pieces; subclasses define the embedding and the long-scale operator."""
+
+  def _setup_common(self, config, num_edgetype, filter_mlp_in, filter_mlp_hidden):
+    m = config.model
+    self.config = config
+    self.input_dim = m.input_dim
+    self.hidden_dim = m.hidden_dim
+    self.output_dim = m.output_dim
+    self.num_layer = m.num_layer
+    self.num_edgetype = num_edgetype
+    self.dropout = _opt(m, 'dropout', 0.0)
+    self.short_diffusion_dist = check_dist(m.short_diffusion_dist)
+    self.long_diffusion_dist = check_dist(m.long_diffusion_dist)
+    self.max_short_diffusion_dist = max(self.short_diffusion_dist) if self.short_diffusion_dist else None
+    self.max_long_diffusion_dist = max(self.long_diffusion_dist) if self.long_diffusion_dist else None
+    self.num_scale_short = len(self.short_diffusion_dist)
+    self.num_scale_long = len(self.long_diffusion_dist)
+    self.num_eig_vec = m.num_eig_vec
+    self.spectral_filter_kind = m.spectral_filter_kind
+    self._filter_mlp_dims = (filter_mlp_in, filter_mlp_hidden)
+    self._wcache = WeightCache()
+
+  def _build_layers(self):
+    C = self.num_scale_short + self.num_scale_long + self.num_edgetype + 1
+    dims = [self.input_dim] + list(self.hidden_dim) + [self.output_dim]
+    self.filter = nn.ModuleList(
+        [nn.Linear(dims[t] * C, dims[t + 1]) for t in range(self.num_layer)] +
+        [nn.Linear(dims[-2], dims[-1])])
+    return dims
+
+  def _build_spectral_filter(self):
+    if self.spectral_filter_kind == 'MLP' and self.num_scale_long > 0:
+      n_in, hid = self._filter_mlp_dims
+      self.spectral_filter = nn.ModuleList([
+          nn.Sequential(nn.Linear(n_in, hid), nn.ReLU(), nn.Linear(hid, hid), nn.ReLU(),
+                        nn.Linear(hid, hid), nn.ReLU(), nn.Linear(hid, n_in))
+          for _ in range(self.num_layer)
+      ])
+
+  def _build_head(self, dims):
+    self.att_func = nn.Sequential(nn.Linear(dims[-2], 1), nn.Sigmoid())
+    loss = self.config.model.loss
+    if loss == 'CrossEntropy':
+      self.loss_func = torch.nn.CrossEntropyLoss()
+    elif loss == 'MSE':
+      self.loss_func = torch.nn.MSELoss()
+    elif loss == 'L1':
+      self.loss_func = torch.nn.L1Loss()
+    else:
+      raise ValueError("Non-supported loss function!")
+
+  def _init_param(self):
+    """Xavier-uniform weights, zero biases for filter / att_func / spectral_filter Linears
+    (model/lanczos_net.py:74-93); the embedding keeps nn.Embedding's default N(0,1)."""
+    groups = [self.filter, self.att_func]
+    if hasattr(self, 'spectral_filter'):
+      groups += list(self.spectral_filter)
+    for grp in groups:
+      for mod in grp:
+        if isinstance(mod, nn.Linear):
+          nn.init.xavier_uniform_(mod.weight.data)
+          if mod.bias is not None:
+            mod.bias.data.zero_()
+
+  # ------------------------------------------------------------------------------------------
+  def _device(self):
+    dev = self.filter[0].weight.device
+    if dev.type != 'cuda':
+      raise RuntimeError(
+          '%s runs on CUDA (sm_100a) only -- move the module with .cuda(); there is no CPU '
+          'fallback (the CPU reference is the oracle).' % type(self).__name__)
+    return dev
+
+  def _check_mode(self):
+    if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+      raise NotImplementedError(
+          '%s is forward-only in this build: call it under torch.no_grad() (as '
+          'runner.test() / the validation loop do). The backward of the fused ops is the '
+          'next scope row (SURVEY.md 8f1).' % type(self).__name__)
+    if self.training and self.dropout > 0.0:
+      raise NotImplementedError('dropout > 0 in training mode is not supported (forward-only)')
+
+  @staticmethod
+  def _to(dev, t, dtype=None):
+    if t is None:
+      return None
+    if t.device != dev:
+      t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+      t = t.to(dtype)
+    return t
+
+  def _filter_mlp_params(self):
+    if not hasattr(self, 'spectral_filter'):
+      return None
+    out = []
+    for l, seq in enumerate(self.spectral_filter):
+      out.append([('spectral_filter.%d.%d' % (l, i), seq[i].weight, seq[i].bias)
+                  for i in (0, 2, 4, 6)])
+    return out
+
+  def _readout(self, state, mask):
+    head = self.filter[self.num_layer]
+    att = self.att_func[0]
+    return ops.readout(state, head.weight, head.bias, att.weight.reshape(-1), att.bias, mask)
+
+  def _finish(self, score, label):
+    if label is not None:
+      return score, self.loss_func(score, label)
+    return score

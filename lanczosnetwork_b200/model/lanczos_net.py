@@ -1,0 +1,58 @@
+"""Drop-in for the reference ``model.LanczosNet`` (model/lanczos_net.py:13-199): same
+constructor, parameter names and ``forward(node_feat, L, D, V, label=None, mask=None)``;
+the forward runs in hand-written sm_100a CUDA (no CPU path)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..spectral_conv import graph_conv_layer, ritz_filter_coefficients
+from ._common import SpectralNetBase
+
+__all__ = ['LanczosNet']
+
+
+class LanczosNet(SpectralNetBase):
+
+  def __init__(self, config):
+    super(LanczosNet, self).__init__()
+    self.num_atom = config.dataset.num_atom
+    self._setup_common(config, config.dataset.num_bond_type,
+                       len(config.model.long_diffusion_dist), 128)
+    dims = self._build_layers()
+    self.embedding = nn.Embedding(self.num_atom, self.input_dim)
+    self._build_spectral_filter()
+    self._build_head(dims)
+    self._init_param()
+
+  def _initial_state(self, node_feat, dev):
+    return ops.embedding_rows(self._to(dev, node_feat).long(), self.embedding.weight)
+
+  def forward(self, node_feat, L, D, V, label=None, mask=None):
+    """
+      node_feat: long B x N (atom ids); L: float B x N x N x (E+1); D: Ritz values B x K;
+      V: Ritz vectors B x N x K; label: B x P; mask: B x N (uint8 / bool / float).
+      Returns score (B x P) or (score, loss) when label is given.
+    """
+    self._check_mode()
+    dev = self._device()
+    L = self._to(dev, L, torch.float32).contiguous()
+    D = self._to(dev, D, torch.float32).contiguous()
+    V = self._to(dev, V, torch.float32).contiguous()
+    mask = self._to(dev, mask)
+    label = self._to(dev, label)
+    state = self._initial_state(node_feat, dev)
+
+    coeffs = table = None
+    if self.num_scale_long > 0:
+      mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
+      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache)
+
+    for tt in range(self.num_layer):
+      coeff = None
+      if self.num_scale_long > 0:
+        coeff = coeffs[tt] if coeffs is not None else table
+      state = graph_conv_layer(state, L, V, coeff, False, self.short_diffusion_dist,
+                               self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
+                               self._wcache, 'filter.%d' % tt)
+    score = self._readout(state, mask)
+    return self._finish(score, label)

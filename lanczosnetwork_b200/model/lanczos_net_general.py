@@ -1,0 +1,54 @@
+"""Drop-in for the reference ``model.LanczosNetGeneral`` (model/lanczos_net_general.py:13-201):
+LanczosNet with float node features instead of an atom embedding (:156) and the edge-type
+count taken from ``config.dataset.num_edge_type`` (:24)."""
+import torch
+
+from ..spectral_conv import graph_conv_layer, ritz_filter_coefficients
+from ._common import SpectralNetBase
+
+__all__ = ['LanczosNetGeneral']
+
+
+class LanczosNetGeneral(SpectralNetBase):
+
+  def __init__(self, config):
+    super(LanczosNetGeneral, self).__init__()
+    self.node_emb_dim = config.dataset.node_emb_dim
+    self.graph_emb_dim = config.dataset.graph_emb_dim
+    self._setup_common(config, config.dataset.num_edge_type,
+                       len(config.model.long_diffusion_dist), 128)
+    dims = self._build_layers()
+    assert self.input_dim == self.node_emb_dim      # lanczos_net_general.py:45-46
+    assert self.output_dim == self.graph_emb_dim
+    self._build_spectral_filter()
+    self._build_head(dims)
+    self._init_param()
+
+  def forward(self, node_feat, L, D, V, label=None, mask=None):
+    """
+      node_feat: float B x N x D node features; L: B x N x N x (E+1); D: Ritz values B x K;
+      V: Ritz vectors B x N x K; label: B x P; mask: B x N.
+    """
+    self._check_mode()
+    dev = self._device()
+    L = self._to(dev, L, torch.float32).contiguous()
+    D = self._to(dev, D, torch.float32).contiguous()
+    V = self._to(dev, V, torch.float32).contiguous()
+    mask = self._to(dev, mask)
+    label = self._to(dev, label)
+    state = self._to(dev, node_feat, torch.float32).contiguous()
+
+    coeffs = table = None
+    if self.num_scale_long > 0:
+      mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
+      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache)
+
+    for tt in range(self.num_layer):
+      coeff = None
+      if self.num_scale_long > 0:
+        coeff = coeffs[tt] if coeffs is not None else table
+      state = graph_conv_layer(state, L, V, coeff, False, self.short_diffusion_dist,
+                               self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
+                               self._wcache, 'filter.%d' % tt)
+    score = self._readout(state, mask)
+    return self._finish(score, label)

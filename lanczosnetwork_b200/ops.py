@@ -1,0 +1,241 @@
+"""torch-tensor front end of the C ABI (include/lanczosnet_b200.h).
+
+PyTorch is plumbing here: device memory, streams, dtype/contiguity checks.  All arithmetic
+runs in the hand-written CUDA kernels of liblanczosnet_b200.so.  Every function requires
+CUDA tensors and raises otherwise -- there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc
+
+__all__ = [
+    'bgemm', 'split_tf32', 'linear_tf32x3', 'embedding_rows', 'ritz_power_table', 'readout',
+    'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
+    'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
+]
+
+
+def _need_cuda(*tensors):
+  for t in tensors:
+    if t is None:
+      continue
+    if not t.is_cuda:
+      raise RuntimeError('lanczosnetwork_b200 ops run on CUDA (sm_100a) only; got a %s tensor. '
+                         'There is no CPU fallback.' % t.device)
+
+
+def _f32c(t):
+  if t.dtype != torch.float32:
+    t = t.float()
+  return t.contiguous()
+
+
+def _ptr(t):
+  return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(t):
+  return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ints(vals):
+  arr = (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+  return arr
+
+
+def launch_count():
+  return _lib.launch_count()
+
+
+# --------------------------------------------------------------------------------------------
+def bgemm(A, a_str, Bm, b_str, C, c_str, batch, nz, M, N, K, kscale=None, s_str=(0, 0, 0),
+          bias=None, bias_sz=0, relu=False, a_off=0, b_off=0, c_off=0):
+  """C[b,z] = act((A[b,z] * kscale[b,z]) @ B[b,z] + bias); strides in elements, *_off element
+  offsets into the (fp32, CUDA) storage of A / B / C."""
+  _need_cuda(A, Bm, C, kscale, bias)
+  lib = _lib.load()
+  d = GemmDesc()
+  d.A = A.data_ptr() + 4 * a_off
+  d.a_sb, d.a_sz, d.a_sm, d.a_sk = [int(v) for v in a_str]
+  d.B = Bm.data_ptr() + 4 * b_off
+  d.b_sb, d.b_sz, d.b_sk, d.b_sn = [int(v) for v in b_str]
+  d.C = C.data_ptr() + 4 * c_off
+  d.c_sb, d.c_sz, d.c_sm, d.c_sn = [int(v) for v in c_str]
+  d.kscale = kscale.data_ptr() if kscale is not None else None
+  d.s_sb, d.s_sz, d.s_sk = [int(v) for v in s_str]
+  d.bias = bias.data_ptr() if bias is not None else None
+  d.bias_sz = int(bias_sz)
+  d.batch, d.nz, d.M, d.N, d.K, d.relu = int(batch), int(nz), int(M), int(N), int(K), int(bool(relu))
+  with torch.cuda.device(C.device):
+    _lib.check(lib.lnb_batched_gemm(_stream(C), ctypes.byref(d)), 'lnb_batched_gemm')
+  return C
+
+
+def split_tf32(x):
+  """(hi, lo) tf32 split of an fp32 tensor: hi = rna_tf32(x), lo = rna_tf32(x - hi)."""
+  _need_cuda(x)
+  x = _f32c(x)
+  hi = torch.empty_like(x)
+  lo = torch.empty_like(x)
+  with torch.cuda.device(x.device):
+    _lib.check(_lib.load().lnb_split_tf32(_stream(x), _ptr(x), x.numel(), _ptr(hi), _ptr(lo)),
+               'lnb_split_tf32')
+  return hi, lo
+
+
+def linear_tf32x3(x, w_hi, w_lo, bias=None, relu=False, out=None):
+  """act(x @ W^T + bias) on tcgen05 tensor cores (3xTF32).  x [M,K], w_hi/w_lo [N,K]."""
+  _need_cuda(x, w_hi, w_lo, bias)
+  x = _f32c(x)
+  M, K = x.shape
+  N = w_hi.shape[0]
+  if out is None:
+    out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+  with torch.cuda.device(x.device):
+    _lib.check(_lib.load().lnb_linear_tf32x3(_stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo),
+                                             _ptr(bias), M, N, K, int(bool(relu)), _ptr(out)),
+               'lnb_linear_tf32x3')
+  return out
+
+
+def embedding_rows(idx, table):
+  _need_cuda(idx, table)
+  idx = idx.contiguous().long()
+  table = _f32c(table)
+  rows = idx.numel()
+  out = torch.empty(tuple(idx.shape) + (table.shape[1],), device=table.device, dtype=torch.float32)
+  with torch.cuda.device(table.device):
+    _lib.check(_lib.load().lnb_embedding_rows(_stream(table), _ptr(idx), _ptr(table), rows,
+                                              table.shape[0], table.shape[1], _ptr(out)),
+               'lnb_embedding_rows')
+  return out
+
+
+def ritz_power_table(D, powers):
+  """table[..., s] = D ** powers[s]  (model/lanczos_net.py:146-149)."""
+  _need_cuda(D)
+  D = _f32c(D)
+  S = len(powers)
+  out = torch.empty(tuple(D.shape) + (S,), device=D.device, dtype=torch.float32)
+  with torch.cuda.device(D.device):
+    _lib.check(_lib.load().lnb_ritz_power_table(_stream(D), _ptr(D), D.numel(), _ints(powers), S,
+                                                _ptr(out)), 'lnb_ritz_power_table')
+  return out
+
+
+def readout(state, W_out, b_out, w_att, b_att, mask=None):
+  _need_cuda(state, W_out, b_out, w_att, b_att, mask)
+  state = _f32c(state)
+  B, N, H = state.shape
+  P = W_out.shape[0]
+  if mask is not None:
+    mask = (mask != 0).to(torch.uint8).contiguous()
+  out = torch.empty((B, P), device=state.device, dtype=torch.float32)
+  with torch.cuda.device(state.device):
+    _lib.check(_lib.load().lnb_readout(_stream(state), _ptr(state), _ptr(_f32c(W_out)),
+                                       _ptr(_f32c(b_out)), _ptr(_f32c(w_att)), _ptr(_f32c(b_att)),
+                                       _ptr(mask), B, N, H, P, _ptr(out)), 'lnb_readout')
+  return out
+
+
+def gaussian_laplacian(x, L):
+  _need_cuda(x, L)
+  x, L = _f32c(x), _f32c(L)
+  B, N, Dx = x.shape
+  E1 = L.shape[3]
+  out = torch.empty((B, N, N), device=x.device, dtype=torch.float32)
+  with torch.cuda.device(x.device):
+    _lib.check(_lib.load().lnb_gaussian_laplacian(_stream(x), _ptr(x), _ptr(L), B, N, Dx, E1,
+                                                  _ptr(out)), 'lnb_gaussian_laplacian')
+  return out
+
+
+def lanczos_tridiag(A, mask, q1, K):
+  """Returns dict(T [B,K,K], Q [B,N,K], alpha [B,K], beta [B,K], idx [B] int32)."""
+  _need_cuda(A, mask, q1)
+  A = _f32c(A)
+  B, N = A.shape[0], A.shape[1]
+  q1 = _f32c(q1).reshape(B, N)
+  if mask is not None:
+    mask = (mask != 0).to(torch.uint8).contiguous()
+  dev = A.device
+  T = torch.empty((B, K, K), device=dev, dtype=torch.float32)
+  Q = torch.empty((B, N, K), device=dev, dtype=torch.float32)
+  alpha = torch.empty((B, K), device=dev, dtype=torch.float32)
+  beta = torch.empty((B, K), device=dev, dtype=torch.float32)
+  idx = torch.empty((B,), device=dev, dtype=torch.int32)
+  with torch.cuda.device(dev):
+    _lib.check(_lib.load().lnb_lanczos_tridiag(_stream(A), _ptr(A), _ptr(mask), _ptr(q1), B, N, K,
+                                               _ptr(T), _ptr(Q), _ptr(alpha), _ptr(beta),
+                                               _ptr(idx)), 'lnb_lanczos_tridiag')
+  return {'T': T, 'Q': Q, 'alpha': alpha, 'beta': beta, 'idx': idx}
+
+
+def tridiag_ritz(alpha, beta, Q):
+  """Ritz values (descending |theta|) and vectors V = Q S.  Returns (theta, V, status)."""
+  _need_cuda(alpha, beta, Q)
+  alpha, beta, Q = _f32c(alpha), _f32c(beta), _f32c(Q)
+  B, N, K = Q.shape
+  theta = torch.empty((B, K), device=Q.device, dtype=torch.float32)
+  V = torch.empty((B, N, K), device=Q.device, dtype=torch.float32)
+  status = torch.empty((B,), device=Q.device, dtype=torch.int32)
+  with torch.cuda.device(Q.device):
+    _lib.check(_lib.load().lnb_tridiag_ritz(_stream(Q), _ptr(alpha), _ptr(beta), _ptr(Q), B, N, K,
+                                            _ptr(theta), _ptr(V), _ptr(status)), 'lnb_tridiag_ritz')
+  return theta, V, status
+
+
+def tridiag_powers(T, powers):
+  """out[b, r, s, c] = (T_b ** powers[s])[r, c]  (MLP input layout of ada_lanczos_net.py:274)."""
+  _need_cuda(T)
+  T = _f32c(T)
+  B, K = T.shape[0], T.shape[1]
+  S = len(powers)
+  out = torch.empty((B, K, S, K), device=T.device, dtype=torch.float32)
+  with torch.cuda.device(T.device):
+    _lib.check(_lib.load().lnb_tridiag_powers(_stream(T), _ptr(T), B, K, _ints(powers), S,
+                                              _ptr(out)), 'lnb_tridiag_powers')
+  return out
+
+
+def symmetrize_filters(Y, K, S):
+  """G[b,s,r,c] = (Y[b,r,c,s] + Y[b,c,r,s]) / 2 for Y viewed as [B,K,K,S]."""
+  _need_cuda(Y)
+  Y = _f32c(Y)
+  B = Y.shape[0]
+  G = torch.empty((B, S, K, K), device=Y.device, dtype=torch.float32)
+  with torch.cuda.device(Y.device):
+    _lib.check(_lib.load().lnb_symmetrize_filters(_stream(Y), _ptr(Y), B, K, S, _ptr(G)),
+               'lnb_symmetrize_filters')
+  return G
+
+
+def segment_sum_forward(data, segment_index, num_segments, output=None):
+  _need_cuda(data, segment_index, output)
+  data = _f32c(data)
+  seg = segment_index.contiguous().long()
+  B, d1, d2 = data.shape
+  if output is None:
+    output = torch.zeros((B, num_segments, d2), device=data.device, dtype=torch.float32)
+  with torch.cuda.device(data.device):
+    _lib.check(_lib.load().lnb_unsorted_segment_sum_forward(
+        _stream(data), _ptr(data), _ptr(seg), _ints([B, d1, d2]), int(num_segments), _ptr(output)),
+               'lnb_unsorted_segment_sum_forward')
+  return output
+
+
+def segment_sum_backward(grad_output, segment_index, data_shape, grad_data=None):
+  _need_cuda(grad_output, segment_index, grad_data)
+  grad_output = _f32c(grad_output)
+  seg = segment_index.contiguous().long()
+  B, d1, d2 = [int(v) for v in data_shape]
+  if grad_data is None:
+    grad_data = torch.empty((B, d1, d2), device=grad_output.device, dtype=torch.float32)
+  with torch.cuda.device(grad_output.device):
+    _lib.check(_lib.load().lnb_unsorted_segment_sum_backward(
+        _stream(grad_output), _ptr(grad_output), _ptr(seg), _ints([B, d1, d2]),
+        int(grad_output.shape[1]), _ptr(grad_data)), 'lnb_unsorted_segment_sum_backward')
+  return grad_data

@@ -1,0 +1,139 @@
+"""Spectral graph-convolution forward built from the CUDA ops (shared by the three models).
+
+One layer (reference: model/lanczos_net.py:157-182, model/ada_lanczos_net.py:321-347):
+
+    msg = [ L0^k X  (k in short) ] ++ [ Q G_s Q^T X  (s in long) ] ++ [ L_e X  (e = 0..E) ]
+    X'  = ReLU( cat(msg) W^T + b )
+
+B200 mapping: the long-scale filters are applied in factored form Q (G_s (Q^T X)) -- the
+N x N filter matrices V diag(f) V^T of lanczos_net.py:114-123 are never materialised -- and the
+channel-innermost operator tensor L[B,N,N,E+1] is consumed in place through its element
+stride (no strided-slice copies).  Messages are written straight into their column block of
+the concatenated [B*N, C*D] buffer, which the tcgen05 3xTF32 dense kernel then multiplies by W.
+"""
+import torch
+
+from . import ops
+
+__all__ = ['WeightCache', 'dense', 'graph_conv_layer', 'ritz_filter_coefficients']
+
+
+class WeightCache(object):
+  """tf32 hi/lo splits of nn.Linear weights, refreshed when the parameter changes
+  (keyed on storage pointer + in-place version counter)."""
+
+  def __init__(self):
+    self._store = {}
+
+  def split(self, name, weight, pad_to=None):
+    key = (name, weight.device.index)
+    tag = (weight.data_ptr(), weight._version, pad_to)
+    hit = self._store.get(key)
+    if hit is None or hit[0] != tag:
+      w = weight.detach()
+      if pad_to is not None and pad_to != w.shape[1]:
+        w = torch.nn.functional.pad(w, (0, pad_to - w.shape[1]))   # zero input columns
+      hi, lo = ops.split_tf32(w)
+      hit = (tag, hi, lo)
+      self._store[key] = hit
+    return hit[1], hit[2]
+
+  def clear(self):
+    self._store.clear()
+
+
+def dense(x2d, weight, bias, relu, cache, name):
+  """act(x2d @ weight^T + bias).  tcgen05 3xTF32 kernel when rows are 16-byte multiples
+  (x2d may carry zero-padded trailing columns beyond weight.shape[1]), otherwise the generic
+  FFMA GEMM."""
+  M, K = x2d.shape
+  N = weight.shape[0]
+  if K % 4 == 0:
+    w_hi, w_lo = cache.split(name, weight, K)
+    return ops.linear_tf32x3(x2d, w_hi, w_lo, bias, relu)
+  assert K == weight.shape[1]
+  out = torch.empty((M, N), device=x2d.device, dtype=torch.float32)
+  w = weight.detach().contiguous()
+  ops.bgemm(x2d, (0, 0, K, 1), w, (0, 0, 1, K), out, (0, 0, N, 1), 1, 1, M, N, K,
+            bias=bias, relu=relu)
+  return out
+
+
+def ritz_filter_coefficients(D, powers, mlp_layers, cache):
+  """Per-layer multi-scale coefficients of the Ritz values (model/lanczos_net.py:109-113,
+  146-149).  The MLP input does not depend on the layer state, so the table of powers is
+  built once.  mlp_layers: list over layers of [(name,W,b) x 4] or None for the plain-power filter.
+  Returns list over layers of [B,K,S] tensors."""
+  B, K = D.shape
+  table = ops.ritz_power_table(D, powers)            # [B,K,S]
+  if mlp_layers is None:
+    return None, table
+  flat = table.reshape(B * K, len(powers))
+  out = []
+  for params in mlp_layers:
+    h = flat
+    for i, (name, w, b) in enumerate(params):
+      h = dense(h, w, b, i < len(params) - 1, cache, name)
+    out.append(h.reshape(B, K, len(powers)))
+  return out, table
+
+
+def graph_conv_layer(state, L, Qv, coeff, dense_filter, short_dist, num_long, weight, bias, cache,
+                     name):
+  """One spectral convolution layer.
+
+  state [B,N,Din]; L [B,N,N,E1] (channel innermost); Qv [B,N,K] Ritz / Lanczos vectors;
+  coeff: [B,K,S] diagonal filter coefficients (LanczosNet) when dense_filter is False,
+         [B,S,K,K] symmetric filter blocks (AdaLanczosNet) when True; None if num_long == 0.
+  Returns [B,N,H]."""
+  B, N, Din = state.shape
+  E1 = L.shape[3]
+  S = num_long
+  n_short = len(short_dist)
+  C = n_short + S + E1
+  CD = (C * Din + 3) // 4 * 4          # row stride padded to 16 bytes for the tensor-core path
+  dev = state.device
+  if CD != C * Din:
+    msg = torch.zeros((B, N, CD), device=dev, dtype=torch.float32)
+  else:
+    msg = torch.empty((B, N, CD), device=dev, dtype=torch.float32)
+  x_str = (N * Din, 0, Din, 1)
+  col = 0
+  # ---- short diffusion chain: walk <- L0 walk (lanczos_net.py:164-169) --------------------
+  if n_short:
+    l0_str = (N * N * E1, 0, N * E1, E1)
+    src, src_str, src_off = state, x_str, 0
+    tmp = None
+    for step in range(1, max(short_dist) + 1):
+      if step in short_dist:
+        dst, dst_str, dst_off = msg, (N * CD, 0, CD, 1), col * Din
+        col += 1
+      else:
+        tmp = torch.empty((B, N, Din), device=dev, dtype=torch.float32)
+        dst, dst_str, dst_off = tmp, x_str, 0
+      ops.bgemm(L, l0_str, src, src_str, dst, dst_str, B, 1, N, Din, N, b_off=src_off,
+                c_off=dst_off)
+      src, src_off = dst, dst_off
+      src_str = (dst_str[0], 0, dst_str[2], 1)
+  # ---- long diffusion: Q G_s (Q^T X) ------------------------------------------------------
+  if S:
+    K = Qv.shape[2]
+    U = torch.empty((B, K, Din), device=dev, dtype=torch.float32)
+    # U = Q^T X : A[m=k][kk=n] = Q[n*K + k]
+    ops.bgemm(Qv, (N * K, 0, 1, K), state, x_str, U, (K * Din, 0, Din, 1), B, 1, K, Din, N)
+    if dense_filter:
+      W = torch.empty((B, S, K, Din), device=dev, dtype=torch.float32)
+      ops.bgemm(coeff, (S * K * K, K * K, K, 1), U, (K * Din, 0, Din, 1), W,
+                (S * K * Din, K * Din, Din, 1), B, S, K, Din, K)
+      ops.bgemm(Qv, (N * K, 0, K, 1), W, (S * K * Din, K * Din, Din, 1), msg,
+                (N * CD, Din, CD, 1), B, S, N, Din, K, c_off=col * Din)
+    else:
+      ops.bgemm(Qv, (N * K, 0, K, 1), U, (K * Din, 0, Din, 1), msg, (N * CD, Din, CD, 1),
+                B, S, N, Din, K, kscale=coeff, s_str=(K * S, 1, S), c_off=col * Din)
+    col += S
+  # ---- edge types: L_e X (lanczos_net.py:177-178) -----------------------------------------
+  ops.bgemm(L, (N * N * E1, 1, N * E1, E1), state, x_str, msg, (N * CD, Din, CD, 1),
+            B, E1, N, Din, N, c_off=col * Din)
+  # ---- Linear + ReLU (lanczos_net.py:180-181) ---------------------------------------------
+  out = dense(msg.reshape(B * N, CD), weight, bias, True, cache, name)
+  return out.reshape(B, N, -1)

@@ -1,0 +1,276 @@
+"""Kernel-level parity tests: every C-ABI entry point against the CPU oracle / the committed
+reference outputs.  Run on the B200 box (``pytest -m gpu``)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+from oracle import lanczos_oracle as orc
+from oracle import segment_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+  return torch.device('cuda:0')
+
+
+def ops():
+  from lanczosnetwork_b200 import ops as _ops
+  return _ops
+
+
+# ------------------------------------------------------------------------------------------
+# operators/segment_reduction
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape,S', [((3, 7, 5), 4), ((2, 16, 8), 16), ((1, 1, 1), 1),
+                                     ((4, 33, 12), 9), ((0, 5, 4), 3)])
+def test_segment_sum_matches_oracle(shape, S):
+  rng = np.random.RandomState(sum(shape) + S)
+  data = rng.randn(*shape).astype(np.float32)
+  seg = rng.randint(0, S, size=shape[:2]).astype(np.int64)
+  out = ops().segment_sum_forward(torch.from_numpy(data).to(dev()), torch.from_numpy(seg).to(dev()), S)
+  ref = segment_oracle.segment_sum_forward(data, seg, S)
+  np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-6, atol=1e-6)   # fp32 atomics: order
+  gout = rng.randn(shape[0], S, shape[2]).astype(np.float32)
+  gd = ops().segment_sum_backward(torch.from_numpy(gout).to(dev()), torch.from_numpy(seg).to(dev()), shape)
+  assert np.array_equal(gd.cpu().numpy(), segment_oracle.segment_sum_backward(gout, seg, shape))
+
+
+def test_segment_sum_reference_flavours_agree_where_consistent():
+  """S == dim1 and ids shared across the batch: the reference CPU loop, its CUDA kernel and the
+  intended semantics coincide -- and so does ours."""
+  rng = np.random.RandomState(0)
+  B, C, X = 3, 6, 4
+  data = rng.randn(B, C, X).astype(np.float32)
+  seg = np.tile(rng.randint(0, C, size=(1, C)), (B, 1)).astype(np.int64)
+  a = segment_oracle.segment_sum_forward(data, seg, C, 'intended')
+  b = segment_oracle.segment_sum_forward(data, seg, C, 'ref_cuda')
+  c = segment_oracle.segment_sum_forward(data, seg, C, 'ref_cpu')
+  np.testing.assert_allclose(a, b, atol=1e-6)
+  np.testing.assert_allclose(a, c, atol=1e-6)
+  out = ops().segment_sum_forward(torch.from_numpy(data).to(dev()), torch.from_numpy(seg).to(dev()), C)
+  np.testing.assert_allclose(out.cpu().numpy(), a, atol=1e-6)
+
+
+def test_segment_sum_autograd_and_module():
+  from lanczosnetwork_b200.operators.modules import UnsortedSegmentSum
+  rng = np.random.RandomState(3)
+  data = torch.from_numpy(rng.randn(2, 9, 8).astype(np.float32)).to(dev()).requires_grad_(True)
+  seg = torch.from_numpy(rng.randint(0, 5, size=(2, 9))).to(dev())
+  out = UnsortedSegmentSum(5)(data, seg)
+  ref = torch.zeros(2, 5, 8, device=dev()).index_put_(
+      (torch.arange(2, device=dev())[:, None].expand(2, 9), seg), data.detach(), accumulate=True)
+  torch.testing.assert_close(out, ref, rtol=1e-6, atol=1e-6)
+  w = torch.from_numpy(rng.randn(2, 5, 8).astype(np.float32)).to(dev())
+  (out * w).sum().backward()
+  gref = w[torch.arange(2, device=dev())[:, None].expand(2, 9), seg]
+  assert torch.equal(data.grad, gref)
+
+
+def test_native_module_exports_reference_names():
+  from lanczosnetwork_b200.operators._ext import segment_reduction as sr
+  for name in ('unsorted_segment_sum_forward', 'unsorted_segment_sum_forward_gpu',
+               'unsorted_segment_sum_backward', 'unsorted_segment_sum_backward_gpu'):
+    assert callable(getattr(sr, name))
+  with pytest.raises(RuntimeError):
+    sr.unsorted_segment_sum_forward(torch.zeros(1, 2, 3), torch.zeros(1, 2, dtype=torch.long),
+                                    (1, 2, 3), torch.zeros(1, 2, 3))
+
+
+# ------------------------------------------------------------------------------------------
+# generic strided batched GEMM
+# ------------------------------------------------------------------------------------------
+def test_bgemm_strided_channel_innermost_and_transposed():
+  rng = np.random.RandomState(1)
+  B, N, E1, D, K = 5, 26, 7, 40, 20
+  L = torch.from_numpy(rng.randn(B, N, N, E1).astype(np.float32)).to(dev())
+  X = torch.from_numpy(rng.randn(B, N, D).astype(np.float32)).to(dev())
+  C = E1
+  msg = torch.zeros(B, N, C * D, device=dev())
+  ops().bgemm(L, (N * N * E1, 1, N * E1, E1), X, (N * D, 0, D, 1), msg, (N * C * D, D, C * D, 1),
+              B, E1, N, D, N)
+  ref = torch.cat([torch.bmm(L[..., e].double(), X.double()) for e in range(E1)], dim=2)
+  torch.testing.assert_close(msg.double(), ref, rtol=1e-5, atol=1e-5)
+  Q = torch.from_numpy(rng.randn(B, N, K).astype(np.float32)).to(dev())
+  U = torch.empty(B, K, D, device=dev())
+  ops().bgemm(Q, (N * K, 0, 1, K), X, (N * D, 0, D, 1), U, (K * D, 0, D, 1), B, 1, K, D, N)
+  torch.testing.assert_close(U.double(), torch.bmm(Q.transpose(1, 2).double(), X.double()),
+                             rtol=1e-5, atol=1e-5)
+  f = torch.from_numpy(rng.randn(B, K, 3).astype(np.float32)).to(dev())
+  out = torch.empty(B, 3, N, D, device=dev())
+  ops().bgemm(Q, (N * K, 0, K, 1), U, (K * D, 0, D, 1), out, (3 * N * D, N * D, D, 1), B, 3, N, D,
+              K, kscale=f, s_str=(K * 3, 1, 3))
+  ref = torch.einsum('bnk,bks,bkd->bsnd', Q.double(), f.double(), U.double())
+  torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (65, 63, 17), (130, 2, 100), (64, 64, 16)])
+def test_bgemm_bias_relu_edges(M, N, K):
+  rng = np.random.RandomState(M + N + K)
+  A = torch.from_numpy(rng.randn(M, K).astype(np.float32)).to(dev())
+  W = torch.from_numpy(rng.randn(N, K).astype(np.float32)).to(dev())
+  b = torch.from_numpy(rng.randn(N).astype(np.float32)).to(dev())
+  out = torch.empty(M, N, device=dev())
+  ops().bgemm(A, (0, 0, K, 1), W, (0, 0, 1, K), out, (0, 0, N, 1), 1, 1, M, N, K, bias=b, relu=True)
+  ref = torch.relu(A.double() @ W.double().t() + b.double())
+  torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 3xTF32 dense layer
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K,relu', [(128, 128, 32, False), (300, 128, 1920, True),
+                                        (26624, 128, 960, True), (1000, 2000, 512, False),
+                                        (77, 8, 128, False), (2048, 128, 8, True),
+                                        (64, 4096, 2000, True), (5, 40, 100, False)])
+def test_linear_tf32x3_fp32_grade(M, N, K, relu):
+  g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
+  x = torch.randn(M, K, generator=g).to(dev())
+  w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev())
+  b = torch.randn(N, generator=g).to(dev())
+  w_hi, w_lo = ops().split_tf32(w)
+  # the split is exact to ~2^-22 relative and hi is representable in tf32
+  assert torch.equal(w_hi.view(torch.int32) & 0x1FFF, torch.zeros_like(w_hi, dtype=torch.int32))
+  assert (w - (w_hi + w_lo)).abs().max() <= 2.0 ** -21 * w.abs().max()
+  out = ops().linear_tf32x3(x, w_hi, w_lo, b, relu)
+  ref = x.double() @ w.double().t() + b.double()
+  if relu:
+    ref = torch.relu(ref)
+  torch.backends.cuda.matmul.allow_tf32 = False
+  f32 = x @ w.t() + b
+  if relu:
+    f32 = torch.relu(f32)
+  err = (out.double() - ref).abs().max().item()
+  err32 = (f32.double() - ref).abs().max().item()
+  scale = ref.abs().max().item()
+  # stated tolerance: within 8x the error of a true fp32 GEMM, and < 2e-6 of the output scale
+  assert err <= max(8 * err32, 2e-6 * scale), (err, err32, scale)
+
+
+def test_linear_tf32x3_rejects_bad_k():
+  x = torch.randn(4, 10, device=dev())
+  w = torch.randn(8, 10, device=dev())
+  with pytest.raises(RuntimeError):
+    ops().linear_tf32x3(x, w, w, None, False)
+
+
+# ------------------------------------------------------------------------------------------
+# small graph ops
+# ------------------------------------------------------------------------------------------
+def test_embedding_power_table_readout():
+  rng = np.random.RandomState(2)
+  table = torch.from_numpy(rng.randn(70, 64).astype(np.float32))
+  idx = torch.from_numpy(rng.randint(0, 70, size=(9, 26)))
+  out = ops().embedding_rows(idx.to(dev()), table.to(dev()))
+  assert torch.equal(out.cpu(), table[idx])
+
+  D = torch.from_numpy(rng.uniform(-1, 1, size=(9, 20)).astype(np.float32))
+  D[0, -3:] = 0.0
+  powers = [1, 2, 3, 5, 7, 10, 20, 30]
+  tab = ops().ritz_power_table(D.to(dev()), powers).cpu()
+  ref = orc.ritz_power_table(D.double(), powers)
+  np.testing.assert_allclose(tab.numpy(), ref.numpy(), rtol=1.2e-7, atol=1e-45)
+  ref32 = orc.ritz_power_table(D, powers)
+  np.testing.assert_allclose(tab.numpy(), ref32.numpy(), rtol=4e-7, atol=1e-44)
+
+  B, N, H, P = 6, 26, 128, 16
+  state = torch.from_numpy(rng.randn(B, N, H).astype(np.float32))
+  params = {'filter.0.weight': torch.from_numpy(rng.randn(P, H).astype(np.float32) * 0.1),
+            'filter.0.bias': torch.from_numpy(rng.randn(P).astype(np.float32)),
+            'att_func.0.weight': torch.from_numpy(rng.randn(1, H).astype(np.float32) * 0.1),
+            'att_func.0.bias': torch.from_numpy(rng.randn(1).astype(np.float32))}
+  mask = torch.zeros(B, N, dtype=torch.uint8)
+  for b, n in enumerate([26, 1, 7, 13, 20, 25]):
+    mask[b, :n] = 1
+  spec = {'num_layer': 0}
+  for m in (mask, None):
+    ref = orc.readout({k: v.double() for k, v in params.items()}, spec, state.double(), m)
+    out = ops().readout(state.to(dev()), params['filter.0.weight'].to(dev()),
+                        params['filter.0.bias'].to(dev()),
+                        params['att_func.0.weight'].reshape(-1).to(dev()),
+                        params['att_func.0.bias'].to(dev()), None if m is None else m.to(dev()))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_gaussian_laplacian_matches_reference_output():
+  g = load_golden('ada_forward_small.npz')
+  from helpers import deterministic_state_dict
+  from lanczosnetwork_b200 import configs
+  from lanczosnetwork_b200.model import AdaLanczosNet
+  cfg = configs.qm8_ada_lanczos_net(num_layer=2, hidden_dim=[32, 32], num_eig_vec=8,
+                                    long_diffusion_dist=[2, 5], short_diffusion_dist=[1, 3])
+  emb = deterministic_state_dict(AdaLanczosNet(cfg), int(g['weight_seed']))['embedding.weight']
+  x = emb[torch.from_numpy(g['node_feat'])]
+  out = ops().gaussian_laplacian(x.to(dev()), torch.from_numpy(g['L']).to(dev())).cpu().numpy()
+  assert np.array_equal(out != 0, g['Le'] != 0)        # adjacency structure: exact
+  np.testing.assert_allclose(out, g['Le'], rtol=2e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# Lanczos tridiagonalisation / Ritz pairs / powers
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['qm8', 'small', 'nomask', 'cta64', 'cta100'])
+def test_lanczos_matches_reference_outputs(case):
+  g = load_golden('ada_lanczos_layer.npz')
+  A = torch.from_numpy(g[case + '_A'])
+  mask = None if case == 'nomask' else torch.from_numpy(g[case + '_mask'])
+  q1 = torch.from_numpy(g[case + '_q1'])
+  K = int(g[case + '_K'])
+  out = ops().lanczos_tridiag(A.to(dev()), None if mask is None else mask.to(dev()), q1.to(dev()), K)
+  T_ref, Q_ref = g[case + '_T'], g[case + '_Q']
+  T, Q = out['T'].cpu().numpy(), out['Q'].cpu().numpy()
+  o64 = orc.lanczos_tridiagonalise(A.double(), mask, q1.double(), K)
+  # integer / index logic: bit-exact (retained Krylov directions and node rows)
+  assert np.array_equal(out['idx'].cpu().numpy(), o64['idx'].numpy())
+  assert np.array_equal(T != 0, T_ref != 0)
+  assert np.array_equal(Q != 0, Q_ref != 0)
+  # floating point: no further from the fp64 oracle than 4x the reference's own fp32 error,
+  # with an absolute floor (near-breakdown steps amplify rounding by 1/beta)
+  eT_ref = np.abs(T_ref - o64['T'].numpy()).max()
+  eQ_ref = np.abs(Q_ref - o64['Q'].numpy()).max()
+  assert np.abs(T - o64['T'].numpy()).max() <= max(4 * eT_ref, 2e-5)
+  assert np.abs(Q - o64['Q'].numpy()).max() <= max(4 * eQ_ref, 2e-4)
+  np.testing.assert_allclose(out['alpha'].cpu().numpy(), np.diagonal(T, axis1=1, axis2=2))
+
+
+@pytest.mark.parametrize('case', ['qm8', 'small', 'cta64', 'cta100'])
+def test_tridiag_ritz_against_lapack(case):
+  g = load_golden('ada_lanczos_layer.npz')
+  T, Q = g[case + '_T'], g[case + '_Q']
+  alpha = np.ascontiguousarray(np.diagonal(T, axis1=1, axis2=2))
+  K = alpha.shape[1]
+  beta = np.zeros_like(alpha)
+  beta[:, :K - 1] = np.diagonal(T, offset=1, axis1=1, axis2=2)
+  theta, V, status = ops().tridiag_ritz(torch.from_numpy(alpha).to(dev()),
+                                        torch.from_numpy(beta).to(dev()),
+                                        torch.from_numpy(Q).to(dev()))
+  assert int(status.abs().sum()) == 0
+  th_o, S_o, V_o = orc.tridiag_ritz(alpha, beta[:, :K - 1], Q)
+  theta, V = theta.cpu().numpy().astype(np.float64), V.cpu().numpy().astype(np.float64)
+  # Ritz values: ordered by descending magnitude, equal to LAPACK's as a multiset and in order
+  assert np.all(np.diff(np.abs(theta), axis=1) <= 1e-7)
+  np.testing.assert_allclose(np.sort(theta, axis=1), np.sort(th_o, axis=1), atol=3e-6)
+  # sign / rotation invariant filters V g(theta) V^T for g = id, square, |.|^1/2
+  for fn in (lambda t: t, lambda t: t * t, lambda t: np.sqrt(np.abs(t))):
+    ours = np.einsum('bnk,bk,bmk->bnm', V, fn(theta), V)
+    ref = np.einsum('bnk,bk,bmk->bnm', V_o, fn(th_o), V_o)
+    np.testing.assert_allclose(ours, ref, atol=2e-5)
+  # and V diag(theta) V^T reproduces Q T Q^T
+  qtq = np.einsum('bnk,bkj,bmj->bnm', Q.astype(np.float64), T.astype(np.float64), Q.astype(np.float64))
+  np.testing.assert_allclose(np.einsum('bnk,bk,bmk->bnm', V, theta, V), qtq, atol=2e-5)
+
+
+def test_tridiag_powers_and_symmetrize():
+  g = load_golden('ada_lanczos_layer.npz')
+  T = torch.from_numpy(g['qm8_T'])
+  powers = [5, 7, 10, 20, 30]
+  out = ops().tridiag_powers(T.to(dev()), powers).cpu()          # [B,K,S,K]
+  ref = torch.stack(orc.tridiag_power_stack(T.double(), powers), dim=2)   # [B,K,S,K]
+  np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=2e-5, atol=1e-7)
+  B, K, S = 3, 8, 5
+  Y = torch.randn(B, K * K * S)
+  G = ops().symmetrize_filters(Y.to(dev()), K, S).cpu()
+  Y4 = Y.reshape(B, K, K, S)
+  ref = ((Y4 + Y4.transpose(1, 2)) * 0.5).permute(0, 3, 1, 2)
+  assert torch.equal(G, ref.contiguous())

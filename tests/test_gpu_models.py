@@ -1,0 +1,159 @@
+"""Module-level parity: the drop-in nn.Modules against reference outputs (tests/golden) and
+the CPU oracle, plus size-independent properties at the benchmark size.  ``pytest -m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import deterministic_state_dict, load_golden, oracle_spec
+from lanczosnetwork_b200 import configs, data
+from lanczosnetwork_b200.model import AdaLanczosNet, LanczosNet, LanczosNetGeneral
+from oracle import lanczos_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# Stated fp32 tolerance of the full 7-layer forward (scores are O(0.1..1)):
+FWD_ATOL = 2e-5
+FWD_RTOL = 1e-4
+
+
+def dev():
+  return torch.device('cuda:0')
+
+
+def _t(a):
+  return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _build(cls, cfg, seed):
+  mod = cls(cfg)
+  params = deterministic_state_dict(mod, seed)
+  mod.load_state_dict(params)
+  return mod.to(dev()).eval(), params
+
+
+def test_lanczosnet_matches_reference_golden():
+  g = load_golden('lanczosnet_qm8.npz')
+  mod, params = _build(LanczosNet, configs.qm8_lanczos_net(), int(g['weight_seed']))
+  with torch.no_grad():
+    score, loss = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), _t(g['D']).to(dev()),
+                      _t(g['V']).to(dev()), label=_t(g['label']).to(dev()),
+                      mask=_t(g['node_mask']).to(dev()))
+  np.testing.assert_allclose(score.cpu().numpy(), g['score'], rtol=FWD_RTOL, atol=FWD_ATOL)
+  assert abs(float(loss) - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+  # error budget: no further from the fp64 oracle than 4x the reference's own fp32 error
+  spec = oracle_spec(mod, 'LanczosNet')
+  s64 = orc.lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['D'], g['V'],
+                                g['node_mask'], dtype=torch.float64).numpy()
+  e_ref = np.abs(g['score'] - s64).max()
+  e_ours = np.abs(score.cpu().numpy() - s64).max()
+  assert e_ours <= max(4 * e_ref, 5e-6), (e_ours, e_ref)
+
+
+def test_lanczosnet_power_filter_matches_reference_golden():
+  g = load_golden('lanczosnet_qm8.npz')
+  cfg = configs.qm8_lanczos_net(spectral_filter_kind='power', num_layer=2, hidden_dim=[32, 32])
+  mod, _ = _build(LanczosNet, cfg, int(g['weight_seed']) + 100)
+  with torch.no_grad():
+    score = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), _t(g['D']).to(dev()),
+                _t(g['V']).to(dev()), mask=_t(g['node_mask']).to(dev()))
+  np.testing.assert_allclose(score.cpu().numpy(), g['score_power'], rtol=FWD_RTOL, atol=FWD_ATOL)
+
+
+def test_general_matches_reference_golden():
+  g = load_golden('lanczosnet_general_synth.npz')
+  mod, _ = _build(LanczosNetGeneral, configs.graph_lanczos_net(), int(g['weight_seed']))
+  with torch.no_grad():
+    score = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), _t(g['D']).to(dev()),
+                _t(g['V']).to(dev()), mask=_t(g['node_mask']).to(dev()))
+  np.testing.assert_allclose(score.cpu().numpy(), g['score'], rtol=FWD_RTOL, atol=FWD_ATOL)
+
+
+def test_ada_matches_reference_golden():
+  g = load_golden('ada_forward_small.npz')
+  cfg = configs.qm8_ada_lanczos_net(num_layer=2, hidden_dim=[32, 32], num_eig_vec=8,
+                                    long_diffusion_dist=[2, 5], short_diffusion_dist=[1, 3])
+  mod, _ = _build(AdaLanczosNet, cfg, int(g['weight_seed']))
+  torch.manual_seed(int(g['torch_seed']))     # the module draws q1 like the reference (CPU randn)
+  with torch.no_grad():
+    score = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()),
+                mask=_t(g['node_mask']).to(dev()))
+  np.testing.assert_allclose(score.cpu().numpy(), g['score'], rtol=1e-3, atol=5e-5)
+
+
+def test_lanczosnet_vs_oracle_batch256_and_properties():
+  """Benchmark-shaped batch against the fp32 oracle, then size-independent properties:
+  batch-permutation equivariance (bit-exact), invariance to extra zero padding."""
+  batch = data.synthetic_qm8_batch(256, seed=99)
+  mod, params = _build(LanczosNet, configs.qm8_lanczos_net(), 1234)
+  spec = oracle_spec(mod, 'LanczosNet')
+  args = [batch[k] for k in ('node_feat', 'L', 'D', 'V')]
+  ref = orc.lanczos_net_forward(params, spec, *args, batch['node_mask']).numpy()
+  dargs = [_t(a).to(dev()) for a in args]
+  mask = _t(batch['node_mask']).to(dev())
+  with torch.no_grad():
+    out = mod(*dargs, mask=mask)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=FWD_RTOL, atol=FWD_ATOL)
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(1)).to(dev())
+    outp = mod(*[a[perm] for a in dargs], mask=mask[perm])
+    assert torch.equal(outp, out[perm])
+    # pad every graph with 6 extra empty nodes: same scores
+    B, N = dargs[0].shape
+    nf = torch.zeros(B, N + 6, dtype=dargs[0].dtype, device=dev()); nf[:, :N] = dargs[0]
+    Lp = torch.zeros(B, N + 6, N + 6, 7, device=dev()); Lp[:, :N, :N] = dargs[1]
+    Vp = torch.zeros(B, N + 6, 20, device=dev()); Vp[:, :N] = dargs[3]
+    mp = torch.zeros(B, N + 6, dtype=torch.uint8, device=dev()); mp[:, :N] = mask
+    outpad = mod(nf, Lp, dargs[2], Vp, mask=mp)
+    np.testing.assert_allclose(outpad.cpu().numpy(), out.cpu().numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_dropin_surface_and_checkpoint_compat(tmp_path):
+  """Same state_dict keys / shapes as the reference (keys recorded from the reference class),
+  DataParallel wrapping, CPU inputs moved by the module, label -> (score, loss)."""
+  g = load_golden('lanczosnet_qm8.npz')
+  cfg = configs.qm8_lanczos_net()
+  mod = LanczosNet(cfg)
+  keys = list(mod.state_dict().keys())
+  assert keys[:2] == ['filter.0.weight', 'filter.0.bias']
+  assert 'embedding.weight' in keys and 'att_func.0.weight' in keys
+  assert 'spectral_filter.6.6.bias' in keys and len(keys) == 16 + 1 + 56 + 2
+  snap = {'model': deterministic_state_dict(mod, 5), 'optimizer': {}, 'step': 0}
+  path = str(tmp_path / 'model_snapshot_best.pth')
+  torch.save(snap, path)                                   # utils/train_helper.py:14-25 format
+  mod.load_state_dict(torch.load(path)['model'])           # utils/train_helper.py:28-32
+  wrapped = torch.nn.DataParallel(mod, device_ids=[0]).cuda().eval()   # runner/qm8_runner.py:291-292
+  with torch.no_grad():
+    score, loss = wrapped(_t(g['node_feat']).cuda(), _t(g['L']), _t(g['D']).cuda(),
+                          _t(g['V']).cuda(), label=_t(g['label']).cuda(),
+                          mask=_t(g['node_mask']).cuda())
+  assert score.shape == (8, 16) and torch.isfinite(score).all() and loss.ndim == 0
+  with pytest.raises(NotImplementedError):
+    wrapped.module(_t(g['node_feat']).cuda(), _t(g['L']).cuda(), _t(g['D']).cuda(),
+                   _t(g['V']).cuda(), mask=_t(g['node_mask']).cuda())   # grad enabled -> forward-only
+  with pytest.raises(RuntimeError):
+    LanczosNet(cfg)(_t(g['node_feat']), _t(g['L']), _t(g['D']), _t(g['V']))   # CPU module: loud
+
+
+def test_lanczos_plus_ritz_pipeline_reproduces_low_rank_operator():
+  """The north-star pipeline adjacency -> Lanczos -> QL -> Ritz pairs: for graphs with
+  n_b <= K the Ritz decomposition reproduces the operator on the Krylov space."""
+  from lanczosnetwork_b200 import ops
+  rng = np.random.RandomState(4)
+  sizes = [12, 9, 15, 7, 18, 20, 5, 11]
+  N, K = 20, 20
+  A = np.zeros((len(sizes), N, N), np.float32)
+  mask = np.zeros((len(sizes), N), np.uint8)
+  for b, n in enumerate(sizes):
+    _, adjs = data.synthetic_molecule(rng, n)
+    A[b, :n, :n] = data.get_laplacian(adjs.sum(axis=2))
+    mask[b, :n] = 1
+  q1 = rng.randn(len(sizes), N).astype(np.float32)
+  lz = ops.lanczos_tridiag(_t(A).to(dev()), _t(mask).to(dev()), _t(q1).to(dev()), K)
+  theta, V, status = ops.tridiag_ritz(lz['alpha'], lz['beta'], lz['Q'])
+  assert int(status.sum()) == 0
+  o = orc.lanczos_tridiagonalise(_t(A).double(), _t(mask), _t(q1).double(), K)
+  assert np.array_equal(lz['idx'].cpu().numpy(), o['idx'].numpy())
+  th, S, Vo = orc.tridiag_ritz(o['alpha'].numpy(), o['beta'].numpy()[:, :K - 1], o['Q'].numpy())
+  ours = np.einsum('bnk,bk,bmk->bnm', V.cpu().numpy().astype(np.float64),
+                   theta.cpu().numpy().astype(np.float64), V.cpu().numpy().astype(np.float64))
+  ref = np.einsum('bnk,bk,bmk->bnm', Vo, th, Vo)
+  np.testing.assert_allclose(ours, ref, atol=5e-5)

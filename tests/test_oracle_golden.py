@@ -1,0 +1,125 @@
+"""Pin the oracle against outputs of the REFERENCE itself (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from /root/reference).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import deterministic_state_dict, load_golden, oracle_spec
+from lanczosnetwork_b200 import configs
+from lanczosnetwork_b200.model import AdaLanczosNet, LanczosNet, LanczosNetGeneral
+from oracle import graph_prep
+from oracle import lanczos_oracle as orc
+
+
+def test_data_helper_fixture():
+  g = load_golden('data_helper_fixture.npz')
+  L4 = graph_prep.laplacian_L4(g['adj'])
+  np.testing.assert_allclose(L4, g['L4'], rtol=0, atol=1e-15)
+  # the survey's hand-checked known answers
+  np.testing.assert_allclose(L4[0], [1 / 3, 0.288675, 0, 0, 0.288675, 0], atol=1e-6)
+  D, V = graph_prep.eig_topk_by_magnitude(L4, k=100)
+  np.testing.assert_allclose(D, g['D'], atol=1e-12)
+  np.testing.assert_allclose(D, [1.0, 0.72039, 0.427016, -0.316134, 0.146376, -0.060981], atol=1e-6)
+  # eigenvectors up to sign
+  np.testing.assert_allclose(np.abs(V), np.abs(g['V']), atol=1e-10)
+  D3, V3 = graph_prep.eig_topk_by_magnitude(L4, k=3)
+  np.testing.assert_allclose(D3, g['D3'], atol=1e-12)
+
+
+def test_collate_matches_reference():
+  g = load_golden('lanczosnet_qm8.npz')
+  samples = []
+  for b, n in enumerate(g['sizes']):
+    rec = graph_prep.prepare_molecule(g['adjs'][b, :n, :n].astype(np.float64))
+    rec['node_feat'] = g['node_feat'][b, :n]
+    samples.append(rec)
+  out = graph_prep.collate(samples, 20)
+  assert np.array_equal(out['node_feat'], g['node_feat'])
+  assert np.array_equal(out['node_mask'], g['node_mask'])
+  assert np.array_equal(out['L'], g['L'])          # bit-exact operator construction
+  np.testing.assert_allclose(out['D'], g['D'], atol=1e-6)
+  # Ritz vectors: compare the sign/rotation-invariant filter V diag(D) V^T
+  rec_o = np.einsum('bnk,bk,bmk->bnm', out['V'], out['D'], out['V'])
+  rec_g = np.einsum('bnk,bk,bmk->bnm', g['V'], g['D'], g['V'])
+  np.testing.assert_allclose(rec_o, rec_g, atol=2e-6)
+
+
+def test_lanczosnet_forward_matches_reference():
+  g = load_golden('lanczosnet_qm8.npz')
+  cfg = configs.qm8_lanczos_net()
+  mod = LanczosNet(cfg)
+  params = deterministic_state_dict(mod, int(g['weight_seed']))
+  spec = oracle_spec(mod, 'LanczosNet')
+  score = orc.lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['D'], g['V'],
+                                  g['node_mask'])
+  np.testing.assert_allclose(score.numpy(), g['score'], rtol=1e-4, atol=2e-6)
+  p32 = orc._cast(params, torch.float32)
+  Lf0 = orc.spectral_filters_from_ritz(p32, spec, torch.from_numpy(g['D']),
+                                       torch.from_numpy(g['V']), 0)
+  np.testing.assert_allclose(Lf0.numpy(), g['Lf0'], rtol=1e-4, atol=1e-6)
+  # fp64 oracle: the reference fp32 result sits within fp32 rounding of it
+  s64 = orc.lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['D'], g['V'],
+                                g['node_mask'], dtype=torch.float64)
+  assert np.abs(s64.numpy() - g['score']).max() < 2e-5
+
+
+def test_lanczosnet_power_filter_matches_reference():
+  g = load_golden('lanczosnet_qm8.npz')
+  cfg = configs.qm8_lanczos_net(spectral_filter_kind='power', num_layer=2, hidden_dim=[32, 32])
+  mod = LanczosNet(cfg)
+  params = deterministic_state_dict(mod, int(g['weight_seed']) + 100)
+  spec = oracle_spec(mod, 'LanczosNet')
+  score = orc.lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['D'], g['V'],
+                                  g['node_mask'])
+  np.testing.assert_allclose(score.numpy(), g['score_power'], rtol=1e-4, atol=2e-6)
+
+
+def test_general_forward_matches_reference():
+  g = load_golden('lanczosnet_general_synth.npz')
+  cfg = configs.graph_lanczos_net()
+  mod = LanczosNetGeneral(cfg)
+  params = deterministic_state_dict(mod, int(g['weight_seed']))
+  spec = oracle_spec(mod, 'LanczosNetGeneral')
+  score = orc.lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['D'], g['V'],
+                                  g['node_mask'])
+  np.testing.assert_allclose(score.numpy(), g['score'], rtol=1e-4, atol=5e-6)
+
+
+@pytest.mark.parametrize('case', ['qm8', 'small', 'nomask', 'cta64', 'cta100'])
+def test_lanczos_layer_matches_reference(case):
+  g = load_golden('ada_lanczos_layer.npz')
+  A = torch.from_numpy(g[case + '_A'])
+  mask = None if case == 'nomask' else torch.from_numpy(g[case + '_mask'])
+  q1 = torch.from_numpy(g[case + '_q1'])
+  K = int(g[case + '_K'])
+  out = orc.lanczos_tridiagonalise(A, mask, q1, K)
+  T_ref, Q_ref = g[case + '_T'], g[case + '_Q']
+  # integer structure is exact: which Krylov directions / node rows survive
+  assert np.array_equal(out['T'].numpy() != 0, T_ref != 0)
+  assert np.array_equal(out['Q'].numpy() != 0, Q_ref != 0)
+  np.testing.assert_allclose(out['T'].numpy(), T_ref, atol=5e-5)
+  np.testing.assert_allclose(out['Q'].numpy(), Q_ref, atol=2e-3)
+
+
+def test_ada_forward_matches_reference():
+  g = load_golden('ada_forward_small.npz')
+  cfg = configs.qm8_ada_lanczos_net(num_layer=2, hidden_dim=[32, 32], num_eig_vec=8,
+                                    long_diffusion_dist=[2, 5], short_diffusion_dist=[1, 3])
+  mod = AdaLanczosNet(cfg)
+  params = deterministic_state_dict(mod, int(g['weight_seed']))
+  spec = oracle_spec(mod, 'AdaLanczosNet')
+  score, aux = orc.ada_lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['node_mask'],
+                                           g['q1'], return_aux=True)
+  np.testing.assert_allclose(aux['Le'].numpy(), g['Le'], rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(score.numpy(), g['score'], rtol=1e-3, atol=2e-5)
+
+
+def test_tridiag_ritz_oracle_reconstructs_T():
+  g = load_golden('ada_lanczos_layer.npz')
+  T = g['qm8_T']
+  alpha = np.diagonal(T, axis1=1, axis2=2)
+  beta = np.diagonal(T, offset=1, axis1=1, axis2=2)
+  theta, S = orc.tridiag_ritz(alpha, beta)
+  rec = np.einsum('bik,bk,bjk->bij', S, theta, S)
+  np.testing.assert_allclose(rec, T, atol=1e-12)
+  assert np.all(np.diff(np.abs(theta), axis=1) <= 1e-15)
