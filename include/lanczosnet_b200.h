@@ -73,11 +73,33 @@ int lnb_batched_gemm(lnb_stream_t stream, const lnb_gemm_desc* desc /* host */);
  * (nn.Linear of model/lanczos_net.py:181 and the 4096-wide MLP of ada_lanczos_net.py:54-63).
  * fp32 in/out; computed as 3xTF32 split products (hi*hi + hi*lo + lo*hi) with fp32 TMEM
  * accumulation -> fp32-grade accuracy.  W_hi / W_lo are the tf32 split of W produced once by
- * lnb_split_tf32.  Requirements: K % 32 == 0, N % 16 == 0 (N <= 256 per tile column block).
+ * lnb_split_tf32.  Requirements: K % 4 == 0 and 16-byte aligned operands; any M, N.
+ * Two TMEM accumulators (A_hi*W_hi and the two correction products) are summed in fp32 by the
+ * epilogue so the small terms do not add truncation steps to the large accumulator.
  * ------------------------------------------------------------------------------------- */
 int lnb_split_tf32(lnb_stream_t stream, const float* x, int64_t n, float* hi, float* lo);
 int lnb_linear_tf32x3(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
                       const float* bias, int M, int N, int K, int relu, float* C);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused spectral graph-convolution layer (model/lanczos_net.py:157-182):
+ *   out[b,n,:] = act( cat_c(M_c X_b)[n,:] W^T + bias ),  channels c = S long scales
+ *   (V diag(coeff[:,:,s]) V^T) followed by the E1 edge-type operators L[...,e].
+ * One persistent tcgen05 kernel: message tiles are produced on CUDA cores straight into tensor
+ * memory (never written to HBM) and multiplied by TMA-staged W_hi/W_lo tiles (3xTF32).
+ * lnb_graph_prepare compresses the (layer-invariant) dense operators once per forward:
+ *   ell_val/ell_idx [B,E1,N,N] (t-major ELL rows, zero-filled to ell_max[b,e]), qext[b] =
+ *   {rows, columns} of Q that are not identically zero.  Skipping exact zeros is exact.
+ * Requirements of the fused kernel: N <= 128, Din % 32 == 0, K <= 32, H % 4 == 0; W is
+ * [H, (S+E1)*Din].  Returns LNB_ERR_UNSUPPORTED otherwise (callers use the unfused ops).
+ * ------------------------------------------------------------------------------------- */
+int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
+                      int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* qext);
+int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q, const float* coeff,
+                            const float* ell_val, const uint8_t* ell_idx, const int32_t* ell_max,
+                            const int32_t* qext, const float* W_hi, const float* W_lo,
+                            const float* bias, int B, int N, int Din, int E1, int K, int S, int H,
+                            int relu, float* out);
 
 /* ---------------------------------------------------------------------------------------
  * Embedding rows (model/lanczos_net.py:154): out[r, :] = table[idx[r], :].

@@ -68,8 +68,10 @@ extern "C" {
 int lnb_unsorted_segment_sum_forward(lnb_stream_t stream, const float* data,
                                      const int64_t* segment_ids, const int* data_shape,
                                      int num_segments, float* output) {
-  LNB_REQUIRE(data && segment_ids && data_shape && output, "segment_sum_forward: null pointer");
+  LNB_REQUIRE(data_shape, "segment_sum_forward: null shape");
   int B = data_shape[0], d1 = data_shape[1], d2 = data_shape[2];
+  if ((int64_t)B * d1 * d2 == 0) return LNB_OK;   // empty input: nothing to add
+  LNB_REQUIRE(data && segment_ids && output, "segment_sum_forward: null pointer");
   LNB_REQUIRE(B >= 0 && d1 >= 0 && d2 >= 0 && num_segments > 0,
               "segment_sum_forward: bad shape [%d,%d,%d] S=%d", B, d1, d2, num_segments);
   int64_t n = (int64_t)B * d1 * d2;
@@ -90,9 +92,10 @@ int lnb_unsorted_segment_sum_forward(lnb_stream_t stream, const float* data,
 int lnb_unsorted_segment_sum_backward(lnb_stream_t stream, const float* grad_output,
                                       const int64_t* segment_ids, const int* data_shape,
                                       int num_segments, float* grad_data) {
-  LNB_REQUIRE(grad_output && segment_ids && data_shape && grad_data,
-              "segment_sum_backward: null pointer");
+  LNB_REQUIRE(data_shape, "segment_sum_backward: null shape");
   int B = data_shape[0], d1 = data_shape[1], d2 = data_shape[2];
+  if ((int64_t)B * d1 * d2 == 0) return LNB_OK;
+  LNB_REQUIRE(grad_output && segment_ids && grad_data, "segment_sum_backward: null pointer");
   LNB_REQUIRE(B >= 0 && d1 >= 0 && d2 >= 0 && num_segments > 0,
               "segment_sum_backward: bad shape [%d,%d,%d] S=%d", B, d1, d2, num_segments);
   int64_t n = (int64_t)B * d1 * d2;

@@ -1,0 +1,283 @@
+// Persistent tcgen05 3xTF32 GEMM skeleton (sm_100a):
+//     D[128 x 128 tile] = sum_k A[rows, k] * W[n, k]        fp32-grade accuracy from TF32 MMAs
+// The A operand of every 128x32 k-block is PRODUCED BY CUDA-CORE WARPS straight into tensor
+// memory (tcgen05.st, row r <-> TMEM lane r, k <-> column), so a policy can either load rows
+// from HBM (dense layer) or compute them on the fly (fused graph messages) -- the tensor-core
+// side is identical.  W_hi / W_lo tiles arrive by TMA (SWIZZLE_128B) through an mbarrier ring.
+//
+// Accuracy: tensor-core accumulation truncates, so the 3 split products are kept in two
+// accumulators -- D_main += A_hi*W_hi and D_corr += A_lo*W_hi + A_hi*W_lo -- and summed in fp32
+// by the epilogue (the small terms no longer add truncation steps to the large accumulator).
+//
+// CTA = 10 warps, 1 CTA / SM, persistent over tiles:
+//   warps 0-3, 4-7  producer groups P0 / P1 (alternate k-blocks; 2 TMEM stages each), then epilogue
+//   warp 8          TMA producer (W tiles)
+//   warp 9          TMEM allocation + single-thread tcgen05.mma issue / commit
+// TMEM (512 columns): [0,128) D_main, [128,256) D_corr, [256,512) 4 A stages x (32 hi + 32 lo).
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace tcg {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int NB_STAGES = 3;
+constexpr int NA_STAGES = 4;                       // 2 per producer group
+constexpr int TILE_B_BYTES = BN * BK * 4;          // 16 KB per hi or lo tile
+constexpr int TMEM_COLS = 512;
+constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;
+constexpr int PRODUCER_THREADS = 256;
+constexpr int THREADS = PRODUCER_THREADS + 64;
+constexpr int CORE_SMEM = 2 * NB_STAGES * TILE_B_BYTES + 256;   // W ring + barriers/holder
+
+struct Core {
+  uint8_t* Bhi;
+  uint8_t* Blo;
+  uint64_t* b_full;    // [NB_STAGES]
+  uint64_t* b_empty;   // [NB_STAGES]
+  uint64_t* a_full;    // [NA_STAGES]
+  uint64_t* a_empty;   // [NA_STAGES]
+  uint64_t* acc_full;  // [1]
+  uint64_t* acc_empty; // [1]
+  uint32_t* tmem_holder;
+};
+
+__device__ __forceinline__ Core carve(uint8_t* base) {
+  Core c;
+  c.Bhi = base;
+  c.Blo = base + NB_STAGES * TILE_B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * NB_STAGES * TILE_B_BYTES);
+  c.b_full = bars;
+  c.b_empty = c.b_full + NB_STAGES;
+  c.a_full = c.b_empty + NB_STAGES;
+  c.a_empty = c.a_full + NA_STAGES;
+  c.acc_full = c.a_empty + NA_STAGES;
+  c.acc_empty = c.acc_full + 1;
+  c.tmem_holder = reinterpret_cast<uint32_t*>(c.acc_empty + 1);
+  return c;
+}
+
+__device__ __forceinline__ void producers_sync() {   // named barrier 1: the 256 producer threads
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// Policy contract (all __device__):
+//   struct Params;                                     kernel parameter block (by value)
+//   static int  num_tiles(const Params&), n_tiles(const Params&), num_kblocks(const Params&);
+//   Policy(const Params&, uint8_t* policy_smem, int tid)   constructed by producer threads only
+//   void tile_begin(int m_tile)                        may call producers_sync()
+//   void produce(int kb, float (&v)[32])               the 32 A values of this thread's row
+//   void tile_end()                                    after the tile's last produce()
+//   float* out_row(int n0)                             output pointer of this row (nullptr: skip)
+//   int out_cols() ; const float* bias(); bool relu()
+template <class Policy>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
+               const __grid_constant__ CUtensorMap map_lo, const typename Policy::Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  Core c = carve(base);
+  uint8_t* policy_smem = base + CORE_SMEM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_tiles = Policy::num_tiles(p);
+  const int n_tiles = Policy::n_tiles(p);
+  const int nkb = Policy::num_kblocks(p);
+
+  if (warp == 8 && lane == 0) {
+    tc05::tma_prefetch_desc(&map_hi);
+    tc05::tma_prefetch_desc(&map_lo);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int s = 0; s < NB_STAGES; ++s) { tc05::mbar_init(&c.b_full[s], 1); tc05::mbar_init(&c.b_empty[s], 1); }
+      for (int s = 0; s < NA_STAGES; ++s) { tc05::mbar_init(&c.a_full[s], 128); tc05::mbar_init(&c.a_empty[s], 1); }
+      tc05::mbar_init(c.acc_full, 1);
+      tc05::mbar_init(c.acc_empty, PRODUCER_THREADS);
+      tc05::fence_barrier_init();
+    }
+    __syncwarp();
+    tc05::tmem_alloc(c.tmem_holder, TMEM_COLS);
+  }
+  tc05::fence_before_thread_sync();
+  __syncthreads();
+  tc05::fence_after_thread_sync();
+  const uint32_t tmem_base = *c.tmem_holder;
+
+  if (warp < 8) {
+    // ================================ producers + epilogue ================================
+    const int grp = warp >> 2;                       // 0 / 1
+    const int wq = warp & 3;                         // TMEM lane quarter
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    Policy pol(p, policy_smem, tid);
+    uint32_t cnt = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
+      pol.tile_begin(m_tile);
+      for (int kb = grp; kb < nkb; kb += 2, ++cnt) {
+        float v[32];
+        pol.produce(kb, v);
+        const uint32_t sa = grp * 2 + (cnt & 1u);
+        tc05::mbar_wait(&c.a_empty[sa], ((cnt >> 1) & 1u) ^ 1u);
+        tc05::fence_after_thread_sync();
+        uint32_t part[32];
+        const uint32_t a_hi = lane_addr + COL_A + sa * 64;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(v[j]);
+        tc05::tmem_st_32x32(a_hi, part);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(v[j] - __uint_as_float(part[j]));
+        tc05::tmem_st_32x32(a_hi + 32, part);
+        tc05::tmem_wait_st();
+        tc05::fence_before_thread_sync();
+        tc05::mbar_arrive(&c.a_full[sa]);
+      }
+      pol.tile_end();
+      // ---- epilogue: this group owns accumulator columns [grp*64, grp*64+64) ----
+      tc05::mbar_wait(c.acc_full, tcount & 1u);
+      tc05::fence_after_thread_sync();
+      const int n0 = n_tile * BN;
+      float* orow = pol.out_row(n0);
+      const int ncols = pol.out_cols();
+      const float* bias = pol.bias();
+      const bool relu = pol.relu();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = grp * 64 + cc * 32;
+        uint32_t vm[32], vc[32];
+        tc05::tmem_ld_32x32(lane_addr + COL_MAIN + col, vm);
+        tc05::tmem_ld_32x32(lane_addr + COL_CORR + col, vc);
+        tc05::tmem_wait_ld();
+        const int nb = n0 + col;
+        if (orow != nullptr && nb < ncols) {
+          const bool vec_ok = (ncols % 4) == 0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int n = nb + j + u;
+              float x = __uint_as_float(vm[j + u]) + __uint_as_float(vc[j + u]);
+              if (n < ncols) {
+                if (bias) x += __ldg(bias + n);
+                if (relu) x = fmaxf(x, 0.f);
+              }
+              o[u] = x;
+            }
+            if (vec_ok && nb + j + 3 < ncols) {
+              *reinterpret_cast<float4*>(orow + col + j) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (nb + j + u < ncols) orow[col + j + u] = o[u];
+            }
+          }
+        }
+      }
+      tc05::fence_before_thread_sync();
+      tc05::mbar_arrive(c.acc_empty);
+    }
+  } else if (warp == 8) {
+    // ================================ TMA producer (W tiles) ==============================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          const uint32_t sb = cnt % NB_STAGES;
+          tc05::mbar_wait(&c.b_empty[sb], ((cnt / NB_STAGES) & 1u) ^ 1u);
+          tc05::mbar_arrive_expect_tx(&c.b_full[sb], 2 * TILE_B_BYTES);
+          tc05::tma_load_2d(c.Bhi + sb * TILE_B_BYTES, &map_hi, &c.b_full[sb], kb * BK, n0);
+          tc05::tma_load_2d(c.Blo + sb * TILE_B_BYTES, &map_lo, &c.b_full[sb], kb * BK, n0);
+        }
+      }
+    }
+  } else {
+    // ================================ MMA issuer ==========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc05::umma_idesc_tf32(BM, BN);
+      uint32_t cnt_b = 0, cnt_a[2] = {0, 0}, tcount = 0;
+      const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        tc05::mbar_wait(c.acc_empty, (tcount & 1u) ^ 1u);     // epilogue of the previous tile done
+        tc05::fence_after_thread_sync();
+        for (int kb = 0; kb < nkb; ++kb, ++cnt_b) {
+          const int g = kb & 1;
+          const uint32_t sa = g * 2 + (cnt_a[g] & 1u);
+          const uint32_t pha = (cnt_a[g] >> 1) & 1u;
+          ++cnt_a[g];
+          const uint32_t sb = cnt_b % NB_STAGES;
+          tc05::mbar_wait(&c.b_full[sb], (cnt_b / NB_STAGES) & 1u);
+          tc05::mbar_wait(&c.a_full[sa], pha);
+          tc05::fence_after_thread_sync();
+          const uint32_t a_hi = tmem_base + COL_A + sa * 64, a_lo = a_hi + 32;
+          const uint64_t dhi = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Bhi + sb * TILE_B_BYTES));
+          const uint64_t dlo = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Blo + sb * TILE_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            tc05::umma_tf32_ts(d_corr, a_lo + 8 * k, dhi + 2 * k, idesc, first);
+            tc05::umma_tf32_ts(d_corr, a_hi + 8 * k, dlo + 2 * k, idesc, 1u);
+            tc05::umma_tf32_ts(d_main, a_hi + 8 * k, dhi + 2 * k, idesc, first);
+          }
+          tc05::umma_commit(&c.a_empty[sa]);
+          tc05::umma_commit(&c.b_empty[sb]);
+        }
+        tc05::umma_commit(c.acc_full);
+      }
+    }
+  }
+
+  tc05::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc05::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host helpers --------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;   // idempotent lookup; benign if two threads race
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// Row-major [rows, cols] fp32 weight matrix; box = 32 columns (128 B) x 128 rows; 128 B swizzle.
+inline int make_weight_map(CUtensorMap* map, const float* W, int rows, int cols, const char* who) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { lnb::set_err("%s: cuTensorMapEncodeTiled unavailable", who); return LNB_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lnb::set_err("%s: cuTensorMapEncodeTiled failed (CUresult %d)", who, (int)r);
+    return LNB_ERR_ARG;
+  }
+  return LNB_OK;
+}
+
+inline int sm_count() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
+}  // namespace tcg

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..spectral_conv import dense, graph_conv_layer
+from ..spectral_conv import GraphContext, dense, graph_conv_layer
 from ._common import SpectralNetBase
 
 __all__ = ['AdaLanczosNet']
@@ -67,6 +67,7 @@ class AdaLanczosNet(SpectralNetBase):
       powers = ops.tridiag_powers(lz['T'], self.long_diffusion_dist)     # [B,K,S,K], once
       self.last_lanczos = lz
 
+    ctx = GraphContext(L, Q)
     for tt in range(self.num_layer):
       G = None
       if S > 0:
@@ -79,7 +80,7 @@ class AdaLanczosNet(SpectralNetBase):
           G = ops.symmetrize_filters(h, K, S)                            # [B,S,K,K]
         else:
           G = powers.permute(0, 2, 1, 3).contiguous()
-      state = graph_conv_layer(state, L, Q, G, True, self.short_diffusion_dist, S,
+      state = graph_conv_layer(state, ctx, G, True, self.short_diffusion_dist, S,
                                self.filter[tt].weight, self.filter[tt].bias, self._wcache,
                                'filter.%d' % tt)
     score = self._readout(state, mask)

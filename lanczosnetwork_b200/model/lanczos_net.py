@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..spectral_conv import graph_conv_layer, ritz_filter_coefficients
+from ..spectral_conv import GraphContext, graph_conv_layer, ritz_filter_coefficients
 from ._common import SpectralNetBase
 
 __all__ = ['LanczosNet']
@@ -42,6 +42,7 @@ class LanczosNet(SpectralNetBase):
     label = self._to(dev, label)
     state = self._initial_state(node_feat, dev)
 
+    ctx = GraphContext(L, V)
     coeffs = table = None
     if self.num_scale_long > 0:
       mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
@@ -51,7 +52,7 @@ class LanczosNet(SpectralNetBase):
       coeff = None
       if self.num_scale_long > 0:
         coeff = coeffs[tt] if coeffs is not None else table
-      state = graph_conv_layer(state, L, V, coeff, False, self.short_diffusion_dist,
+      state = graph_conv_layer(state, ctx, coeff, False, self.short_diffusion_dist,
                                self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
                                self._wcache, 'filter.%d' % tt)
     score = self._readout(state, mask)

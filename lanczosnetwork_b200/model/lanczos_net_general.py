@@ -3,7 +3,7 @@ LanczosNet with float node features instead of an atom embedding (:156) and the 
 count taken from ``config.dataset.num_edge_type`` (:24)."""
 import torch
 
-from ..spectral_conv import graph_conv_layer, ritz_filter_coefficients
+from ..spectral_conv import GraphContext, graph_conv_layer, ritz_filter_coefficients
 from ._common import SpectralNetBase
 
 __all__ = ['LanczosNetGeneral']
@@ -38,6 +38,7 @@ class LanczosNetGeneral(SpectralNetBase):
     label = self._to(dev, label)
     state = self._to(dev, node_feat, torch.float32).contiguous()
 
+    ctx = GraphContext(L, V)
     coeffs = table = None
     if self.num_scale_long > 0:
       mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
@@ -47,7 +48,7 @@ class LanczosNetGeneral(SpectralNetBase):
       coeff = None
       if self.num_scale_long > 0:
         coeff = coeffs[tt] if coeffs is not None else table
-      state = graph_conv_layer(state, L, V, coeff, False, self.short_diffusion_dist,
+      state = graph_conv_layer(state, ctx, coeff, False, self.short_diffusion_dist,
                                self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
                                self._wcache, 'filter.%d' % tt)
     score = self._readout(state, mask)

@@ -12,7 +12,8 @@ from . import _lib
 from ._lib import GemmDesc
 
 __all__ = [
-    'bgemm', 'split_tf32', 'linear_tf32x3', 'embedding_rows', 'ritz_power_table', 'readout',
+    'bgemm', 'split_tf32', 'linear_tf32x3', 'graph_prepare', 'spectral_conv_fused',
+    'fused_conv_supported', 'embedding_rows', 'ritz_power_table', 'readout',
     'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
@@ -98,6 +99,57 @@ def linear_tf32x3(x, w_hi, w_lo, bias=None, relu=False, out=None):
     _lib.check(_lib.load().lnb_linear_tf32x3(_stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo),
                                              _ptr(bias), M, N, K, int(bool(relu)), _ptr(out)),
                'lnb_linear_tf32x3')
+  return out
+
+
+def graph_prepare(L, Q):
+  """Per-forward ELL compression of the dense operators L [B,N,N,E1] and the extents of Q
+  [B,N,K] for the fused convolution kernel.  Returns (ell_val, ell_idx, ell_max, qext)."""
+  _need_cuda(L, Q)
+  L, Q = _f32c(L), _f32c(Q)
+  B, N, _, E1 = L.shape
+  K = Q.shape[2]
+  dev = L.device
+  ell_val = torch.empty((B, E1, N, N), device=dev, dtype=torch.float32)
+  ell_idx = torch.empty((B, E1, N, N), device=dev, dtype=torch.uint8)
+  ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
+  qext = torch.empty((B, 2), device=dev, dtype=torch.int32)
+  with torch.cuda.device(dev):
+    _lib.check(_lib.load().lnb_graph_prepare(_stream(L), _ptr(L), _ptr(Q), B, N, E1, K,
+                                             _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),
+                                             _ptr(qext)), 'lnb_graph_prepare')
+  return ell_val, ell_idx, ell_max, qext
+
+
+def fused_conv_supported(N, Din, K, H, n_short, dense_filter, S=8, E1=7):
+  """Shapes the fused tcgen05 convolution kernel handles (others use the unfused ops);
+  mirrors the checks of lnb_spectral_conv_fused."""
+  if n_short or dense_filter or N > 128 or Din % 32 or K > 32 or H % 4:
+    return False
+  G = 128 // (32 if N <= 32 else (64 if N <= 64 else 128))
+  smem = (98560 + 1024 + 4 * (G * N * (Din + 4) + G * K * Din + G * N * (K | 1) + G * K * S) +
+          4 * G * (E1 + 2) + 16)
+  return smem <= 227 * 1024
+
+
+def spectral_conv_fused(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True):
+  """One fused spectral convolution layer: X [B,N,Din], Q [B,N,K], coeff [B,K,S] diagonal
+  filter coefficients, prep = graph_prepare(L, Q), W [H, (S+E1)*Din] split -> [B,N,H]."""
+  _need_cuda(X, Q, coeff, w_hi, w_lo, bias)
+  X, Q, coeff = _f32c(X), _f32c(Q), _f32c(coeff)
+  ell_val, ell_idx, ell_max, qext = prep
+  B, N, Din = X.shape
+  K = Q.shape[2]
+  S = coeff.shape[2]
+  E1 = ell_val.shape[1]
+  H = w_hi.shape[0]
+  assert w_hi.shape[1] == (S + E1) * Din, (w_hi.shape, S, E1, Din)
+  out = torch.empty((B, N, H), device=X.device, dtype=torch.float32)
+  with torch.cuda.device(X.device):
+    _lib.check(_lib.load().lnb_spectral_conv_fused(
+        _stream(X), _ptr(X), _ptr(Q), _ptr(coeff), _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),
+        _ptr(qext), _ptr(w_hi), _ptr(w_lo), _ptr(bias), B, N, Din, E1, K, S, H, int(bool(relu)),
+        _ptr(out)), 'lnb_spectral_conv_fused')
   return out
 
 

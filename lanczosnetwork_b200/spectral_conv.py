@@ -15,7 +15,8 @@ import torch
 
 from . import ops
 
-__all__ = ['WeightCache', 'dense', 'graph_conv_layer', 'ritz_filter_coefficients']
+__all__ = ['WeightCache', 'GraphContext', 'dense', 'graph_conv_layer', 'graph_conv_layer_unfused',
+           'ritz_filter_coefficients']
 
 
 class WeightCache(object):
@@ -78,9 +79,39 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache):
   return out, table
 
 
-def graph_conv_layer(state, L, Qv, coeff, dense_filter, short_dist, num_long, weight, bias, cache,
+class GraphContext(object):
+  """Layer-invariant per-forward state: the operators, the Ritz / Lanczos vectors and (lazily)
+  their compressed form for the fused kernel."""
+
+  def __init__(self, L, Qv):
+    self.L = L
+    self.Qv = Qv
+    self._prep = None
+
+  def prep(self):
+    if self._prep is None:
+      self._prep = ops.graph_prepare(self.L, self.Qv)
+    return self._prep
+
+
+def graph_conv_layer(state, ctx, coeff, dense_filter, short_dist, num_long, weight, bias, cache,
                      name):
-  """One spectral convolution layer.
+  """One spectral convolution layer: the fused tcgen05 kernel when the shape allows it
+  (LanczosNet-style diagonal filters), otherwise the unfused ops below."""
+  L, Qv = ctx.L, ctx.Qv
+  B, N, Din = state.shape
+  if (num_long > 0 and Qv is not None and
+      ops.fused_conv_supported(N, Din, Qv.shape[2], weight.shape[0], len(short_dist), dense_filter,
+                               num_long, L.shape[3])):
+    w_hi, w_lo = cache.split(name, weight)
+    return ops.spectral_conv_fused(state, Qv, coeff, ctx.prep(), w_hi, w_lo, bias, True)
+  return graph_conv_layer_unfused(state, L, Qv, coeff, dense_filter, short_dist, num_long, weight,
+                                  bias, cache, name)
+
+
+def graph_conv_layer_unfused(state, L, Qv, coeff, dense_filter, short_dist, num_long, weight, bias,
+                             cache, name):
+  """One spectral convolution layer from the general-shape ops.
 
   state [B,N,Din]; L [B,N,N,E1] (channel innermost); Qv [B,N,K] Ritz / Lanczos vectors;
   coeff: [B,K,S] diagonal filter coefficients (LanczosNet) when dense_filter is False,
