@@ -80,6 +80,13 @@ int lnb_batched_gemm(lnb_stream_t stream, const lnb_gemm_desc* desc /* host */);
 int lnb_split_tf32(lnb_stream_t stream, const float* x, int64_t n, float* hi, float* lo);
 int lnb_linear_tf32x3(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
                       const float* bias, int M, int N, int K, int relu, float* C);
+/* Block-diagonal ("grouped") variant: C[:, g*N:(g+1)*N] = act(A[:, g*K:(g+1)*K] @ W_g^T + b_g)
+ * with A [M, groups*K], W stacked [groups*N, K], bias [groups*N], C [M, groups*N].  Used to run
+ * the per-layer Ritz-filter MLPs of all layers (model/lanczos_net.py:47-58,109-113) in one launch
+ * per MLP stage. */
+int lnb_linear_tf32x3_grouped(lnb_stream_t stream, const float* A, const float* W_hi,
+                              const float* W_lo, const float* bias, int M, int groups, int N, int K,
+                              int relu, float* C);
 
 /* ---------------------------------------------------------------------------------------
  * Fused spectral graph-convolution layer (model/lanczos_net.py:157-182):

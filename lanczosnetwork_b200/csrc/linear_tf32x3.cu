@@ -11,13 +11,20 @@
 namespace {
 
 struct RowLoadPolicy {
+  // groups > 1: block-diagonal ("grouped") layer -- column block g of A [M, groups*K] times
+  // W_g [N, K] (stacked [groups*N, K]) into column block g of C [M, groups*N].
   struct Params {
     const float* A;
     const float* bias;
     float* C;
-    int M, N, K, relu;
+    int M, N, K, relu, groups;
   };
-  static __device__ __forceinline__ int n_tiles(const Params& p) { return (p.N + tcg::BN - 1) / tcg::BN; }
+  static __device__ __forceinline__ int tiles_per_group(const Params& p) { return (p.N + tcg::BN - 1) / tcg::BN; }
+  static __device__ __forceinline__ int n_tiles(const Params& p) { return p.groups * tiles_per_group(p); }
+  static __device__ __forceinline__ int w_row0(const Params& p, int n_tile) {
+    const int tpg = tiles_per_group(p);
+    return (n_tile / tpg) * p.N + (n_tile % tpg) * tcg::BN;
+  }
   static __device__ __forceinline__ int num_tiles(const Params& p) {
     return ((p.M + tcg::BM - 1) / tcg::BM) * n_tiles(p);
   }
@@ -25,13 +32,15 @@ struct RowLoadPolicy {
 
   const Params& p;
   const int r, grp;
+  const int lda, ldc;
   const float* arow;
   bool row_ok;
   int row;
   float cur[32];
 
   __device__ RowLoadPolicy(const Params& p_, uint8_t*, int tid)
-      : p(p_), r(tid & 127), grp(tid >> 7), arow(nullptr), row_ok(false), row(0) {}
+      : p(p_), r(tid & 127), grp(tid >> 7), lda(p_.groups * p_.K), ldc(p_.groups * p_.N),
+        arow(nullptr), row_ok(false), row(0) {}
 
   __device__ __forceinline__ void load(int kb, float (&v)[32]) {
 #pragma unroll
@@ -42,23 +51,28 @@ struct RowLoadPolicy {
       v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
   }
-  __device__ __forceinline__ void tile_begin(int m_tile) {
+  __device__ __forceinline__ void tile_begin(int m_tile, int n_tile) {
     row = m_tile * tcg::BM + r;
     row_ok = row < p.M;
-    arow = p.A + (int64_t)(row_ok ? row : 0) * p.K;
+    arow = p.A + (int64_t)(row_ok ? row : 0) * lda + (n_tile / tiles_per_group(p)) * p.K;
     load(grp, cur);
   }
   __device__ __forceinline__ void produce(int kb, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = cur[j];
-    load(kb + 2, cur);          // this group's next k-block (zeros past K)
+    load(kb + tcg::NGROUPS, cur);   // this group's next k-block (zeros past K)
   }
   __device__ __forceinline__ void tile_end() {}
-  __device__ __forceinline__ float* out_row(int n0) const {
-    return row_ok ? p.C + (int64_t)row * p.N + n0 : nullptr;
+  __device__ __forceinline__ float* out_ptr(int n_tile) const {
+    return row_ok ? p.C + (int64_t)row * ldc + w_row0(p, n_tile) : nullptr;
   }
-  __device__ __forceinline__ int out_cols() const { return p.N; }
-  __device__ __forceinline__ const float* bias() const { return p.bias; }
+  __device__ __forceinline__ int cols_valid(int n_tile) const {
+    const int left = p.N - (n_tile % tiles_per_group(p)) * tcg::BN;
+    return left < tcg::BN ? left : tcg::BN;
+  }
+  __device__ __forceinline__ const float* bias_ptr(int n_tile) const {
+    return p.bias ? p.bias + w_row0(p, n_tile) : nullptr;
+  }
   __device__ __forceinline__ bool relu() const { return p.relu != 0; }
 };
 
@@ -66,27 +80,43 @@ constexpr size_t SMEM_BYTES = tcg::CORE_SMEM + 1024;
 
 }  // namespace
 
-extern "C" int lnb_linear_tf32x3(lnb_stream_t stream, const float* A, const float* W_hi,
-                                 const float* W_lo, const float* bias, int M, int N, int K,
-                                 int relu, float* C) {
-  LNB_REQUIRE(A && W_hi && W_lo && C, "linear_tf32x3: null pointer");
-  LNB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "linear_tf32x3: bad dims M=%d N=%d K=%d", M, N, K);
-  LNB_REQUIRE(K % 4 == 0, "linear_tf32x3: K=%d must be a multiple of 4 (16-byte rows)", K);
-  LNB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W_hi & 15) == 0 && ((uintptr_t)W_lo & 15) == 0 &&
-                  ((uintptr_t)C & 15) == 0,
-              "linear_tf32x3: operands must be 16-byte aligned");
+static int launch_linear(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
+                         const float* bias, int M, int N, int K, int groups, int relu, float* C,
+                         const char* who) {
+  LNB_REQUIRE(A && W_hi && W_lo && C, "%s: null pointer", who);
+  LNB_REQUIRE(M >= 0 && N >= 1 && K >= 1 && groups >= 1, "%s: bad dims M=%d N=%d K=%d groups=%d",
+              who, M, N, K, groups);
+  LNB_REQUIRE(K % 4 == 0, "%s: K=%d must be a multiple of 4 (16-byte rows)", who, K);
+  LNB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W_hi & 15) == 0 && ((uintptr_t)W_lo & 15) == 0,
+              "%s: A / W must be 16-byte aligned", who);
   if (M == 0) return LNB_OK;
   CUtensorMap map_hi, map_lo;
-  int rc = tcg::make_weight_map(&map_hi, W_hi, N, K, "linear_tf32x3");
+  int rc = tcg::make_weight_map(&map_hi, W_hi, groups * N, K, who);
   if (rc != LNB_OK) return rc;
-  rc = tcg::make_weight_map(&map_lo, W_lo, N, K, "linear_tf32x3");
+  rc = tcg::make_weight_map(&map_lo, W_lo, groups * N, K, who);
   if (rc != LNB_OK) return rc;
   auto kern = tcg::tc_gemm_kernel<RowLoadPolicy>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-  RowLoadPolicy::Params p{A, bias, C, M, N, K, relu};
-  const int tiles = lnb::ceil_div(M, tcg::BM) * lnb::ceil_div(N, tcg::BN);
+  RowLoadPolicy::Params p{A, bias, C, M, N, K, relu, groups};
+  const int tiles = lnb::ceil_div(M, tcg::BM) * lnb::ceil_div(N, tcg::BN) * groups;
   const int grid = tiles < tcg::sm_count() ? tiles : tcg::sm_count();
   kern<<<grid, tcg::THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_hi, map_lo, p);
   lnb::count_launch();
-  return lnb::finish_launch("linear_tf32x3");
+  return lnb::finish_launch(who);
 }
+
+extern "C" {
+
+int lnb_linear_tf32x3(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
+                      const float* bias, int M, int N, int K, int relu, float* C) {
+  return launch_linear(stream, A, W_hi, W_lo, bias, M, N, K, 1, relu, C, "linear_tf32x3");
+}
+
+int lnb_linear_tf32x3_grouped(lnb_stream_t stream, const float* A, const float* W_hi,
+                              const float* W_lo, const float* bias, int M, int groups, int N, int K,
+                              int relu, float* C) {
+  return launch_linear(stream, A, W_hi, W_lo, bias, M, N, K, groups, relu, C,
+                       "linear_tf32x3_grouped");
+}
+
+}  // extern "C"

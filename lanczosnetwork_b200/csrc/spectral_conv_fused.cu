@@ -101,6 +101,7 @@ struct SpectralPolicy {
     const float* bias;      // [H]
     float* out;             // [B, N, H]
     int B, N, Din, E1, K, S, H, relu, NS;
+    int TCAP;               // ELL entries per (row, channel) staged in shared memory
   };
   static __device__ __forceinline__ int n_tiles(const Params& p) { return (p.H + tcg::BN - 1) / tcg::BN; }
   static __device__ __forceinline__ int num_tiles(const Params& p) {
@@ -119,6 +120,8 @@ struct SpectralPolicy {
   float* Qs;                // [G][N][KP]
   float* Fs;                // [G][K][S]
   int* Es;                  // [G][E1 + 2]  ell_max per channel, n_eff, k_eff
+  float* Ev;                // [G][E1][TCAP][NS] staged ELL values
+  uint8_t* Ei;              // [G][E1][TCAP][NS] staged ELL column indices
   int b;                    // graph of this row (or -1)
   bool valid;
 
@@ -130,6 +133,8 @@ struct SpectralPolicy {
     Qs = Us + (size_t)G * p.K * p.Din;
     Fs = Qs + (size_t)G * p.N * KP;
     Es = reinterpret_cast<int*>(Fs + (size_t)G * p.K * p.S);
+    Ev = reinterpret_cast<float*>(Es + (size_t)G * (p.E1 + 2));
+    Ei = reinterpret_cast<uint8_t*>(Ev + (size_t)G * p.E1 * p.TCAP * p.NS);
   }
 
   static size_t smem_bytes(int N, int Din, int K, int S, int E1, int NS) {
@@ -138,8 +143,11 @@ struct SpectralPolicy {
                 (size_t)G * K * S;
     return fl * 4 + (size_t)G * (E1 + 2) * 4 + 16;
   }
+  static size_t ell_stage_bytes(int E1, int NS, int tcap) {
+    return (size_t)(tcg::BM / NS) * E1 * tcap * NS * 5;
+  }
 
-  __device__ void tile_begin(int m_tile) {
+  __device__ void tile_begin(int m_tile, int /*n_tile*/) {
     const int b0 = m_tile * G;
     b = b0 + g;
     valid = (b < p.B) && (n < p.N);
@@ -171,6 +179,21 @@ struct SpectralPolicy {
       if (b0 + gg < p.B)
         v = (w < p.E1) ? p.ell_max[(b0 + gg) * p.E1 + w] : p.qext[(b0 + gg) * 2 + (w - p.E1)];
       Es[e] = v;
+    }
+    // ELL rows of the tile's graphs (first TCAP entries per row/channel), zero beyond the
+    // channel maximum so the inner loop needs no per-lane guard
+    for (int e = tid; e < G * p.E1 * p.TCAP * p.NS; e += tcg::PRODUCER_THREADS) {
+      const int nn = e % p.NS, t = (e / p.NS) % p.TCAP;
+      const int ch = (e / (p.NS * p.TCAP)) % p.E1, gg = e / (p.NS * p.TCAP * p.E1);
+      float v = 0.f;
+      int ix = 0;
+      if (b0 + gg < p.B && nn < p.N && t < __ldg(p.ell_max + (b0 + gg) * p.E1 + ch)) {
+        const int64_t off = (((int64_t)(b0 + gg) * p.E1 + ch) * p.N + t) * p.N + nn;
+        v = __ldg(p.ell_val + off);
+        ix = __ldg(p.ell_idx + off);
+      }
+      Ev[e] = v;
+      Ei[e] = (uint8_t)ix;
     }
     tcg::producers_sync();
     // ---- U_g = Q_g^T X_g  (K x Din per graph): thread <-> (graph, column), all k in registers
@@ -229,8 +252,24 @@ struct SpectralPolicy {
       const float* val = p.ell_val + ((int64_t)(b * p.E1 + e) * p.N) * p.N + nn;
       const uint8_t* idx = p.ell_idx + ((int64_t)(b * p.E1 + e) * p.N) * p.N + nn;
       const float* xs = Xs + (size_t)g * p.N * XP + d0;
+      const int ts = tmax < p.TCAP ? tmax : p.TCAP;
+      const float* ev = Ev + ((size_t)(g * p.E1 + e) * p.TCAP) * p.NS + n;
+      const uint8_t* ei = Ei + ((size_t)(g * p.E1 + e) * p.TCAP) * p.NS + n;
 #pragma unroll 2
-      for (int t = 0; t < tmax; ++t) {
+      for (int t = 0; t < ts; ++t) {
+        const float a = ev[t * p.NS];
+        const int i = ei[t * p.NS];
+        const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 tt = x4[q];
+          v[4 * q + 0] = fmaf(a, tt.x, v[4 * q + 0]);
+          v[4 * q + 1] = fmaf(a, tt.y, v[4 * q + 1]);
+          v[4 * q + 2] = fmaf(a, tt.z, v[4 * q + 2]);
+          v[4 * q + 3] = fmaf(a, tt.w, v[4 * q + 3]);
+        }
+      }
+      for (int t = ts; t < tmax; ++t) {            // rows denser than the staged capacity
         const float a = (n < p.N) ? __ldg(val + (int64_t)t * p.N) : 0.f;
         const int i = __ldg(idx + (int64_t)t * p.N);
         const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
@@ -246,11 +285,17 @@ struct SpectralPolicy {
     }
   }
   __device__ __forceinline__ void tile_end() {}
-  __device__ __forceinline__ float* out_row(int n0) const {
-    return valid ? p.out + ((int64_t)b * p.N + n) * p.H + n0 : nullptr;
+  static __device__ __forceinline__ int w_row0(const Params&, int n_tile) { return n_tile * tcg::BN; }
+  __device__ __forceinline__ float* out_ptr(int n_tile) const {
+    return valid ? p.out + ((int64_t)b * p.N + n) * p.H + n_tile * tcg::BN : nullptr;
   }
-  __device__ __forceinline__ int out_cols() const { return p.H; }
-  __device__ __forceinline__ const float* bias() const { return p.bias; }
+  __device__ __forceinline__ int cols_valid(int n_tile) const {
+    const int left = p.H - n_tile * tcg::BN;
+    return left < tcg::BN ? left : tcg::BN;
+  }
+  __device__ __forceinline__ const float* bias_ptr(int n_tile) const {
+    return p.bias ? p.bias + n_tile * tcg::BN : nullptr;
+  }
   __device__ __forceinline__ bool relu() const { return p.relu != 0; }
 };
 
@@ -286,7 +331,12 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
   }
   if (B == 0) return LNB_OK;
   const int NS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-  const size_t smem = tcg::CORE_SMEM + 1024 + SpectralPolicy::smem_bytes(N, Din, K, S, E1, NS);
+  size_t smem = tcg::CORE_SMEM + 1024 + SpectralPolicy::smem_bytes(N, Din, K, S, E1, NS);
+  int tcap = 0;
+  if (smem <= 227 * 1024) {
+    while (tcap < 8 && smem + SpectralPolicy::ell_stage_bytes(E1, NS, tcap + 1) <= 227 * 1024) ++tcap;
+    smem += SpectralPolicy::ell_stage_bytes(E1, NS, tcap);
+  }
   if (smem > 227 * 1024) {
     lnb::set_err("spectral_conv_fused: tile state (N=%d, Din=%d, K=%d) needs %zu B of shared memory",
                  N, Din, K, smem);
@@ -301,7 +351,7 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
   auto kern = tcg::tc_gemm_kernel<SpectralPolicy>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   SpectralPolicy::Params p{X, Q, coeff, ell_val, ell_idx, ell_max, qext, bias, out,
-                           B, N, Din, E1, K, S, H, relu, NS};
+                           B, N, Din, E1, K, S, H, relu, NS, tcap};
   const int G = tcg::BM / NS;
   const int tiles = lnb::ceil_div(B, G) * lnb::ceil_div(H, tcg::BN);
   const int grid = tiles < tcg::sm_count() ? tiles : tcg::sm_count();

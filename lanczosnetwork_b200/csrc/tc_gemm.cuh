@@ -9,10 +9,11 @@
 // accumulators -- D_main += A_hi*W_hi and D_corr += A_lo*W_hi + A_hi*W_lo -- and summed in fp32
 // by the epilogue (the small terms no longer add truncation steps to the large accumulator).
 //
-// CTA = 10 warps, 1 CTA / SM, persistent over tiles:
-//   warps 0-3, 4-7  producer groups P0 / P1 (alternate k-blocks; 2 TMEM stages each), then epilogue
-//   warp 8          TMA producer (W tiles)
-//   warp 9          TMEM allocation + single-thread tcgen05.mma issue / commit
+// CTA = 14 warps, 1 CTA / SM, persistent over tiles:
+//   warps 0-11      three producer groups of 4 warps (k-block kb -> group kb % 3, TMEM A stage
+//                   = global k-block count % 4), then epilogue
+//   warp 12         TMA producer (W tiles)
+//   warp 13         TMEM allocation + single-thread tcgen05.mma issue / commit
 // TMEM (512 columns): [0,128) D_main, [128,256) D_corr, [256,512) 4 A stages x (32 hi + 32 lo).
 #pragma once
 #include "common.cuh"
@@ -22,11 +23,13 @@ namespace tcg {
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int NB_STAGES = 3;
-constexpr int NA_STAGES = 4;                       // 2 per producer group
+constexpr int NA_STAGES = 4;                       // TMEM ring of A stages
+constexpr int NGROUPS = 3;                         // producer groups (4 warps each)
 constexpr int TILE_B_BYTES = BN * BK * 4;          // 16 KB per hi or lo tile
 constexpr int TMEM_COLS = 512;
 constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;
-constexpr int PRODUCER_THREADS = 256;
+constexpr int PRODUCER_THREADS = 128 * NGROUPS;
+constexpr int TMA_WARP = 4 * NGROUPS, MMA_WARP = 4 * NGROUPS + 1;
 constexpr int THREADS = PRODUCER_THREADS + 64;
 constexpr int CORE_SMEM = 2 * NB_STAGES * TILE_B_BYTES + 256;   // W ring + barriers/holder
 
@@ -57,19 +60,22 @@ __device__ __forceinline__ Core carve(uint8_t* base) {
   return c;
 }
 
-__device__ __forceinline__ void producers_sync() {   // named barrier 1: the 256 producer threads
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+__device__ __forceinline__ void producers_sync() {   // named barrier 1: all producer threads
+  asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
 }
 
 // Policy contract (all __device__):
 //   struct Params;                                     kernel parameter block (by value)
 //   static int  num_tiles(const Params&), n_tiles(const Params&), num_kblocks(const Params&);
 //   Policy(const Params&, uint8_t* policy_smem, int tid)   constructed by producer threads only
-//   void tile_begin(int m_tile)                        may call producers_sync()
+//   void tile_begin(int m_tile, int n_tile)            may call producers_sync()
 //   void produce(int kb, float (&v)[32])               the 32 A values of this thread's row
 //   void tile_end()                                    after the tile's last produce()
-//   float* out_row(int n0)                             output pointer of this row (nullptr: skip)
-//   int out_cols() ; const float* bias(); bool relu()
+//   static int w_row0(const Params&, int n_tile)       first W row (TMA coordinate) of the tile
+//   float* out_ptr(int n_tile)                         this row's output for the tile's first
+//                                                      column (nullptr: skip the row)
+//   int cols_valid(int n_tile)                         number of valid output columns in the tile
+//   const float* bias_ptr(int n_tile)  (may be null);  bool relu()
 template <class Policy>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
@@ -85,11 +91,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int n_tiles = Policy::n_tiles(p);
   const int nkb = Policy::num_kblocks(p);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == TMA_WARP && lane == 0) {
     tc05::tma_prefetch_desc(&map_hi);
     tc05::tma_prefetch_desc(&map_lo);
   }
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < NB_STAGES; ++s) { tc05::mbar_init(&c.b_full[s], 1); tc05::mbar_init(&c.b_empty[s], 1); }
       for (int s = 0; s < NA_STAGES; ++s) { tc05::mbar_init(&c.a_full[s], 128); tc05::mbar_init(&c.a_empty[s], 1); }
@@ -105,21 +111,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   tc05::fence_after_thread_sync();
   const uint32_t tmem_base = *c.tmem_holder;
 
-  if (warp < 8) {
+  if (warp < TMA_WARP) {
     // ================================ producers + epilogue ================================
-    const int grp = warp >> 2;                       // 0 / 1
+    const int grp = warp >> 2;                       // producer group
     const int wq = warp & 3;                         // TMEM lane quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
     Policy pol(p, policy_smem, tid);
-    uint32_t cnt = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t gk0 = 0, tcount = 0;                    // gk0: global k-block count at tile start
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount, gk0 += nkb) {
       const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
-      pol.tile_begin(m_tile);
-      for (int kb = grp; kb < nkb; kb += 2, ++cnt) {
+      pol.tile_begin(m_tile, n_tile);
+      for (int kb = grp; kb < nkb; kb += NGROUPS) {
         float v[32];
         pol.produce(kb, v);
-        const uint32_t sa = grp * 2 + (cnt & 1u);
-        tc05::mbar_wait(&c.a_empty[sa], ((cnt >> 1) & 1u) ^ 1u);
+        const uint32_t gk = gk0 + kb;
+        const uint32_t sa = gk % NA_STAGES;
+        tc05::mbar_wait(&c.a_empty[sa], ((gk / NA_STAGES) & 1u) ^ 1u);
         tc05::fence_after_thread_sync();
         uint32_t part[32];
         const uint32_t a_hi = lane_addr + COL_A + sa * 64;
@@ -134,30 +141,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         tc05::mbar_arrive(&c.a_full[sa]);
       }
       pol.tile_end();
-      // ---- epilogue: this group owns accumulator columns [grp*64, grp*64+64) ----
+      // ---- epilogue: 32-column chunk cc belongs to group cc % NGROUPS ----
       tc05::mbar_wait(c.acc_full, tcount & 1u);
       tc05::fence_after_thread_sync();
-      const int n0 = n_tile * BN;
-      float* orow = pol.out_row(n0);
-      const int ncols = pol.out_cols();
-      const float* bias = pol.bias();
+      float* orow = pol.out_ptr(n_tile);
+      const int ncols = pol.cols_valid(n_tile);
+      const float* bias = pol.bias_ptr(n_tile);
       const bool relu = pol.relu();
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col = grp * 64 + cc * 32;
+      for (int cc = grp; cc < BN / 32; cc += NGROUPS) {
+        const int col = cc * 32;
         uint32_t vm[32], vc[32];
         tc05::tmem_ld_32x32(lane_addr + COL_MAIN + col, vm);
         tc05::tmem_ld_32x32(lane_addr + COL_CORR + col, vc);
         tc05::tmem_wait_ld();
-        const int nb = n0 + col;
-        if (orow != nullptr && nb < ncols) {
-          const bool vec_ok = (ncols % 4) == 0;
+        if (orow != nullptr && col < ncols) {
+          const bool vec_ok = (reinterpret_cast<uintptr_t>(orow + col) & 15) == 0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int n = nb + j + u;
+              const int n = col + j + u;
               float x = __uint_as_float(vm[j + u]) + __uint_as_float(vc[j + u]);
               if (n < ncols) {
                 if (bias) x += __ldg(bias + n);
@@ -165,12 +170,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
               }
               o[u] = x;
             }
-            if (vec_ok && nb + j + 3 < ncols) {
+            if (vec_ok && col + j + 3 < ncols) {
               *reinterpret_cast<float4*>(orow + col + j) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (nb + j + u < ncols) orow[col + j + u] = o[u];
+                if (col + j + u < ncols) orow[col + j + u] = o[u];
             }
           }
         }
@@ -178,12 +183,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       tc05::fence_before_thread_sync();
       tc05::mbar_arrive(c.acc_empty);
     }
-  } else if (warp == 8) {
+  } else if (warp == TMA_WARP) {
     // ================================ TMA producer (W tiles) ==============================
     if (lane == 0) {
       uint32_t cnt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * BN;
+        const int n0 = Policy::w_row0(p, tile % n_tiles);
         for (int kb = 0; kb < nkb; ++kb, ++cnt) {
           const uint32_t sb = cnt % NB_STAGES;
           tc05::mbar_wait(&c.b_empty[sb], ((cnt / NB_STAGES) & 1u) ^ 1u);
@@ -197,16 +202,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
     // ================================ MMA issuer ==========================================
     if (lane == 0) {
       constexpr uint32_t idesc = tc05::umma_idesc_tf32(BM, BN);
-      uint32_t cnt_b = 0, cnt_a[2] = {0, 0}, tcount = 0;
+      uint32_t cnt_b = 0, tcount = 0;
       const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
         tc05::mbar_wait(c.acc_empty, (tcount & 1u) ^ 1u);     // epilogue of the previous tile done
         tc05::fence_after_thread_sync();
         for (int kb = 0; kb < nkb; ++kb, ++cnt_b) {
-          const int g = kb & 1;
-          const uint32_t sa = g * 2 + (cnt_a[g] & 1u);
-          const uint32_t pha = (cnt_a[g] >> 1) & 1u;
-          ++cnt_a[g];
+          const uint32_t sa = cnt_b % NA_STAGES;       // cnt_b == global k-block count
+          const uint32_t pha = (cnt_b / NA_STAGES) & 1u;
           const uint32_t sb = cnt_b % NB_STAGES;
           tc05::mbar_wait(&c.b_full[sb], (cnt_b / NB_STAGES) & 1u);
           tc05::mbar_wait(&c.a_full[sa], pha);
@@ -231,7 +234,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
 
   tc05::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     __syncwarp();
     tc05::tmem_dealloc(tmem_base, TMEM_COLS);
   }

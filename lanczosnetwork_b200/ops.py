@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import GemmDesc
 
 __all__ = [
-    'bgemm', 'split_tf32', 'linear_tf32x3', 'graph_prepare', 'spectral_conv_fused',
+    'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
     'fused_conv_supported', 'embedding_rows', 'ritz_power_table', 'readout',
     'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
@@ -99,6 +99,24 @@ def linear_tf32x3(x, w_hi, w_lo, bias=None, relu=False, out=None):
     _lib.check(_lib.load().lnb_linear_tf32x3(_stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo),
                                              _ptr(bias), M, N, K, int(bool(relu)), _ptr(out)),
                'lnb_linear_tf32x3')
+  return out
+
+
+def linear_tf32x3_grouped(x, w_hi, w_lo, bias, groups, relu=False):
+  """Block-diagonal layer: out[:, g*N:(g+1)*N] = act(x[:, g*K:(g+1)*K] @ W_g^T + b_g) with
+  x [M, groups*K], w_hi/w_lo [groups*N, K] (stacked), bias [groups*N]."""
+  _need_cuda(x, w_hi, w_lo, bias)
+  x = _f32c(x)
+  M = x.shape[0]
+  K = w_hi.shape[1]
+  N = w_hi.shape[0] // groups
+  assert x.shape[1] == groups * K and w_hi.shape[0] == groups * N
+  out = torch.empty((M, groups * N), device=x.device, dtype=torch.float32)
+  with torch.cuda.device(x.device):
+    _lib.check(_lib.load().lnb_linear_tf32x3_grouped(_stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo),
+                                                     _ptr(bias), M, groups, N, K,
+                                                     int(bool(relu)), _ptr(out)),
+               'lnb_linear_tf32x3_grouped')
   return out
 
 

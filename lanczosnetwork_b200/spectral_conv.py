@@ -39,6 +39,19 @@ class WeightCache(object):
       self._store[key] = hit
     return hit[1], hit[2]
 
+  def split_stacked(self, name, weights, biases):
+    """(hi, lo, bias) of torch.cat(weights, 0) / torch.cat(biases) -- the stacked form the
+    grouped dense kernel consumes (one launch for the same MLP stage of every layer)."""
+    dev = weights[0].device
+    key = (name, dev.index)
+    tag = tuple((w.data_ptr(), w._version) for w in list(weights) + list(biases))
+    hit = self._store.get(key)
+    if hit is None or hit[0] != tag:
+      hi, lo = ops.split_tf32(torch.cat([w.detach() for w in weights], dim=0))
+      hit = (tag, hi, lo, torch.cat([b.detach() for b in biases], dim=0).contiguous())
+      self._store[key] = hit
+    return hit[1], hit[2], hit[3]
+
   def clear(self):
     self._store.clear()
 
@@ -62,20 +75,36 @@ def dense(x2d, weight, bias, relu, cache, name):
 
 def ritz_filter_coefficients(D, powers, mlp_layers, cache):
   """Per-layer multi-scale coefficients of the Ritz values (model/lanczos_net.py:109-113,
-  146-149).  The MLP input does not depend on the layer state, so the table of powers is
-  built once.  mlp_layers: list over layers of [(name,W,b) x 4] or None for the plain-power filter.
-  Returns list over layers of [B,K,S] tensors."""
+  146-149).  The MLP input does not depend on the layer state, so the power table is built once
+  and every MLP stage runs for ALL layers in one launch: stage 0 as a dense layer with the
+  layers' first weights stacked along the output dimension, stages 1-3 as block-diagonal
+  (grouped) dense layers.  mlp_layers: list over layers of [(name, W, b) x 4] or None for the
+  plain-power filter.  Returns (list over layers of [B,K,S] tensors or None, table [B,K,S])."""
   B, K = D.shape
+  S = len(powers)
   table = ops.ritz_power_table(D, powers)            # [B,K,S]
   if mlp_layers is None:
     return None, table
-  flat = table.reshape(B * K, len(powers))
+  nl = len(mlp_layers)
+  flat = table.reshape(B * K, S)
+  if S % 4 == 0 and mlp_layers[0][0][1].shape[0] % 4 == 0:
+    h = flat
+    for stage in range(4):
+      ws = [mlp_layers[l][stage][1] for l in range(nl)]
+      bs = [mlp_layers[l][stage][2] for l in range(nl)]
+      w_hi, w_lo, bias = cache.split_stacked('spectral_filter.*.%d' % (2 * stage), ws, bs)
+      if stage == 0:
+        h = ops.linear_tf32x3(h, w_hi, w_lo, bias, True)               # shared input
+      else:
+        h = ops.linear_tf32x3_grouped(h, w_hi, w_lo, bias, nl, stage < 3)
+    coeff = h.reshape(B, K, nl, S).permute(2, 0, 1, 3).contiguous()     # [layers,B,K,S]
+    return [coeff[l] for l in range(nl)], table
   out = []
   for params in mlp_layers:
     h = flat
     for i, (name, w, b) in enumerate(params):
       h = dense(h, w, b, i < len(params) - 1, cache, name)
-    out.append(h.reshape(B, K, len(powers)))
+    out.append(h.reshape(B, K, S))
   return out, table
 
 
