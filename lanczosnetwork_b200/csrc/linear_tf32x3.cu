@@ -21,14 +21,28 @@ struct RowLoadPolicy {
   };
   static __device__ __forceinline__ int tiles_per_group(const Params& p) { return (p.N + tcg::BN - 1) / tcg::BN; }
   static __device__ __forceinline__ int n_tiles(const Params& p) { return p.groups * tiles_per_group(p); }
-  static __device__ __forceinline__ int w_row0(const Params& p, int n_tile) {
-    const int tpg = tiles_per_group(p);
-    return (n_tile / tpg) * p.N + (n_tile % tpg) * tcg::BN;
-  }
   static __device__ __forceinline__ int num_tiles(const Params& p) {
     return ((p.M + tcg::BM - 1) / tcg::BM) * n_tiles(p);
   }
-  static __device__ __forceinline__ int num_kblocks(const Params& p) { return (p.K + tcg::BK - 1) / tcg::BK; }
+  static __device__ __forceinline__ int num_steps(const Params& p, int cta, int ncta) {
+    const int t = num_tiles(p);
+    return t > cta ? (t - cta + ncta - 1) / ncta : 0;
+  }
+  static __device__ __forceinline__ void decode(const Params& p, int cta, int ncta, int it,
+                                                int& m_tile, int& sub) {
+    const int tile = cta + it * ncta, nt = n_tiles(p);
+    m_tile = tile / nt;
+    sub = tile % nt;
+  }
+  static __device__ __forceinline__ int num_kblocks(const Params& p, int) { return (p.K + tcg::BK - 1) / tcg::BK; }
+  static __device__ __forceinline__ int w_row0(const Params& p, int sub) {
+    const int tpg = tiles_per_group(p);
+    return (sub / tpg) * p.N + (sub % tpg) * tcg::BN;
+  }
+  static __device__ __forceinline__ void w_coords(const Params& p, int sub, int kb, int& col0, int& row0) {
+    col0 = kb * tcg::BK;
+    row0 = w_row0(p, sub);
+  }
 
   const Params& p;
   const int r, grp;
@@ -51,29 +65,24 @@ struct RowLoadPolicy {
       v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
   }
-  __device__ __forceinline__ void tile_begin(int m_tile, int n_tile) {
+  __device__ __forceinline__ void step_begin(int m_tile, int sub) {
     row = m_tile * tcg::BM + r;
     row_ok = row < p.M;
-    arow = p.A + (int64_t)(row_ok ? row : 0) * lda + (n_tile / tiles_per_group(p)) * p.K;
+    arow = p.A + (int64_t)(row_ok ? row : 0) * lda + (sub / tiles_per_group(p)) * p.K;
     load(grp, cur);
   }
-  __device__ __forceinline__ void produce(int kb, float (&v)[32]) {
+  __device__ __forceinline__ void produce(int, int kb, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = cur[j];
     load(kb + tcg::NGROUPS, cur);   // this group's next k-block (zeros past K)
   }
-  __device__ __forceinline__ void tile_end() {}
-  __device__ __forceinline__ float* out_ptr(int n_tile) const {
-    return row_ok ? p.C + (int64_t)row * ldc + w_row0(p, n_tile) : nullptr;
+  __device__ __forceinline__ void store(int sub, int col, const float (&x)[32]) {
+    const int left = p.N - (sub % tiles_per_group(p)) * tcg::BN;
+    const int w0 = w_row0(p, sub);
+    tcg::store_row_chunk(row_ok ? p.C + (int64_t)row * ldc + w0 : nullptr,
+                         left < tcg::BN ? left : tcg::BN, p.bias ? p.bias + w0 : nullptr,
+                         p.relu != 0, col, x);
   }
-  __device__ __forceinline__ int cols_valid(int n_tile) const {
-    const int left = p.N - (n_tile % tiles_per_group(p)) * tcg::BN;
-    return left < tcg::BN ? left : tcg::BN;
-  }
-  __device__ __forceinline__ const float* bias_ptr(int n_tile) const {
-    return p.bias ? p.bias + w_row0(p, n_tile) : nullptr;
-  }
-  __device__ __forceinline__ bool relu() const { return p.relu != 0; }
 };
 
 constexpr size_t SMEM_BYTES = tcg::CORE_SMEM + 1024;

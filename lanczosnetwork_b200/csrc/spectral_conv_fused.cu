@@ -89,6 +89,15 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
 }
 
 // --------------------------------------------------------------------------------------------
+// Two accumulator lifetimes ("steps") per tile of G graphs:
+//   step 0  Z_g = sum_s (f_s . U_g) W_s^T      rows = (graph, Ritz index k): the producer only
+//           scales rows of U_g = V_g^T X_g (staged in smem) by the filter coefficient -- the
+//           N x N filters and even the per-node long-scale messages never exist; the result
+//           (K x H per graph) is drained to shared memory;
+//   step 1  E = sum_e (L_e X_g) W_e^T          rows = (graph, node): sparse ELL rows times X_g;
+//           epilogue: out = ReLU(E + V_g Z_g + b).
+// Algebra: sum_s V diag(f_s) V^T X W_s^T = V [ sum_s diag(f_s) (V^T X) W_s^T ].
+// --------------------------------------------------------------------------------------------
 struct SpectralPolicy {
   struct Params {
     const float* X;         // [B, N, Din]
@@ -103,175 +112,182 @@ struct SpectralPolicy {
     int B, N, Din, E1, K, S, H, relu, NS;
     int TCAP;               // ELL entries per (row, channel) staged in shared memory
   };
-  static __device__ __forceinline__ int n_tiles(const Params& p) { return (p.H + tcg::BN - 1) / tcg::BN; }
-  static __device__ __forceinline__ int num_tiles(const Params& p) {
+  static __device__ __forceinline__ int m_tiles(const Params& p) {
     const int G = tcg::BM / p.NS;
-    return ((p.B + G - 1) / G) * n_tiles(p);
+    return (p.B + G - 1) / G;
   }
-  static __device__ __forceinline__ int num_kblocks(const Params& p) {
-    return (p.S + p.E1) * p.Din / tcg::BK;
+  static __device__ __forceinline__ int num_steps(const Params& p, int cta, int ncta) {
+    const int t = m_tiles(p);
+    const int mine = t > cta ? (t - cta + ncta - 1) / ncta : 0;
+    return p.S > 0 ? 2 * mine : mine;
+  }
+  static __device__ __forceinline__ void decode(const Params& p, int cta, int ncta, int it,
+                                                int& m_tile, int& sub) {
+    if (p.S > 0) { m_tile = cta + (it >> 1) * ncta; sub = it & 1; }
+    else { m_tile = cta + it * ncta; sub = 1; }
+  }
+  static __device__ __forceinline__ int num_kblocks(const Params& p, int sub) {
+    return (sub == 0 ? p.S : p.E1) * p.Din / tcg::BK;
+  }
+  static __device__ __forceinline__ void w_coords(const Params& p, int sub, int kb, int& col0, int& row0) {
+    col0 = (sub == 0 ? 0 : p.S * p.Din) + kb * tcg::BK;
+    row0 = 0;
   }
 
   const Params& p;
-  const int tid, r, g, n;   // row in tile, graph slot, node
-  const int G, XP, KP;      // slots per tile, padded X row stride, padded Q row stride
+  const int tid, r;
+  const int N, Din, K, S, E1, H, NS, TCAP;   // hot parameters in registers
+  const int G, XP, UP, ZP, KP;               // slots per tile, padded row strides
   float* Xs;                // [G][N][XP]
-  float* Us;                // [G][K][Din]
+  float* UZ;                // U_g [G][K][UP] during step 0, Z_g [G][K][ZP] afterwards
   float* Qs;                // [G][N][KP]
   float* Fs;                // [G][K][S]
   int* Es;                  // [G][E1 + 2]  ell_max per channel, n_eff, k_eff
   float* Ev;                // [G][E1][TCAP][NS] staged ELL values
   uint8_t* Ei;              // [G][E1][TCAP][NS] staged ELL column indices
-  int b;                    // graph of this row (or -1)
-  bool valid;
+  int b0;                   // first graph of the tile
 
   __device__ SpectralPolicy(const Params& p_, uint8_t* smem, int tid_)
-      : p(p_), tid(tid_), r(tid_ & 127), g((tid_ & 127) / p_.NS), n((tid_ & 127) % p_.NS),
-        G(tcg::BM / p_.NS), XP(p_.Din + 4), KP(p_.K | 1), b(-1), valid(false) {
+      : p(p_), tid(tid_), r(tid_ & 127), N(p_.N), Din(p_.Din), K(p_.K), S(p_.S), E1(p_.E1),
+        H(p_.H), NS(p_.NS), TCAP(p_.TCAP), G(tcg::BM / p_.NS), XP(p_.Din + 4), UP(p_.Din + 4),
+        ZP(p_.H + 4), KP(p_.K | 1), b0(0) {
     Xs = reinterpret_cast<float*>(smem);
-    Us = Xs + (size_t)G * p.N * XP;
-    Qs = Us + (size_t)G * p.K * p.Din;
-    Fs = Qs + (size_t)G * p.N * KP;
-    Es = reinterpret_cast<int*>(Fs + (size_t)G * p.K * p.S);
-    Ev = reinterpret_cast<float*>(Es + (size_t)G * (p.E1 + 2));
-    Ei = reinterpret_cast<uint8_t*>(Ev + (size_t)G * p.E1 * p.TCAP * p.NS);
+    UZ = Xs + (size_t)G * N * XP;
+    Qs = UZ + (size_t)G * K * ((Din > H ? Din : H) + 4);
+    Fs = Qs + (size_t)G * N * KP;
+    Es = reinterpret_cast<int*>(Fs + (size_t)G * K * S);
+    Ev = reinterpret_cast<float*>(Es + (size_t)G * (E1 + 2));
+    Ei = reinterpret_cast<uint8_t*>(Ev + (size_t)G * E1 * TCAP * NS);
   }
 
-  static size_t smem_bytes(int N, int Din, int K, int S, int E1, int NS) {
+  static size_t smem_bytes(int N, int Din, int K, int S, int E1, int H, int NS) {
     const int G = tcg::BM / NS;
-    size_t fl = (size_t)G * N * (Din + 4) + (size_t)G * K * Din + (size_t)G * N * (K | 1) +
-                (size_t)G * K * S;
+    size_t fl = (size_t)G * N * (Din + 4) + (size_t)G * K * ((Din > H ? Din : H) + 4) +
+                (size_t)G * N * (K | 1) + (size_t)G * K * S;
     return fl * 4 + (size_t)G * (E1 + 2) * 4 + 16;
   }
   static size_t ell_stage_bytes(int E1, int NS, int tcap) {
     return (size_t)(tcg::BM / NS) * E1 * tcap * NS * 5;
   }
 
-  __device__ void tile_begin(int m_tile, int /*n_tile*/) {
-    const int b0 = m_tile * G;
-    b = b0 + g;
-    valid = (b < p.B) && (n < p.N);
-    if (b >= p.B) b = -1;
-    tcg::producers_sync();                       // previous tile's readers are done
-    // ---- stage X, Q, filter coefficients, extents of the G graphs --------------------------
-    const int dv = p.Din / 4;
-    for (int e = tid; e < G * p.N * dv; e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (p.N * dv), rem = e % (p.N * dv);
+  __device__ void step_begin(int m_tile, int sub) {
+    tcg::producers_sync();              // previous step's smem readers / Z writers are done
+    if (sub == 1 && S > 0) return;      // tile state was staged by step 0
+    b0 = m_tile * G;
+    // ---- stage X, Q, filter coefficients, extents, ELL rows of the G graphs ---------------
+    const int dv = Din / 4;
+    for (int e = tid; e < G * N * dv; e += tcg::PRODUCER_THREADS) {
+      const int gg = e / (N * dv), rem = e % (N * dv);
       const int nn = rem / dv, q4 = rem % dv;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (b0 + gg < p.B)
-        v = __ldg(reinterpret_cast<const float4*>(p.X + ((int64_t)(b0 + gg) * p.N + nn) * p.Din) + q4);
-      *reinterpret_cast<float4*>(Xs + ((size_t)gg * p.N + nn) * XP + 4 * q4) = v;
+        v = __ldg(reinterpret_cast<const float4*>(p.X + ((int64_t)(b0 + gg) * N + nn) * Din) + q4);
+      *reinterpret_cast<float4*>(Xs + ((size_t)gg * N + nn) * XP + 4 * q4) = v;
     }
-    for (int e = tid; e < G * p.N * p.K; e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (p.N * p.K), rem = e % (p.N * p.K);
-      const int nn = rem / p.K, kk = rem % p.K;
-      Qs[((size_t)gg * p.N + nn) * KP + kk] =
-          (b0 + gg < p.B) ? __ldg(p.Q + ((int64_t)(b0 + gg) * p.N + nn) * p.K + kk) : 0.f;
+    for (int e = tid; e < G * N * K; e += tcg::PRODUCER_THREADS) {
+      const int gg = e / (N * K), rem = e % (N * K);
+      const int nn = rem / K, kk = rem % K;
+      Qs[((size_t)gg * N + nn) * KP + kk] =
+          (b0 + gg < p.B) ? __ldg(p.Q + ((int64_t)(b0 + gg) * N + nn) * K + kk) : 0.f;
     }
-    for (int e = tid; e < G * p.K * p.S; e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (p.K * p.S);
-      Fs[e] = (b0 + gg < p.B) ? __ldg(p.coeff + (int64_t)(b0 + gg) * p.K * p.S + e % (p.K * p.S)) : 0.f;
+    for (int e = tid; e < G * K * S; e += tcg::PRODUCER_THREADS) {
+      const int gg = e / (K * S);
+      Fs[e] = (b0 + gg < p.B) ? __ldg(p.coeff + (int64_t)(b0 + gg) * K * S + e % (K * S)) : 0.f;
     }
-    for (int e = tid; e < G * (p.E1 + 2); e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (p.E1 + 2), w = e % (p.E1 + 2);
+    for (int e = tid; e < G * (E1 + 2); e += tcg::PRODUCER_THREADS) {
+      const int gg = e / (E1 + 2), w = e % (E1 + 2);
       int v = 0;
       if (b0 + gg < p.B)
-        v = (w < p.E1) ? p.ell_max[(b0 + gg) * p.E1 + w] : p.qext[(b0 + gg) * 2 + (w - p.E1)];
+        v = (w < E1) ? p.ell_max[(b0 + gg) * E1 + w] : p.qext[(b0 + gg) * 2 + (w - E1)];
       Es[e] = v;
     }
-    // ELL rows of the tile's graphs (first TCAP entries per row/channel), zero beyond the
-    // channel maximum so the inner loop needs no per-lane guard
-    for (int e = tid; e < G * p.E1 * p.TCAP * p.NS; e += tcg::PRODUCER_THREADS) {
-      const int nn = e % p.NS, t = (e / p.NS) % p.TCAP;
-      const int ch = (e / (p.NS * p.TCAP)) % p.E1, gg = e / (p.NS * p.TCAP * p.E1);
+    // first TCAP ELL entries per row/channel, zero beyond the channel maximum
+    for (int e = tid; e < G * E1 * TCAP * NS; e += tcg::PRODUCER_THREADS) {
+      const int nn = e % NS, t = (e / NS) % TCAP;
+      const int ch = (e / (NS * TCAP)) % E1, gg = e / (NS * TCAP * E1);
       float v = 0.f;
       int ix = 0;
-      if (b0 + gg < p.B && nn < p.N && t < __ldg(p.ell_max + (b0 + gg) * p.E1 + ch)) {
-        const int64_t off = (((int64_t)(b0 + gg) * p.E1 + ch) * p.N + t) * p.N + nn;
+      if (b0 + gg < p.B && nn < N && t < __ldg(p.ell_max + (b0 + gg) * E1 + ch)) {
+        const int64_t off = (((int64_t)(b0 + gg) * E1 + ch) * N + t) * N + nn;
         v = __ldg(p.ell_val + off);
         ix = __ldg(p.ell_idx + off);
       }
       Ev[e] = v;
       Ei[e] = (uint8_t)ix;
     }
+    if (S == 0) { tcg::producers_sync(); return; }
     tcg::producers_sync();
     // ---- U_g = Q_g^T X_g  (K x Din per graph): thread <-> (graph, column), all k in registers
-    for (int pr = tid; pr < G * p.Din; pr += tcg::PRODUCER_THREADS) {
-      const int gg = pr / p.Din, d = pr % p.Din;
-      const int n_eff = Es[gg * (p.E1 + 2) + p.E1];
+    for (int pr = tid; pr < G * Din; pr += tcg::PRODUCER_THREADS) {
+      const int gg = pr / Din, d = pr % Din;
+      const int n_eff = Es[gg * (E1 + 2) + E1];
       float acc[KMAX];
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-      const float* xs = Xs + (size_t)gg * p.N * XP + d;
-      const float* qs = Qs + (size_t)gg * p.N * KP;
+      const float* xs = Xs + (size_t)gg * N * XP + d;
+      const float* qs = Qs + (size_t)gg * N * KP;
       for (int nn = 0; nn < n_eff; ++nn) {
         const float x = xs[(size_t)nn * XP];
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
-          if (k < p.K) acc[k] = fmaf(qs[nn * KP + k], x, acc[k]);
+          if (k < K) acc[k] = fmaf(qs[nn * KP + k], x, acc[k]);
       }
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < p.K) Us[((size_t)gg * p.K + k) * p.Din + d] = acc[k];
+        if (k < K) UZ[((size_t)gg * K + k) * UP + d] = acc[k];
     }
     tcg::producers_sync();
   }
 
-  __device__ __forceinline__ void produce(int kb, float (&v)[32]) {
+  __device__ __forceinline__ void produce(int sub, int kb, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
     const int j0 = kb * tcg::BK;
-    const int c = j0 / p.Din, d0 = j0 % p.Din;
-    if (b < 0) return;                            // warp-uniform: a warp never straddles graphs
-    const int* es = Es + g * (p.E1 + 2);
-    if (c < p.S) {
-      // long scale s = c:  row n of (Q * f_s) times U_g[:, d0:d0+32]
-      const int k_eff = es[p.E1 + 1];
-      const float* qrow = Qs + ((size_t)g * p.N + (n < p.N ? n : 0)) * KP;
-      const float* f = Fs + (size_t)g * p.K * p.S + c;
-      const float* u = Us + (size_t)g * p.K * p.Din + d0;
-#pragma unroll 2
-      for (int i = 0; i < k_eff; ++i) {
-        const float a = (n < p.N) ? qrow[i] * f[i * p.S] : 0.f;
-        const float4* u4 = reinterpret_cast<const float4*>(u + (size_t)i * p.Din);
+    if (sub == 0) {
+      // row = (graph r/32, Ritz index r%32): f[k,s] * U_g[k, d0:d0+32]
+      const int g0 = r >> 5, k = r & 31;
+      if (g0 >= G || b0 + g0 >= p.B || k >= K) return;
+      const int s = j0 / Din, d0 = j0 % Din;
+      const float f = Fs[((size_t)g0 * K + k) * S + s];
+      const float4* u4 = reinterpret_cast<const float4*>(UZ + ((size_t)g0 * K + k) * UP + d0);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = u4[q];
-          v[4 * q + 0] = fmaf(a, t.x, v[4 * q + 0]);
-          v[4 * q + 1] = fmaf(a, t.y, v[4 * q + 1]);
-          v[4 * q + 2] = fmaf(a, t.z, v[4 * q + 2]);
-          v[4 * q + 3] = fmaf(a, t.w, v[4 * q + 3]);
-        }
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = u4[q];
+        v[4 * q + 0] = f * t.x; v[4 * q + 1] = f * t.y; v[4 * q + 2] = f * t.z; v[4 * q + 3] = f * t.w;
       }
-    } else {
-      // edge type e = c - S: sparse row of L_e (ELL) times X_g[:, d0:d0+32]
-      const int e = c - p.S;
-      const int tmax = es[e];
-      const int nn = (n < p.N) ? n : 0;
-      const float* val = p.ell_val + ((int64_t)(b * p.E1 + e) * p.N) * p.N + nn;
-      const uint8_t* idx = p.ell_idx + ((int64_t)(b * p.E1 + e) * p.N) * p.N + nn;
-      const float* xs = Xs + (size_t)g * p.N * XP + d0;
-      const int ts = tmax < p.TCAP ? tmax : p.TCAP;
-      const float* ev = Ev + ((size_t)(g * p.E1 + e) * p.TCAP) * p.NS + n;
-      const uint8_t* ei = Ei + ((size_t)(g * p.E1 + e) * p.TCAP) * p.NS + n;
+      return;
+    }
+    // edge type e: sparse row of L_e (ELL) times X_g[:, d0:d0+32]; row = (graph r/NS, node r%NS)
+    const int g = r / NS, n = r % NS;
+    const int b = b0 + g;
+    if (b >= p.B) return;                         // warp-uniform: a warp never straddles graphs
+    const int e = j0 / Din, d0 = j0 % Din;
+    const int tmax = Es[g * (E1 + 2) + e];
+    const float* xs = Xs + (size_t)g * N * XP + d0;
+    const int ts = tmax < TCAP ? tmax : TCAP;
+    const float* ev = Ev + ((size_t)(g * E1 + e) * TCAP) * NS + n;
+    const uint8_t* ei = Ei + ((size_t)(g * E1 + e) * TCAP) * NS + n;
 #pragma unroll 2
-      for (int t = 0; t < ts; ++t) {
-        const float a = ev[t * p.NS];
-        const int i = ei[t * p.NS];
-        const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
+    for (int t = 0; t < ts; ++t) {
+      const float a = ev[t * NS];
+      const int i = ei[t * NS];
+      const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 tt = x4[q];
-          v[4 * q + 0] = fmaf(a, tt.x, v[4 * q + 0]);
-          v[4 * q + 1] = fmaf(a, tt.y, v[4 * q + 1]);
-          v[4 * q + 2] = fmaf(a, tt.z, v[4 * q + 2]);
-          v[4 * q + 3] = fmaf(a, tt.w, v[4 * q + 3]);
-        }
+      for (int q = 0; q < 8; ++q) {
+        const float4 tt = x4[q];
+        v[4 * q + 0] = fmaf(a, tt.x, v[4 * q + 0]);
+        v[4 * q + 1] = fmaf(a, tt.y, v[4 * q + 1]);
+        v[4 * q + 2] = fmaf(a, tt.z, v[4 * q + 2]);
+        v[4 * q + 3] = fmaf(a, tt.w, v[4 * q + 3]);
       }
-      for (int t = ts; t < tmax; ++t) {            // rows denser than the staged capacity
-        const float a = (n < p.N) ? __ldg(val + (int64_t)t * p.N) : 0.f;
-        const int i = __ldg(idx + (int64_t)t * p.N);
+    }
+    if (ts < tmax) {                               // rows denser than the staged capacity
+      const int nn = (n < N) ? n : 0;
+      const float* val = p.ell_val + ((int64_t)(b * E1 + e) * N) * N + nn;
+      const uint8_t* idx = p.ell_idx + ((int64_t)(b * E1 + e) * N) * N + nn;
+      for (int t = ts; t < tmax; ++t) {
+        const float a = (n < N) ? __ldg(val + (int64_t)t * N) : 0.f;
+        const int i = __ldg(idx + (int64_t)t * N);
         const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -284,19 +300,44 @@ struct SpectralPolicy {
       }
     }
   }
-  __device__ __forceinline__ void tile_end() {}
-  static __device__ __forceinline__ int w_row0(const Params&, int n_tile) { return n_tile * tcg::BN; }
-  __device__ __forceinline__ float* out_ptr(int n_tile) const {
-    return valid ? p.out + ((int64_t)b * p.N + n) * p.H + n_tile * tcg::BN : nullptr;
+
+  __device__ __forceinline__ void store(int sub, int col, float (&x)[32]) {
+    if (sub == 0) {
+      // drain Z_g[k, col:col+32] to shared memory (overwrites U_g, which is dead by now)
+      const int g0 = r >> 5, k = r & 31;
+      if (g0 < G && k < K && col < H) {
+        float4* z4 = reinterpret_cast<float4*>(UZ + ((size_t)g0 * K + k) * ZP + col);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          z4[q] = make_float4(x[4 * q + 0], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+      }
+      return;
+    }
+    const int g = r / NS, n = r % NS;
+    const int b = b0 + g;
+    if (b >= p.B) return;
+    if (S > 0 && col < H) {
+      // long-scale part: + V_g[n, :] Z_g[:, col:col+32]
+      const int k_eff = Es[g * (E1 + 2) + E1 + 1];
+      const float* qrow = Qs + ((size_t)g * N + (n < N ? n : 0)) * KP;
+      const float* z = UZ + (size_t)g * K * ZP + col;
+#pragma unroll 2
+      for (int k = 0; k < k_eff; ++k) {
+        const float a = qrow[k];
+        const float4* z4 = reinterpret_cast<const float4*>(z + (size_t)k * ZP);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = z4[q];
+          x[4 * q + 0] = fmaf(a, t.x, x[4 * q + 0]);
+          x[4 * q + 1] = fmaf(a, t.y, x[4 * q + 1]);
+          x[4 * q + 2] = fmaf(a, t.z, x[4 * q + 2]);
+          x[4 * q + 3] = fmaf(a, t.w, x[4 * q + 3]);
+        }
+      }
+    }
+    tcg::store_row_chunk(n < N ? p.out + ((int64_t)b * N + n) * H : nullptr, H, p.bias,
+                         p.relu != 0, col, x);
   }
-  __device__ __forceinline__ int cols_valid(int n_tile) const {
-    const int left = p.H - n_tile * tcg::BN;
-    return left < tcg::BN ? left : tcg::BN;
-  }
-  __device__ __forceinline__ const float* bias_ptr(int n_tile) const {
-    return p.bias ? p.bias + n_tile * tcg::BN : nullptr;
-  }
-  __device__ __forceinline__ bool relu() const { return p.relu != 0; }
 };
 
 }  // namespace
@@ -324,14 +365,14 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
               "spectral_conv_fused: null pointer");
   LNB_REQUIRE(B >= 0 && N >= 1 && Din >= 1 && E1 >= 1 && K >= 1 && S >= 0 && H >= 1,
               "spectral_conv_fused: bad dims");
-  if (N > 128 || Din % 32 != 0 || K > KMAX || H % 4 != 0) {
+  if (N > 128 || Din % 32 != 0 || K > KMAX || H % 4 != 0 || H > tcg::BN) {
     lnb::set_err("spectral_conv_fused: unsupported shape N=%d Din=%d K=%d H=%d "
-                 "(needs N<=128, Din%%32==0, K<=%d, H%%4==0)", N, Din, K, H, KMAX);
+                 "(needs N<=128, Din%%32==0, K<=%d, H%%4==0, H<=128)", N, Din, K, H, KMAX);
     return LNB_ERR_UNSUPPORTED;
   }
   if (B == 0) return LNB_OK;
   const int NS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-  size_t smem = tcg::CORE_SMEM + 1024 + SpectralPolicy::smem_bytes(N, Din, K, S, E1, NS);
+  size_t smem = tcg::CORE_SMEM + 1024 + SpectralPolicy::smem_bytes(N, Din, K, S, E1, H, NS);
   int tcap = 0;
   if (smem <= 227 * 1024) {
     while (tcap < 8 && smem + SpectralPolicy::ell_stage_bytes(E1, NS, tcap + 1) <= 227 * 1024) ++tcap;
@@ -353,7 +394,7 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
   SpectralPolicy::Params p{X, Q, coeff, ell_val, ell_idx, ell_max, qext, bias, out,
                            B, N, Din, E1, K, S, H, relu, NS, tcap};
   const int G = tcg::BM / NS;
-  const int tiles = lnb::ceil_div(B, G) * lnb::ceil_div(H, tcg::BN);
+  const int tiles = lnb::ceil_div(B, G);
   const int grid = tiles < tcg::sm_count() ? tiles : tcg::sm_count();
   kern<<<grid, tcg::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
   lnb::count_launch();

@@ -64,32 +64,33 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
   asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
 }
 
-// Policy contract (all __device__):
-//   struct Params;                                     kernel parameter block (by value)
-//   static int  num_tiles(const Params&), n_tiles(const Params&), num_kblocks(const Params&);
-//   Policy(const Params&, uint8_t* policy_smem, int tid)   constructed by producer threads only
-//   void tile_begin(int m_tile, int n_tile)            may call producers_sync()
-//   void produce(int kb, float (&v)[32])               the 32 A values of this thread's row
-//   void tile_end()                                    after the tile's last produce()
-//   static int w_row0(const Params&, int n_tile)       first W row (TMA coordinate) of the tile
-//   float* out_ptr(int n_tile)                         this row's output for the tile's first
-//                                                      column (nullptr: skip the row)
-//   int cols_valid(int n_tile)                         number of valid output columns in the tile
-//   const float* bias_ptr(int n_tile)  (may be null);  bool relu()
+// Policy contract (all __device__).  A "step" is one accumulator lifetime: its k-blocks are
+// produced / multiplied, then the epilogue hands the 128 x 128 result to the policy.
+//   struct Params;                                       kernel parameter block (by value)
+//   static int  num_steps(const Params&, int cta, int ncta)       steps this CTA runs
+//   static void decode(const Params&, int cta, int ncta, int it, int& m_tile, int& sub)
+//   static int  num_kblocks(const Params&, int sub)
+//   static void w_coords(const Params&, int sub, int kb, int& col0, int& row0)   TMA coords of W
+//   Policy(const Params&, uint8_t* policy_smem, int tid)  constructed by producer threads only
+//   void step_begin(int m_tile, int sub)                  may call producers_sync()
+//   void produce(int sub, int kb, float (&v)[32])         the 32 A values of this thread's row
+//   void store(int sub, int col, float (&x)[32])          accumulator columns [col, col+32) of
+//                                                         this thread's row (main + corr summed)
 template <class Policy>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
                const __grid_constant__ CUtensorMap map_lo, const typename Policy::Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // 1024-byte alignment (SWIZZLE_128B) by OFFSETTING the __shared__ array -- keeps the
+  // shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
+  const uint32_t pad = (1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* base = smem_raw + pad;
   Core c = carve(base);
   uint8_t* policy_smem = base + CORE_SMEM;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int num_tiles = Policy::num_tiles(p);
-  const int n_tiles = Policy::n_tiles(p);
-  const int nkb = Policy::num_kblocks(p);
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int nsteps = Policy::num_steps(p, cta, ncta);
 
   if (warp == TMA_WARP && lane == 0) {
     tc05::tma_prefetch_desc(&map_hi);
@@ -117,13 +118,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
     const int wq = warp & 3;                         // TMEM lane quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
     Policy pol(p, policy_smem, tid);
-    uint32_t gk0 = 0, tcount = 0;                    // gk0: global k-block count at tile start
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount, gk0 += nkb) {
-      const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
-      pol.tile_begin(m_tile, n_tile);
+    uint32_t gk0 = 0;                                // global k-block count at step start
+    for (int it = 0; it < nsteps; ++it) {
+      int m_tile, sub;
+      Policy::decode(p, cta, ncta, it, m_tile, sub);
+      const int nkb = Policy::num_kblocks(p, sub);
+      pol.step_begin(m_tile, sub);
       for (int kb = grp; kb < nkb; kb += NGROUPS) {
         float v[32];
-        pol.produce(kb, v);
+        pol.produce(sub, kb, v);
         const uint32_t gk = gk0 + kb;
         const uint32_t sa = gk % NA_STAGES;
         tc05::mbar_wait(&c.a_empty[sa], ((gk / NA_STAGES) & 1u) ^ 1u);
@@ -140,14 +143,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         tc05::fence_before_thread_sync();
         tc05::mbar_arrive(&c.a_full[sa]);
       }
-      pol.tile_end();
+      gk0 += nkb;
       // ---- epilogue: 32-column chunk cc belongs to group cc % NGROUPS ----
-      tc05::mbar_wait(c.acc_full, tcount & 1u);
+      tc05::mbar_wait(c.acc_full, (uint32_t)it & 1u);
       tc05::fence_after_thread_sync();
-      float* orow = pol.out_ptr(n_tile);
-      const int ncols = pol.cols_valid(n_tile);
-      const float* bias = pol.bias_ptr(n_tile);
-      const bool relu = pol.relu();
 #pragma unroll 1
       for (int cc = grp; cc < BN / 32; cc += NGROUPS) {
         const int col = cc * 32;
@@ -155,30 +154,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         tc05::tmem_ld_32x32(lane_addr + COL_MAIN + col, vm);
         tc05::tmem_ld_32x32(lane_addr + COL_CORR + col, vc);
         tc05::tmem_wait_ld();
-        if (orow != nullptr && col < ncols) {
-          const bool vec_ok = (reinterpret_cast<uintptr_t>(orow + col) & 15) == 0;
+        float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float o[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int n = col + j + u;
-              float x = __uint_as_float(vm[j + u]) + __uint_as_float(vc[j + u]);
-              if (n < ncols) {
-                if (bias) x += __ldg(bias + n);
-                if (relu) x = fmaxf(x, 0.f);
-              }
-              o[u] = x;
-            }
-            if (vec_ok && col + j + 3 < ncols) {
-              *reinterpret_cast<float4*>(orow + col + j) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (col + j + u < ncols) orow[col + j + u] = o[u];
-            }
-          }
-        }
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+        pol.store(sub, col, x);
       }
       tc05::fence_before_thread_sync();
       tc05::mbar_arrive(c.acc_empty);
@@ -187,14 +166,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
     // ================================ TMA producer (W tiles) ==============================
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = Policy::w_row0(p, tile % n_tiles);
+      for (int it = 0; it < nsteps; ++it) {
+        int m_tile, sub;
+        Policy::decode(p, cta, ncta, it, m_tile, sub);
+        const int nkb = Policy::num_kblocks(p, sub);
         for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          int col0, row0;
+          Policy::w_coords(p, sub, kb, col0, row0);
           const uint32_t sb = cnt % NB_STAGES;
           tc05::mbar_wait(&c.b_empty[sb], ((cnt / NB_STAGES) & 1u) ^ 1u);
           tc05::mbar_arrive_expect_tx(&c.b_full[sb], 2 * TILE_B_BYTES);
-          tc05::tma_load_2d(c.Bhi + sb * TILE_B_BYTES, &map_hi, &c.b_full[sb], kb * BK, n0);
-          tc05::tma_load_2d(c.Blo + sb * TILE_B_BYTES, &map_lo, &c.b_full[sb], kb * BK, n0);
+          tc05::tma_load_2d(c.Bhi + sb * TILE_B_BYTES, &map_hi, &c.b_full[sb], col0, row0);
+          tc05::tma_load_2d(c.Blo + sb * TILE_B_BYTES, &map_lo, &c.b_full[sb], col0, row0);
         }
       }
     }
@@ -202,10 +185,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
     // ================================ MMA issuer ==========================================
     if (lane == 0) {
       constexpr uint32_t idesc = tc05::umma_idesc_tf32(BM, BN);
-      uint32_t cnt_b = 0, tcount = 0;
+      uint32_t cnt_b = 0;
       const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        tc05::mbar_wait(c.acc_empty, (tcount & 1u) ^ 1u);     // epilogue of the previous tile done
+      for (int it = 0; it < nsteps; ++it) {
+        int m_tile, sub;
+        Policy::decode(p, cta, ncta, it, m_tile, sub);
+        const int nkb = Policy::num_kblocks(p, sub);
+        tc05::mbar_wait(c.acc_empty, ((uint32_t)it & 1u) ^ 1u);   // previous epilogue done
         tc05::fence_after_thread_sync();
         for (int kb = 0; kb < nkb; ++kb, ++cnt_b) {
           const uint32_t sa = cnt_b % NA_STAGES;       // cnt_b == global k-block count
@@ -237,6 +223,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   if (warp == MMA_WARP) {
     __syncwarp();
     tc05::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Epilogue helper: bias / ReLU / bounds-checked store of 32 accumulator columns of one row.
+__device__ __forceinline__ void store_row_chunk(float* orow, int ncols, const float* bias, bool relu,
+                                                int col, const float (&x)[32]) {
+  if (orow == nullptr || col >= ncols) return;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(orow + col) & 15) == 0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = col + j + u;
+      float y = x[j + u];
+      if (n < ncols) {
+        if (bias) y += __ldg(bias + n);
+        if (relu) y = fmaxf(y, 0.f);
+      }
+      o[u] = y;
+    }
+    if (vec_ok && col + j + 3 < ncols) {
+      *reinterpret_cast<float4*>(orow + col + j) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (col + j + u < ncols) orow[col + j + u] = o[u];
+    }
   }
 }
 
