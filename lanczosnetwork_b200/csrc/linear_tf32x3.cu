@@ -18,6 +18,7 @@ struct RowLoadPolicy {
     const float* bias;
     float* C;
     int M, N, K, relu, groups;
+    int dbg;                // debug experiment flags (LNB_DBG), 0 in production
   };
   static __device__ __forceinline__ int tiles_per_group(const Params& p) { return (p.N + tcg::BN - 1) / tcg::BN; }
   static __device__ __forceinline__ int n_tiles(const Params& p) { return p.groups * tiles_per_group(p); }
@@ -65,11 +66,11 @@ struct RowLoadPolicy {
       v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
   }
-  __device__ __forceinline__ void step_begin(int m_tile, int sub) {
+  __device__ __forceinline__ void step_begin(int m_tile, int sub, int kb_first) {
     row = m_tile * tcg::BM + r;
     row_ok = row < p.M;
     arow = p.A + (int64_t)(row_ok ? row : 0) * lda + (sub / tiles_per_group(p)) * p.K;
-    load(grp, cur);
+    load(kb_first, cur);
   }
   __device__ __forceinline__ void produce(int, int kb, float (&v)[32]) {
 #pragma unroll
@@ -106,7 +107,7 @@ static int launch_linear(lnb_stream_t stream, const float* A, const float* W_hi,
   if (rc != LNB_OK) return rc;
   auto kern = tcg::tc_gemm_kernel<RowLoadPolicy>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-  RowLoadPolicy::Params p{A, bias, C, M, N, K, relu, groups};
+  RowLoadPolicy::Params p{A, bias, C, M, N, K, relu, groups, tcg::debug_flags()};
   const int tiles = lnb::ceil_div(M, tcg::BM) * lnb::ceil_div(N, tcg::BN) * groups;
   const int grid = tiles < tcg::sm_count() ? tiles : tcg::sm_count();
   kern<<<grid, tcg::THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_hi, map_lo, p);

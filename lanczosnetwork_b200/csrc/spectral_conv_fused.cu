@@ -111,6 +111,7 @@ struct SpectralPolicy {
     float* out;             // [B, N, H]
     int B, N, Din, E1, K, S, H, relu, NS;
     int TCAP;               // ELL entries per (row, channel) staged in shared memory
+    int dbg;                // debug experiment flags (LNB_DBG), 0 in production
   };
   static __device__ __forceinline__ int m_tiles(const Params& p) {
     const int G = tcg::BM / p.NS;
@@ -170,7 +171,7 @@ struct SpectralPolicy {
     return (size_t)(tcg::BM / NS) * E1 * tcap * NS * 5;
   }
 
-  __device__ void step_begin(int m_tile, int sub) {
+  __device__ void step_begin(int m_tile, int sub, int /*kb_first*/) {
     tcg::producers_sync();              // previous step's smem readers / Z writers are done
     if (sub == 1 && S > 0) return;      // tile state was staged by step 0
     b0 = m_tile * G;
@@ -392,7 +393,7 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
   auto kern = tcg::tc_gemm_kernel<SpectralPolicy>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   SpectralPolicy::Params p{X, Q, coeff, ell_val, ell_idx, ell_max, qext, bias, out,
-                           B, N, Din, E1, K, S, H, relu, NS, tcap};
+                           B, N, Din, E1, K, S, H, relu, NS, tcap, tcg::debug_flags()};
   const int G = tcg::BM / NS;
   const int tiles = lnb::ceil_div(B, G);
   const int grid = tiles < tcg::sm_count() ? tiles : tcg::sm_count();

@@ -18,28 +18,26 @@
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
+#include <stdlib.h>
 
 namespace tcg {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int NB_STAGES = 3;
-constexpr int NA_STAGES = 4;                       // TMEM ring of A stages
-constexpr int NGROUPS = 3;                         // producer groups (4 warps each)
+constexpr int NSTAGES = 3;                         // pipeline stages == producer groups
+constexpr int NGROUPS = NSTAGES;                   // group g owns stage g (k-block kb -> kb % 3)
 constexpr int TILE_B_BYTES = BN * BK * 4;          // 16 KB per hi or lo tile
+constexpr int STAGE_B_BYTES = 2 * TILE_B_BYTES;    // [W_hi tile | W_lo tile] = 256 rows x 128 B
 constexpr int TMEM_COLS = 512;
-constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;
+constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;   // A stage s: COL_A + 64 s (hi), +32 (lo)
 constexpr int PRODUCER_THREADS = 128 * NGROUPS;
 constexpr int TMA_WARP = 4 * NGROUPS, MMA_WARP = 4 * NGROUPS + 1;
 constexpr int THREADS = PRODUCER_THREADS + 64;
-constexpr int CORE_SMEM = 2 * NB_STAGES * TILE_B_BYTES + 256;   // W ring + barriers/holder
+constexpr int CORE_SMEM = NSTAGES * STAGE_B_BYTES + 256;   // W ring + barriers/holder
 
 struct Core {
-  uint8_t* Bhi;
-  uint8_t* Blo;
-  uint64_t* b_full;    // [NB_STAGES]
-  uint64_t* b_empty;   // [NB_STAGES]
-  uint64_t* a_full;    // [NA_STAGES]
-  uint64_t* a_empty;   // [NA_STAGES]
+  uint8_t* Bst;        // [NSTAGES][hi 16 KB | lo 16 KB]
+  uint64_t* full;      // [NSTAGES]  4 producer-warp arrivals + 1 TMA arrive.expect_tx
+  uint64_t* empty;     // [NSTAGES]  1 tcgen05.commit
   uint64_t* acc_full;  // [1]
   uint64_t* acc_empty; // [1]
   uint32_t* tmem_holder;
@@ -47,14 +45,11 @@ struct Core {
 
 __device__ __forceinline__ Core carve(uint8_t* base) {
   Core c;
-  c.Bhi = base;
-  c.Blo = base + NB_STAGES * TILE_B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * NB_STAGES * TILE_B_BYTES);
-  c.b_full = bars;
-  c.b_empty = c.b_full + NB_STAGES;
-  c.a_full = c.b_empty + NB_STAGES;
-  c.a_empty = c.a_full + NA_STAGES;
-  c.acc_full = c.a_empty + NA_STAGES;
+  c.Bst = base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + NSTAGES * STAGE_B_BYTES);
+  c.full = bars;
+  c.empty = c.full + NSTAGES;
+  c.acc_full = c.empty + NSTAGES;
   c.acc_empty = c.acc_full + 1;
   c.tmem_holder = reinterpret_cast<uint32_t*>(c.acc_empty + 1);
   return c;
@@ -72,7 +67,8 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
 //   static int  num_kblocks(const Params&, int sub)
 //   static void w_coords(const Params&, int sub, int kb, int& col0, int& row0)   TMA coords of W
 //   Policy(const Params&, uint8_t* policy_smem, int tid)  constructed by producer threads only
-//   void step_begin(int m_tile, int sub)                  may call producers_sync()
+//   void step_begin(int m_tile, int sub, int kb_first)    may call producers_sync(); kb_first =
+//                                                         this thread's first k-block of the step
 //   void produce(int sub, int kb, float (&v)[32])         the 32 A values of this thread's row
 //   void store(int sub, int col, float (&x)[32])          accumulator columns [col, col+32) of
 //                                                         this thread's row (main + corr summed)
@@ -98,10 +94,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   }
   if (warp == MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < NB_STAGES; ++s) { tc05::mbar_init(&c.b_full[s], 1); tc05::mbar_init(&c.b_empty[s], 1); }
-      for (int s = 0; s < NA_STAGES; ++s) { tc05::mbar_init(&c.a_full[s], 128); tc05::mbar_init(&c.a_empty[s], 1); }
+      for (int s = 0; s < NSTAGES; ++s) { tc05::mbar_init(&c.full[s], 5); tc05::mbar_init(&c.empty[s], 1); }
       tc05::mbar_init(c.acc_full, 1);
-      tc05::mbar_init(c.acc_empty, PRODUCER_THREADS);
+      tc05::mbar_init(c.acc_empty, 4 * NGROUPS);       // one arrival per producer warp
       tc05::fence_barrier_init();
     }
     __syncwarp();
@@ -114,36 +109,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
 
   if (warp < TMA_WARP) {
     // ================================ producers + epilogue ================================
-    const int grp = warp >> 2;                       // producer group
+    const int grp = warp >> 2;                       // producer group == pipeline stage
     const int wq = warp & 3;                         // TMEM lane quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const uint32_t a_hi = lane_addr + COL_A + grp * 64;
     Policy pol(p, policy_smem, tid);
+    uint32_t use = 0;                                // uses of this group's stage so far
     uint32_t gk0 = 0;                                // global k-block count at step start
     for (int it = 0; it < nsteps; ++it) {
       int m_tile, sub;
       Policy::decode(p, cta, ncta, it, m_tile, sub);
       const int nkb = Policy::num_kblocks(p, sub);
-      pol.step_begin(m_tile, sub);
-      for (int kb = grp; kb < nkb; kb += NGROUPS) {
-        float v[32];
-        pol.produce(sub, kb, v);
-        const uint32_t gk = gk0 + kb;
-        const uint32_t sa = gk % NA_STAGES;
-        tc05::mbar_wait(&c.a_empty[sa], ((gk / NA_STAGES) & 1u) ^ 1u);
-        tc05::fence_after_thread_sync();
-        uint32_t part[32];
-        const uint32_t a_hi = lane_addr + COL_A + sa * 64;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(v[j]);
-        tc05::tmem_st_32x32(a_hi, part);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(v[j] - __uint_as_float(part[j]));
-        tc05::tmem_st_32x32(a_hi + 32, part);
-        tc05::tmem_wait_st();
-        tc05::fence_before_thread_sync();
-        tc05::mbar_arrive(&c.a_full[sa]);
-      }
+      // stage (== group) of a k-block is its GLOBAL index % 3, like the TMA / MMA warps count it
+      const int kb_first = (grp + NGROUPS - (int)(gk0 % NGROUPS)) % NGROUPS;
       gk0 += nkb;
+      pol.step_begin(m_tile, sub, kb_first);
+      for (int kb = kb_first; kb < nkb; kb += NGROUPS, ++use) {
+        float v[32];
+        if (!(p.dbg & 8)) pol.produce(sub, kb, v);
+        tc05::mbar_wait(&c.empty[grp], (use & 1u) ^ 1u);
+        tc05::fence_after_thread_sync();
+        if (!(p.dbg & 1)) {
+          uint32_t part[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(v[j]);
+          tc05::tmem_st_32x32(a_hi, part);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(v[j] - __uint_as_float(part[j]));
+          tc05::tmem_st_32x32(a_hi + 32, part);
+          tc05::tmem_wait_st();
+        }
+        tc05::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) tc05::mbar_arrive(&c.full[grp]);
+      }
       // ---- epilogue: 32-column chunk cc belongs to group cc % NGROUPS ----
       tc05::mbar_wait(c.acc_full, (uint32_t)it & 1u);
       tc05::fence_after_thread_sync();
@@ -160,60 +159,68 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         pol.store(sub, col, x);
       }
       tc05::fence_before_thread_sync();
-      tc05::mbar_arrive(c.acc_empty);
+      __syncwarp();
+      if (lane == 0) tc05::mbar_arrive(c.acc_empty);
     }
   } else if (warp == TMA_WARP) {
     // ================================ TMA producer (W tiles) ==============================
-    if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int it = 0; it < nsteps; ++it) {
-        int m_tile, sub;
-        Policy::decode(p, cta, ncta, it, m_tile, sub);
-        const int nkb = Policy::num_kblocks(p, sub);
-        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-          int col0, row0;
-          Policy::w_coords(p, sub, kb, col0, row0);
-          const uint32_t sb = cnt % NB_STAGES;
-          tc05::mbar_wait(&c.b_empty[sb], ((cnt / NB_STAGES) & 1u) ^ 1u);
-          tc05::mbar_arrive_expect_tx(&c.b_full[sb], 2 * TILE_B_BYTES);
-          tc05::tma_load_2d(c.Bhi + sb * TILE_B_BYTES, &map_hi, &c.b_full[sb], col0, row0);
-          tc05::tma_load_2d(c.Blo + sb * TILE_B_BYTES, &map_lo, &c.b_full[sb], col0, row0);
+    // the whole warp runs the loop (warp-uniform control flow); one elected lane issues
+    uint32_t cnt = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      int m_tile, sub;
+      Policy::decode(p, cta, ncta, it, m_tile, sub);
+      const int nkb = Policy::num_kblocks(p, sub);
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        int col0, row0;
+        Policy::w_coords(p, sub, kb, col0, row0);
+        const uint32_t st = cnt % NSTAGES;
+        tc05::mbar_wait(&c.empty[st], ((cnt / NSTAGES) & 1u) ^ 1u);
+        if (tc05::elect_one()) {
+          if (p.dbg & 4) {
+            tc05::mbar_arrive(&c.full[st]);
+          } else {
+            uint8_t* dst = c.Bst + st * STAGE_B_BYTES;
+            tc05::mbar_arrive_expect_tx(&c.full[st], STAGE_B_BYTES);
+            tc05::tma_load_2d(dst, &map_hi, &c.full[st], col0, row0);
+            tc05::tma_load_2d(dst + TILE_B_BYTES, &map_lo, &c.full[st], col0, row0);
+          }
         }
+        __syncwarp();
       }
     }
   } else {
     // ================================ MMA issuer ==========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc05::umma_idesc_tf32(BM, BN);
-      uint32_t cnt_b = 0;
-      const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
-      for (int it = 0; it < nsteps; ++it) {
-        int m_tile, sub;
-        Policy::decode(p, cta, ncta, it, m_tile, sub);
-        const int nkb = Policy::num_kblocks(p, sub);
-        tc05::mbar_wait(c.acc_empty, ((uint32_t)it & 1u) ^ 1u);   // previous epilogue done
+    // per k-step of 8:  [D_main | D_corr] += A_hi * [W_hi ; W_lo]^T   (one N = 256 MMA)
+    //                    D_corr           += A_lo * W_hi^T            (one N = 128 MMA)
+    constexpr uint32_t idesc256 = tc05::umma_idesc_tf32(BM, 2 * BN);
+    constexpr uint32_t idesc128 = tc05::umma_idesc_tf32(BM, BN);
+    uint32_t cnt = 0;
+    const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
+    for (int it = 0; it < nsteps; ++it) {
+      int m_tile, sub;
+      Policy::decode(p, cta, ncta, it, m_tile, sub);
+      const int nkb = Policy::num_kblocks(p, sub);
+      tc05::mbar_wait(c.acc_empty, ((uint32_t)it & 1u) ^ 1u);   // previous epilogue done
+      tc05::fence_after_thread_sync();
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        const uint32_t st = cnt % NSTAGES;
+        tc05::mbar_wait(&c.full[st], (cnt / NSTAGES) & 1u);
         tc05::fence_after_thread_sync();
-        for (int kb = 0; kb < nkb; ++kb, ++cnt_b) {
-          const uint32_t sa = cnt_b % NA_STAGES;       // cnt_b == global k-block count
-          const uint32_t pha = (cnt_b / NA_STAGES) & 1u;
-          const uint32_t sb = cnt_b % NB_STAGES;
-          tc05::mbar_wait(&c.b_full[sb], (cnt_b / NB_STAGES) & 1u);
-          tc05::mbar_wait(&c.a_full[sa], pha);
-          tc05::fence_after_thread_sync();
-          const uint32_t a_hi = tmem_base + COL_A + sa * 64, a_lo = a_hi + 32;
-          const uint64_t dhi = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Bhi + sb * TILE_B_BYTES));
-          const uint64_t dlo = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Blo + sb * TILE_B_BYTES));
+        if (tc05::elect_one()) {
+          const uint32_t a_hi = tmem_base + COL_A + st * 64, a_lo = a_hi + 32;
+          const uint64_t dB = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Bst + st * STAGE_B_BYTES));
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-            tc05::umma_tf32_ts(d_corr, a_lo + 8 * k, dhi + 2 * k, idesc, first);
-            tc05::umma_tf32_ts(d_corr, a_hi + 8 * k, dlo + 2 * k, idesc, 1u);
-            tc05::umma_tf32_ts(d_main, a_hi + 8 * k, dhi + 2 * k, idesc, first);
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              tc05::umma_tf32_ts(d_main, a_hi + 8 * k, dB + 2 * k, idesc256, acc);
+              tc05::umma_tf32_ts(d_corr, a_lo + 8 * k, dB + 2 * k, idesc128, 1u);
+            }
           }
-          tc05::umma_commit(&c.a_empty[sa]);
-          tc05::umma_commit(&c.b_empty[sb]);
+          tc05::umma_commit(&c.empty[st]);
+          if (kb == nkb - 1) tc05::umma_commit(c.acc_full);
         }
-        tc05::umma_commit(c.acc_full);
+        __syncwarp();
       }
     }
   }
@@ -288,6 +295,13 @@ inline int make_weight_map(CUtensorMap* map, const float* W, int rows, int cols,
     return LNB_ERR_ARG;
   }
   return LNB_OK;
+}
+
+// LNB_DBG=<bits>: pipeline experiments (1 skip TMEM stores, 2 skip MMA issue, 4 skip TMA loads,
+// 8 skip produce()).  Results are wrong with any bit set; for profiling only.
+inline int debug_flags() {
+  const char* e = getenv("LNB_DBG");
+  return e ? atoi(e) : 0;
 }
 
 inline int sm_count() {
