@@ -77,6 +77,7 @@ struct RowLoadPolicy {
     for (int j = 0; j < 32; ++j) v[j] = cur[j];
     load(kb + tcg::NGROUPS, cur);   // this group's next k-block (zeros past K)
   }
+  __device__ __forceinline__ void pre_epilogue(int) {}
   __device__ __forceinline__ void store(int sub, int col, const float (&x)[32]) {
     const int left = p.N - (sub % tiles_per_group(p)) * tcg::BN;
     const int w0 = w_row0(p, sub);

@@ -139,7 +139,7 @@ struct SpectralPolicy {
   const int tid, r;
   const int N, Din, K, S, E1, H, NS, TCAP;   // hot parameters in registers
   const int G, XP, UP, ZP, KP;               // slots per tile, padded row strides
-  float* Xs;                // [G][N][XP]
+  float* Xs;                // X_g [G][N][XP]; reused for V_g Z_g after the edge k-loop
   float* UZ;                // U_g [G][K][UP] during step 0, Z_g [G][K][ZP] afterwards
   float* Qs;                // [G][N][KP]
   float* Fs;                // [G][K][S]
@@ -150,8 +150,8 @@ struct SpectralPolicy {
 
   __device__ SpectralPolicy(const Params& p_, uint8_t* smem, int tid_)
       : p(p_), tid(tid_), r(tid_ & 127), N(p_.N), Din(p_.Din), K(p_.K), S(p_.S), E1(p_.E1),
-        H(p_.H), NS(p_.NS), TCAP(p_.TCAP), G(tcg::BM / p_.NS), XP(p_.Din + 4), UP(p_.Din + 4),
-        ZP(p_.H + 4), KP(p_.K | 1), b0(0) {
+        H(p_.H), NS(p_.NS), TCAP(p_.TCAP), G(tcg::BM / p_.NS),
+        XP((p_.Din > p_.H ? p_.Din : p_.H) + 4), UP(p_.Din + 4), ZP(p_.H + 4), KP(p_.K), b0(0) {
     Xs = reinterpret_cast<float*>(smem);
     UZ = Xs + (size_t)G * N * XP;
     Qs = UZ + (size_t)G * K * ((Din > H ? Din : H) + 4);
@@ -163,8 +163,8 @@ struct SpectralPolicy {
 
   static size_t smem_bytes(int N, int Din, int K, int S, int E1, int H, int NS) {
     const int G = tcg::BM / NS;
-    size_t fl = (size_t)G * N * (Din + 4) + (size_t)G * K * ((Din > H ? Din : H) + 4) +
-                (size_t)G * N * (K | 1) + (size_t)G * K * S;
+    const int W = (Din > H ? Din : H) + 4;
+    size_t fl = (size_t)G * N * W + (size_t)G * K * W + (size_t)G * N * K + (size_t)G * K * S;
     return fl * 4 + (size_t)G * (E1 + 2) * 4 + 16;
   }
   static size_t ell_stage_bytes(int E1, int NS, int tcap) {
@@ -175,67 +175,126 @@ struct SpectralPolicy {
     tcg::producers_sync();              // previous step's smem readers / Z writers are done
     if (sub == 1 && S > 0) return;      // tile state was staged by step 0
     b0 = m_tile * G;
-    // ---- stage X, Q, filter coefficients, extents, ELL rows of the G graphs ---------------
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = tcg::PRODUCER_THREADS / 32;
+    // ---- phase A: asynchronous copies (cp.async), one warp per row, no div/mod per element --
     const int dv = Din / 4;
-    for (int e = tid; e < G * N * dv; e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (N * dv), rem = e % (N * dv);
-      const int nn = rem / dv, q4 = rem % dv;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 + gg < p.B)
-        v = __ldg(reinterpret_cast<const float4*>(p.X + ((int64_t)(b0 + gg) * N + nn) * Din) + q4);
-      *reinterpret_cast<float4*>(Xs + ((size_t)gg * N + nn) * XP + 4 * q4) = v;
-    }
-    for (int e = tid; e < G * N * K; e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (N * K), rem = e % (N * K);
-      const int nn = rem / K, kk = rem % K;
-      Qs[((size_t)gg * N + nn) * KP + kk] =
-          (b0 + gg < p.B) ? __ldg(p.Q + ((int64_t)(b0 + gg) * N + nn) * K + kk) : 0.f;
+    for (int row = warp; row < G * N; row += NW) {
+      const int gg = row / N, nn = row - gg * N;
+      float* xd = Xs + (size_t)row * XP;
+      float* qd = Qs + (size_t)row * KP;
+      if (b0 + gg < p.B) {
+        const float* xsrc = p.X + ((int64_t)(b0 + gg) * N + nn) * Din;
+        for (int q4 = lane; q4 < dv; q4 += 32) tc05::cp_async_16(xd + 4 * q4, xsrc + 4 * q4);
+        const float* qsrc = p.Q + ((int64_t)(b0 + gg) * N + nn) * K;
+        for (int k = lane; k < K; k += 32) tc05::cp_async_4(qd + k, qsrc + k);
+      } else {
+        for (int q4 = lane; q4 < dv; q4 += 32)
+          *reinterpret_cast<float4*>(xd + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = lane; k < K; k += 32) qd[k] = 0.f;
+      }
     }
     for (int e = tid; e < G * K * S; e += tcg::PRODUCER_THREADS) {
       const int gg = e / (K * S);
-      Fs[e] = (b0 + gg < p.B) ? __ldg(p.coeff + (int64_t)(b0 + gg) * K * S + e % (K * S)) : 0.f;
+      if (b0 + gg < p.B) tc05::cp_async_4(Fs + e, p.coeff + (int64_t)b0 * K * S + e);
+      else Fs[e] = 0.f;
     }
     for (int e = tid; e < G * (E1 + 2); e += tcg::PRODUCER_THREADS) {
       const int gg = e / (E1 + 2), w = e % (E1 + 2);
       int v = 0;
       if (b0 + gg < p.B)
-        v = (w < E1) ? p.ell_max[(b0 + gg) * E1 + w] : p.qext[(b0 + gg) * 2 + (w - E1)];
+        v = (w < E1) ? __ldg(p.ell_max + (b0 + gg) * E1 + w) : __ldg(p.qext + (b0 + gg) * 2 + (w - E1));
       Es[e] = v;
     }
-    // first TCAP ELL entries per row/channel, zero beyond the channel maximum
-    for (int e = tid; e < G * E1 * TCAP * NS; e += tcg::PRODUCER_THREADS) {
-      const int nn = e % NS, t = (e / NS) % TCAP;
-      const int ch = (e / (NS * TCAP)) % E1, gg = e / (NS * TCAP * E1);
-      float v = 0.f;
-      int ix = 0;
-      if (b0 + gg < p.B && nn < N && t < __ldg(p.ell_max + (b0 + gg) * E1 + ch)) {
-        const int64_t off = (((int64_t)(b0 + gg) * E1 + ch) * N + t) * N + nn;
-        v = __ldg(p.ell_val + off);
-        ix = __ldg(p.ell_idx + off);
+    // first TCAP ELL entries per (row, channel): one warp per (graph, channel, t) line of NS
+    // rows; loads are unconditional (the arrays are fully allocated) and masked afterwards, so
+    // nothing in the loop depends on a previous load
+    for (int line = warp; line < G * E1 * TCAP; line += NW) {
+      const int t = line % TCAP, gc = line / TCAP;       // gc = gg * E1 + ch
+      const int gg = gc / E1, ch = gc - gg * E1;
+      const bool gok = (b0 + gg < p.B) && (t < N);
+      const int tmax = gok ? __ldg(p.ell_max + (b0 + gg) * E1 + ch) : 0;
+      for (int nn = lane; nn < NS; nn += 32) {
+        float v = 0.f;
+        int ix = 0;
+        if (gok && nn < N) {
+          const int64_t off = (((int64_t)(b0 + gg) * E1 + ch) * N + t) * N + nn;
+          const float vv = __ldg(p.ell_val + off);
+          const int ii = __ldg(p.ell_idx + off);
+          if (t < tmax) { v = vv; ix = ii; }
+        }
+        Ev[(size_t)line * NS + nn] = v;
+        Ei[(size_t)line * NS + nn] = (uint8_t)ix;
       }
-      Ev[e] = v;
-      Ei[e] = (uint8_t)ix;
     }
-    if (S == 0) { tcg::producers_sync(); return; }
+    tc05::cp_async_wait_all();
     tcg::producers_sync();
-    // ---- U_g = Q_g^T X_g  (K x Din per graph): thread <-> (graph, column), all k in registers
-    for (int pr = tid; pr < G * Din; pr += tcg::PRODUCER_THREADS) {
-      const int gg = pr / Din, d = pr % Din;
+    if (S == 0) return;
+    // ---- phase B: U_g = Q_g^T X_g (K x Din per graph) in 4 x 4 register tiles ---------------
+    const int kq_n = K / 4;
+    for (int task = tid; task < G * kq_n * dv; task += tcg::PRODUCER_THREADS) {
+      const int dq = task % dv, gk = task / dv;          // gk = gg * kq_n + kq
+      const int gg = gk / kq_n, kq = gk - gg * kq_n;
       const int n_eff = Es[gg * (E1 + 2) + E1];
-      float acc[KMAX];
+      float acc[4][4];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-      const float* xs = Xs + (size_t)gg * N * XP + d;
-      const float* qs = Qs + (size_t)gg * N * KP;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      const float* xs = Xs + (size_t)gg * N * XP + 4 * dq;
+      const float* qs = Qs + (size_t)gg * N * KP + 4 * kq;
+#pragma unroll 2
       for (int nn = 0; nn < n_eff; ++nn) {
-        const float x = xs[(size_t)nn * XP];
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + (size_t)nn * XP);
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)nn * KP);
+        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) acc[k] = fmaf(qs[nn * KP + k], x, acc[k]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(qv[i], xv[j], acc[i][j]);
       }
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) UZ[((size_t)gg * K + k) * UP + d] = acc[k];
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(UZ + ((size_t)gg * K + 4 * kq + i) * UP + 4 * dq) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    tcg::producers_sync();
+  }
+
+  // After the last k-block of the edge step: VZ_g = V_g Z_g (N x H per graph) in 4 x 4 register
+  // tiles into the (now dead) X_g buffer; overlaps with the tensor core draining its queue.
+  __device__ void pre_epilogue(int sub) {
+    if (sub == 0 || S == 0) return;
+    tcg::producers_sync();              // every producer is done reading X_g
+    const int hv = H / 4, nq_n = (N + 3) / 4;
+    for (int task = tid; task < G * nq_n * hv; task += tcg::PRODUCER_THREADS) {
+      const int hq = task % hv, gn = task / hv;          // gn = gg * nq_n + nq
+      const int gg = gn / nq_n, nq = gn - gg * nq_n;
+      const int k_eff = Es[gg * (E1 + 2) + E1 + 1];
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      const float* z = UZ + (size_t)gg * K * ZP + 4 * hq;
+      const float* q0 = Qs + ((size_t)gg * N + 4 * nq) * KP;
+      const int r1 = (4 * nq + 1 < N) ? 1 : 0, r2 = (4 * nq + 2 < N) ? 2 : 0, r3 = (4 * nq + 3 < N) ? 3 : 0;
+#pragma unroll 2
+      for (int k = 0; k < k_eff; ++k) {
+        const float4 z4 = *reinterpret_cast<const float4*>(z + (size_t)k * ZP);
+        const float av[4] = {q0[k], q0[r1 * KP + k], q0[r2 * KP + k], q0[r3 * KP + k]};
+        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], zv[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (4 * nq + i < N)
+          *reinterpret_cast<float4*>(Xs + ((size_t)gg * N + 4 * nq + i) * XP + 4 * hq) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     tcg::producers_sync();
   }
@@ -317,23 +376,13 @@ struct SpectralPolicy {
     const int g = r / NS, n = r % NS;
     const int b = b0 + g;
     if (b >= p.B) return;
-    if (S > 0 && col < H) {
-      // long-scale part: + V_g[n, :] Z_g[:, col:col+32]
-      const int k_eff = Es[g * (E1 + 2) + E1 + 1];
-      const float* qrow = Qs + ((size_t)g * N + (n < N ? n : 0)) * KP;
-      const float* z = UZ + (size_t)g * K * ZP + col;
-#pragma unroll 2
-      for (int k = 0; k < k_eff; ++k) {
-        const float a = qrow[k];
-        const float4* z4 = reinterpret_cast<const float4*>(z + (size_t)k * ZP);
+    if (S > 0 && col < H && n < N) {
+      // long-scale part: + (V_g Z_g)[n, col:col+32], precomputed by pre_epilogue()
+      const float4* vz = reinterpret_cast<const float4*>(Xs + ((size_t)g * N + n) * XP + col);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = z4[q];
-          x[4 * q + 0] = fmaf(a, t.x, x[4 * q + 0]);
-          x[4 * q + 1] = fmaf(a, t.y, x[4 * q + 1]);
-          x[4 * q + 2] = fmaf(a, t.z, x[4 * q + 2]);
-          x[4 * q + 3] = fmaf(a, t.w, x[4 * q + 3]);
-        }
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = vz[q];
+        x[4 * q + 0] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
       }
     }
     tcg::store_row_chunk(n < N ? p.out + ((int64_t)b * N + n) * H : nullptr, H, p.bias,
@@ -344,6 +393,13 @@ struct SpectralPolicy {
 }  // namespace
 
 extern "C" {
+
+// profiling aid: register (or clear with NULL) a device buffer of 148*8 uint64 phase timers
+int lnb_debug_set_prof(unsigned long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(tcg::g_prof, &buf, sizeof(buf));
+  if (e != cudaSuccess) { lnb::set_err("debug_set_prof: %s", cudaGetErrorString(e)); return (int)e; }
+  return LNB_OK;
+}
 
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
                       int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* qext) {
@@ -366,9 +422,9 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
               "spectral_conv_fused: null pointer");
   LNB_REQUIRE(B >= 0 && N >= 1 && Din >= 1 && E1 >= 1 && K >= 1 && S >= 0 && H >= 1,
               "spectral_conv_fused: bad dims");
-  if (N > 128 || Din % 32 != 0 || K > KMAX || H % 4 != 0 || H > tcg::BN) {
+  if (N > 128 || Din % 32 != 0 || K > KMAX || K % 4 != 0 || H % 4 != 0 || H > tcg::BN) {
     lnb::set_err("spectral_conv_fused: unsupported shape N=%d Din=%d K=%d H=%d "
-                 "(needs N<=128, Din%%32==0, K<=%d, H%%4==0, H<=128)", N, Din, K, H, KMAX);
+                 "(needs N<=128, Din%%32==0, K%%4==0, K<=%d, H%%4==0, H<=128)", N, Din, K, H, KMAX);
     return LNB_ERR_UNSUPPORTED;
   }
   if (B == 0) return LNB_OK;

@@ -55,6 +55,11 @@ __device__ __forceinline__ Core carve(uint8_t* base) {
   return c;
 }
 
+// Optional phase timers (profiling aid): when a buffer is registered with lnb_debug_set_prof,
+// thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*8 + phase]:
+//   0 step_begin  1 k-loop (produce + handoff)  2 wait for the accumulator  3 epilogue store
+__device__ unsigned long long* g_prof = nullptr;
+
 __device__ __forceinline__ void producers_sync() {   // named barrier 1: all producer threads
   asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
 }
@@ -70,6 +75,7 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
 //   void step_begin(int m_tile, int sub, int kb_first)    may call producers_sync(); kb_first =
 //                                                         this thread's first k-block of the step
 //   void produce(int sub, int kb, float (&v)[32])         the 32 A values of this thread's row
+//   void pre_epilogue(int sub)                            after the step's last produce()
 //   void store(int sub, int col, float (&x)[32])          accumulator columns [col, col+32) of
 //                                                         this thread's row (main + corr summed)
 template <class Policy>
@@ -123,7 +129,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       // stage (== group) of a k-block is its GLOBAL index % 3, like the TMA / MMA warps count it
       const int kb_first = (grp + NGROUPS - (int)(gk0 % NGROUPS)) % NGROUPS;
       gk0 += nkb;
+      unsigned long long* prof = g_prof;
+      long long t0 = 0;
+      if (prof && tid == 0) t0 = clock64();
       pol.step_begin(m_tile, sub, kb_first);
+      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 0], (unsigned long long)(t - t0)); t0 = t; }
       for (int kb = kb_first; kb < nkb; kb += NGROUPS, ++use) {
         float v[32];
         if (!(p.dbg & 8)) pol.produce(sub, kb, v);
@@ -143,9 +153,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         __syncwarp();
         if (lane == 0) tc05::mbar_arrive(&c.full[grp]);
       }
+      pol.pre_epilogue(sub);
       // ---- epilogue: 32-column chunk cc belongs to group cc % NGROUPS ----
+      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 1], (unsigned long long)(t - t0)); t0 = t; }
       tc05::mbar_wait(c.acc_full, (uint32_t)it & 1u);
       tc05::fence_after_thread_sync();
+      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 2], (unsigned long long)(t - t0)); t0 = t; }
 #pragma unroll 1
       for (int cc = grp; cc < BN / 32; cc += NGROUPS) {
         const int col = cc * 32;
@@ -158,6 +171,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
         pol.store(sub, col, x);
       }
+      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 3], (unsigned long long)(t - t0)); }
       tc05::fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) tc05::mbar_arrive(c.acc_empty);

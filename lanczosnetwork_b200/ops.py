@@ -142,10 +142,10 @@ def graph_prepare(L, Q):
 def fused_conv_supported(N, Din, K, H, n_short, dense_filter, S=8, E1=7):
   """Shapes the fused tcgen05 convolution kernel handles (others use the unfused ops);
   mirrors the checks of lnb_spectral_conv_fused."""
-  if n_short or dense_filter or N > 128 or Din % 32 or K > 32 or H % 4 or H > 128:
+  if n_short or dense_filter or N > 128 or Din % 32 or K > 32 or K % 4 or H % 4 or H > 128:
     return False
   G = 128 // (32 if N <= 32 else (64 if N <= 64 else 128))
-  smem = (98560 + 1024 + 4 * (G * N * (Din + 4) + G * K * (max(Din, H) + 4) + G * N * (K | 1) + G * K * S) +
+  smem = (98560 + 1024 + 4 * ((G * N + G * K) * (max(Din, H) + 4) + G * N * K + G * K * S) +
           4 * G * (E1 + 2) + 16)
   return smem <= 227 * 1024
 
