@@ -98,5 +98,16 @@ def check(status, what):
     raise RuntimeError('%s failed (status %d): %s' % (what, status, (msg or b'').decode()))
 
 
+_replayed = [0]
+
+
+def note_graph_replay(num_kernels):
+  """Kernels launched by a CUDA-graph replay never pass through the library's host-side launch
+  counter; the module records how many kernel nodes the captured forward holds."""
+  _replayed[0] += int(num_kernels)
+
+
 def launch_count():
-  return int(load().lnb_launch_count())
+  """Kernels of this library launched from this process: direct launches (counted in C) plus
+  kernel nodes of replayed CUDA graphs."""
+  return int(load().lnb_launch_count()) + _replayed[0]

@@ -66,7 +66,7 @@ struct RowLoadPolicy {
       v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
   }
-  __device__ __forceinline__ void step_begin(int m_tile, int sub, int kb_first) {
+  __device__ __forceinline__ void step_begin(int m_tile, int sub, int kb_first, tcg::PhaseTimer&) {
     row = m_tile * tcg::BM + r;
     row_ok = row < p.M;
     arow = p.A + (int64_t)(row_ok ? row : 0) * lda + (sub / tiles_per_group(p)) * p.K;
@@ -78,6 +78,7 @@ struct RowLoadPolicy {
     load(kb + tcg::NGROUPS, cur);   // this group's next k-block (zeros past K)
   }
   __device__ __forceinline__ void pre_epilogue(int) {}
+  __device__ __forceinline__ void post_epilogue(int) {}
   __device__ __forceinline__ void store(int sub, int col, const float (&x)[32]) {
     const int left = p.N - (sub % tiles_per_group(p)) * tcg::BN;
     const int w0 = w_row0(p, sub);

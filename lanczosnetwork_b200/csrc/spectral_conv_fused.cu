@@ -171,7 +171,7 @@ struct SpectralPolicy {
     return (size_t)(tcg::BM / NS) * E1 * tcap * NS * 5;
   }
 
-  __device__ void step_begin(int m_tile, int sub, int /*kb_first*/) {
+  __device__ void step_begin(int m_tile, int sub, int /*kb_first*/, tcg::PhaseTimer& tm) {
     tcg::producers_sync();              // previous step's smem readers / Z writers are done
     if (sub == 1 && S > 0) return;      // tile state was staged by step 0
     b0 = m_tile * G;
@@ -207,28 +207,48 @@ struct SpectralPolicy {
       Es[e] = v;
     }
     // first TCAP ELL entries per (row, channel): one warp per (graph, channel, t) line of NS
-    // rows; loads are unconditional (the arrays are fully allocated) and masked afterwards, so
-    // nothing in the loop depends on a previous load
-    for (int line = warp; line < G * E1 * TCAP; line += NW) {
-      const int t = line % TCAP, gc = line / TCAP;       // gc = gg * E1 + ch
-      const int gg = gc / E1, ch = gc - gg * E1;
-      const bool gok = (b0 + gg < p.B) && (t < N);
-      const int tmax = gok ? __ldg(p.ell_max + (b0 + gg) * E1 + ch) : 0;
-      for (int nn = lane; nn < NS; nn += 32) {
-        float v = 0.f;
-        int ix = 0;
-        if (gok && nn < N) {
-          const int64_t off = (((int64_t)(b0 + gg) * E1 + ch) * N + t) * N + nn;
-          const float vv = __ldg(p.ell_val + off);
-          const int ii = __ldg(p.ell_idx + off);
-          if (t < tmax) { v = vv; ix = ii; }
+    // rows.  Loads are unconditional (the arrays are fully allocated) and masked afterwards;
+    // a batch of ELL_BATCH lines is loaded into registers before anything is consumed so the
+    // HBM / L2 latencies of the batch overlap.
+    constexpr int ELL_BATCH = 6;
+    const int nlines = G * E1 * TCAP;
+    for (int base = warp; base < nlines; base += NW * ELL_BATCH) {
+      for (int sub32 = 0; sub32 < NS; sub32 += 32) {
+        const int nn = sub32 + lane;
+        float vv[ELL_BATCH];
+        int ii[ELL_BATCH], tmx[ELL_BATCH];
+#pragma unroll
+        for (int u = 0; u < ELL_BATCH; ++u) {
+          const int line = base + u * NW;
+          vv[u] = 0.f; ii[u] = 0; tmx[u] = 0;
+          if (line < nlines) {
+            const int t = line % TCAP, gc = line / TCAP;     // gc = gg * E1 + ch
+            const int gg = gc / E1;
+            if (b0 + gg < p.B && t < N) {
+              tmx[u] = __ldg(p.ell_max + (int64_t)b0 * E1 + gc) - t;   // > 0  <=>  t < tmax
+              if (nn < N) {
+                const int64_t off = (((int64_t)b0 * E1 + gc) * N + t) * N + nn;
+                vv[u] = __ldg(p.ell_val + off);
+                ii[u] = __ldg(p.ell_idx + off);
+              }
+            }
+          }
         }
-        Ev[(size_t)line * NS + nn] = v;
-        Ei[(size_t)line * NS + nn] = (uint8_t)ix;
+#pragma unroll
+        for (int u = 0; u < ELL_BATCH; ++u) {
+          const int line = base + u * NW;
+          if (line < nlines && nn < NS) {
+            const bool on = tmx[u] > 0;
+            Ev[(size_t)line * NS + nn] = on ? vv[u] : 0.f;
+            Ei[(size_t)line * NS + nn] = (uint8_t)(on ? ii[u] : 0);
+          }
+        }
       }
     }
+    tm.lap(0);
     tc05::cp_async_wait_all();
     tcg::producers_sync();
+    tm.lap(1);
     if (S == 0) return;
     // ---- phase B: U_g = Q_g^T X_g (K x Din per graph) in 4 x 4 register tiles ---------------
     const int kq_n = K / 4;
@@ -260,13 +280,15 @@ struct SpectralPolicy {
             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     tcg::producers_sync();
+    tm.lap(2);
   }
 
   // After the last k-block of the edge step: VZ_g = V_g Z_g (N x H per graph) in 4 x 4 register
   // tiles into the (now dead) X_g buffer; overlaps with the tensor core draining its queue.
   __device__ void pre_epilogue(int sub) {
-    if (sub == 0 || S == 0) return;
+    if (sub == 0) return;
     tcg::producers_sync();              // every producer is done reading X_g
+    if (S == 0) return;
     const int hv = H / 4, nq_n = (N + 3) / 4;
     for (int task = tid; task < G * nq_n * hv; task += tcg::PRODUCER_THREADS) {
       const int hq = task % hv, gn = task / hv;          // gn = gg * nq_n + nq
@@ -297,6 +319,22 @@ struct SpectralPolicy {
               make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     tcg::producers_sync();
+  }
+
+  // Coalesced write-back of the tile's output rows (one warp per row, 16 bytes per lane).
+  __device__ void post_epilogue(int sub) {
+    if (sub == 0) return;
+    tcg::producers_sync();              // every chunk of every row is in shared memory
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = tcg::PRODUCER_THREADS / 32;
+    const int hv = H / 4;
+    for (int row = warp; row < G * N; row += NW) {
+      const int gg = row / N, nn = row - gg * N;
+      if (b0 + gg >= p.B) continue;
+      const float4* src = reinterpret_cast<const float4*>(Xs + (size_t)row * XP);
+      float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)(b0 + gg) * N + nn) * H);
+      for (int q4 = lane; q4 < hv; q4 += 32) dst[q4] = src[q4];
+    }
   }
 
   __device__ __forceinline__ void produce(int sub, int kb, float (&v)[32]) {
@@ -385,8 +423,27 @@ struct SpectralPolicy {
         x[4 * q + 0] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
       }
     }
-    tcg::store_row_chunk(n < N ? p.out + ((int64_t)b * N + n) * H : nullptr, H, p.bias,
-                         p.relu != 0, col, x);
+    // finished output chunk -> shared memory (in place over V Z / X); rows are written to HBM
+    // by post_epilogue() as full 512-byte lines
+    if (n < N && col < H) {
+      float4* o4 = reinterpret_cast<float4*>(Xs + ((size_t)g * N + n) * XP + col);
+      const bool relu = p.relu != 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = col + 4 * q + u;
+          float t = x[4 * q + u];
+          if (c < H) {
+            if (p.bias) t += __ldg(p.bias + c);
+            if (relu) t = fmaxf(t, 0.f);
+          }
+          y[u] = t;
+        }
+        o4[q] = make_float4(y[0], y[1], y[2], y[3]);
+      }
+    }
   }
 };
 

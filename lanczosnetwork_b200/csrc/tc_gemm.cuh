@@ -57,8 +57,21 @@ __device__ __forceinline__ Core carve(uint8_t* base) {
 
 // Optional phase timers (profiling aid): when a buffer is registered with lnb_debug_set_prof,
 // thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*8 + phase]:
-//   0 step_begin  1 k-loop (produce + handoff)  2 wait for the accumulator  3 epilogue store
+//   0 staging issue  1 staging wait  2 U = V^T X   (policy)   3 k-loop  4 pre_epilogue
+//   5 wait for the accumulator  6 tcgen05.ld  7 epilogue store
 __device__ unsigned long long* g_prof = nullptr;
+
+struct PhaseTimer {          // thread 0 of the CTA only; no-op unless a buffer is registered
+  unsigned long long* buf;
+  long long t0;
+  __device__ __forceinline__ void start(int cta, int tid) {
+    buf = (tid == 0 && g_prof) ? g_prof + cta * 8 : nullptr;
+    if (buf) t0 = clock64();
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if (buf) { long long t = clock64(); atomicAdd(&buf[slot], (unsigned long long)(t - t0)); t0 = t; }
+  }
+};
 
 __device__ __forceinline__ void producers_sync() {   // named barrier 1: all producer threads
   asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS) : "memory");
@@ -72,10 +85,11 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
 //   static int  num_kblocks(const Params&, int sub)
 //   static void w_coords(const Params&, int sub, int kb, int& col0, int& row0)   TMA coords of W
 //   Policy(const Params&, uint8_t* policy_smem, int tid)  constructed by producer threads only
-//   void step_begin(int m_tile, int sub, int kb_first)    may call producers_sync(); kb_first =
+//   void step_begin(int m_tile, int sub, int kb_first, PhaseTimer&)   may call producers_sync(); kb_first =
 //                                                         this thread's first k-block of the step
 //   void produce(int sub, int kb, float (&v)[32])         the 32 A values of this thread's row
 //   void pre_epilogue(int sub)                            after the step's last produce()
+//   void post_epilogue(int sub)                           after the step's last store()
 //   void store(int sub, int col, float (&x)[32])          accumulator columns [col, col+32) of
 //                                                         this thread's row (main + corr summed)
 template <class Policy>
@@ -129,11 +143,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       // stage (== group) of a k-block is its GLOBAL index % 3, like the TMA / MMA warps count it
       const int kb_first = (grp + NGROUPS - (int)(gk0 % NGROUPS)) % NGROUPS;
       gk0 += nkb;
-      unsigned long long* prof = g_prof;
-      long long t0 = 0;
-      if (prof && tid == 0) t0 = clock64();
-      pol.step_begin(m_tile, sub, kb_first);
-      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 0], (unsigned long long)(t - t0)); t0 = t; }
+      PhaseTimer tm;
+      tm.start(cta, tid);
+      pol.step_begin(m_tile, sub, kb_first, tm);
       for (int kb = kb_first; kb < nkb; kb += NGROUPS, ++use) {
         float v[32];
         if (!(p.dbg & 8)) pol.produce(sub, kb, v);
@@ -153,12 +165,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         __syncwarp();
         if (lane == 0) tc05::mbar_arrive(&c.full[grp]);
       }
+      tm.lap(3);
       pol.pre_epilogue(sub);
+      tm.lap(4);
       // ---- epilogue: 32-column chunk cc belongs to group cc % NGROUPS ----
-      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 1], (unsigned long long)(t - t0)); t0 = t; }
       tc05::mbar_wait(c.acc_full, (uint32_t)it & 1u);
       tc05::fence_after_thread_sync();
-      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 2], (unsigned long long)(t - t0)); t0 = t; }
+      tm.lap(5);
 #pragma unroll 1
       for (int cc = grp; cc < BN / 32; cc += NGROUPS) {
         const int col = cc * 32;
@@ -166,15 +179,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         tc05::tmem_ld_32x32(lane_addr + COL_MAIN + col, vm);
         tc05::tmem_ld_32x32(lane_addr + COL_CORR + col, vc);
         tc05::tmem_wait_ld();
+        tm.lap(6);
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
         pol.store(sub, col, x);
+        tm.lap(7);
       }
-      if (prof && tid == 0) { long long t = clock64(); atomicAdd(&prof[cta * 8 + 3], (unsigned long long)(t - t0)); }
       tc05::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) tc05::mbar_arrive(c.acc_empty);
+      if (lane == 0) tc05::mbar_arrive(c.acc_empty);    // accumulators are free again
+      pol.post_epilogue(sub);
     }
   } else if (warp == TMA_WARP) {
     // ================================ TMA producer (W tiles) ==============================

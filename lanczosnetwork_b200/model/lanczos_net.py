@@ -24,9 +24,6 @@ class LanczosNet(SpectralNetBase):
     self._build_head(dims)
     self._init_param()
 
-  def _initial_state(self, node_feat, dev):
-    return ops.embedding_rows(self._to(dev, node_feat).long(), self.embedding.weight)
-
   def forward(self, node_feat, L, D, V, label=None, mask=None):
     """
       node_feat: long B x N (atom ids); L: float B x N x N x (E+1); D: Ritz values B x K;
@@ -35,12 +32,14 @@ class LanczosNet(SpectralNetBase):
     """
     self._check_mode()
     dev = self._device()
-    L = self._to(dev, L, torch.float32).contiguous()
-    D = self._to(dev, D, torch.float32).contiguous()
-    V = self._to(dev, V, torch.float32).contiguous()
-    mask = self._to(dev, mask)
-    label = self._to(dev, label)
-    state = self._initial_state(node_feat, dev)
+    score = self._graph_forward(self._forward_impl, (node_feat, L, D, V, mask))
+    return self._finish(score, self._to(dev, label))
+
+  def _forward_impl(self, node_feat, L, D, V, mask):
+    L = L.float().contiguous()
+    D = D.float().contiguous()
+    V = V.float().contiguous()
+    state = ops.embedding_rows(node_feat.long(), self.embedding.weight)
 
     ctx = GraphContext(L, V)
     coeffs = table = None
@@ -55,5 +54,4 @@ class LanczosNet(SpectralNetBase):
       state = graph_conv_layer(state, ctx, coeff, False, self.short_diffusion_dist,
                                self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
                                self._wcache, 'filter.%d' % tt)
-    score = self._readout(state, mask)
-    return self._finish(score, label)
+    return self._readout(state, mask)

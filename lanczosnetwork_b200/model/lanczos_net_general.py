@@ -31,12 +31,14 @@ class LanczosNetGeneral(SpectralNetBase):
     """
     self._check_mode()
     dev = self._device()
-    L = self._to(dev, L, torch.float32).contiguous()
-    D = self._to(dev, D, torch.float32).contiguous()
-    V = self._to(dev, V, torch.float32).contiguous()
-    mask = self._to(dev, mask)
-    label = self._to(dev, label)
-    state = self._to(dev, node_feat, torch.float32).contiguous()
+    score = self._graph_forward(self._forward_impl, (node_feat, L, D, V, mask))
+    return self._finish(score, self._to(dev, label))
+
+  def _forward_impl(self, node_feat, L, D, V, mask):
+    L = L.float().contiguous()
+    D = D.float().contiguous()
+    V = V.float().contiguous()
+    state = node_feat.float().contiguous()
 
     ctx = GraphContext(L, V)
     coeffs = table = None
@@ -51,5 +53,4 @@ class LanczosNetGeneral(SpectralNetBase):
       state = graph_conv_layer(state, ctx, coeff, False, self.short_diffusion_dist,
                                self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
                                self._wcache, 'filter.%d' % tt)
-    score = self._readout(state, mask)
-    return self._finish(score, label)
+    return self._readout(state, mask)

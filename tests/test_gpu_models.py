@@ -157,3 +157,26 @@ def test_lanczos_plus_ritz_pipeline_reproduces_low_rank_operator():
                    theta.cpu().numpy().astype(np.float64), V.cpu().numpy().astype(np.float64))
   ref = np.einsum('bnk,bk,bmk->bnm', Vo, th, Vo)
   np.testing.assert_allclose(ours, ref, atol=5e-5)
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates():
+  g = load_golden('lanczosnet_qm8.npz')
+  mod, _ = _build(LanczosNet, configs.qm8_lanczos_net(), int(g['weight_seed']))
+  args = [_t(g[k]).to(dev()) for k in ('node_feat', 'L', 'D', 'V')]
+  mask = _t(g['node_mask']).to(dev())
+  with torch.no_grad():
+    mod.use_cuda_graph = False
+    eager = mod(*args, mask=mask)
+    mod.use_cuda_graph = True
+    first = mod(*args, mask=mask)          # capture
+    replay = mod(*args, mask=mask)         # replay
+    assert torch.equal(eager, first) and torch.equal(eager, replay)
+    # host (pinned) inputs go straight into the static buffers
+    host = [_t(g[k]).pin_memory() for k in ('node_feat', 'L', 'D', 'V')]
+    assert torch.equal(mod(*host, mask=_t(g['node_mask']).pin_memory()), eager)
+    # an in-place weight update invalidates the captured graph (parameter version changes)
+    mod.filter[7].bias.add_(1.0)
+    shifted = mod(*args, mask=mask)
+    assert not torch.equal(shifted, eager)
+    mod.use_cuda_graph = False
+    assert torch.equal(mod(*args, mask=mask), shifted)

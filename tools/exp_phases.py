@@ -30,8 +30,8 @@ b.record()
 torch.cuda.synchronize()
 _lib.load().lnb_debug_set_prof(None)
 p = prof.cpu().reshape(148, 8).double()
-names = ['step_begin', 'k-loop', 'acc wait', 'epilogue']
+names = ['stage issue', 'stage wait', 'U', 'k-loop', 'pre_epi', 'acc wait', 'tmem ld', 'store']
 print('kernel %.1f us; per-CTA clock64 totals (cycles), CTAs 0..3 and mean over CTAs with 2 tiles:' % (a.elapsed_time(b) * 1e3))
-for i in range(4):
+for i in range(8):
   print('  %-10s cta0 %8d cta1 %8d cta120 %8d  mean(first 100) %8d' % (names[i], p[0, i], p[1, i], p[120, i], p[:100, i].mean()))
-print('  sum cta0 %d' % p[0, :4].sum())
+print('  sum cta0 %d' % p[0, :8].sum())
