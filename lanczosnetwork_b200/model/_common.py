@@ -5,6 +5,8 @@ unchanged (model/lanczos_net.py:15-93, utils/train_helper.py:14-32): ``embedding
 ``filter.{i}.{weight,bias}``, ``spectral_filter.{l}.{0,2,4,6}.{weight,bias}``,
 ``att_func.0.{weight,bias}``.  The forward math lives in CUDA (lanczosnetwork_b200.ops).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -116,7 +118,7 @@ class SpectralNetBase(nn.Module):
   # (CUDA streams and graphs instead of a tracing compiler).  Inputs are copied into static
   # buffers (H2D straight from pinned host memory, or D2D), the graph is replayed, the small
   # score tensor is cloned out.  Recaptured when shapes or any parameter version change.
-  use_cuda_graph = True
+  use_cuda_graph = os.environ.get('LNB_NO_GRAPH', '0') != '1'   # LNB_NO_GRAPH=1: eager (profiling)
 
   def _param_signature(self):
     return tuple((p.data_ptr(), p._version) for p in self.parameters())
