@@ -92,21 +92,27 @@ int lnb_linear_tf32x3_grouped(lnb_stream_t stream, const float* A, const float* 
  * Fused spectral graph-convolution layer (model/lanczos_net.py:157-182):
  *   out[b,n,:] = act( cat_c(M_c X_b)[n,:] W^T + bias ),  channels c = S long scales
  *   (V diag(coeff[:,:,s]) V^T) followed by the E1 edge-type operators L[...,e].
- * One persistent tcgen05 kernel: message tiles are produced on CUDA cores straight into tensor
- * memory (never written to HBM) and multiplied by TMA-staged W_hi/W_lo tiles (3xTF32).
- * lnb_graph_prepare compresses the (layer-invariant) dense operators once per forward:
- *   ell_val/ell_idx [B,E1,N,N] (t-major ELL rows, zero-filled to ell_max[b,e]), qext[b] =
- *   {rows, columns} of Q that are not identically zero.  Skipping exact zeros is exact.
- * Requirements of the fused kernel: N <= 128, Din % 32 == 0, K <= 32, H % 4 == 0; W is
- * [H, (S+E1)*Din].  Returns LNB_ERR_UNSUPPORTED otherwise (callers use the unfused ops).
+ * One persistent tcgen05 kernel; no intermediate of the reference (N x N filters, [B*N, C*D]
+ * messages) exists in HBM.  lnb_graph_prepare runs once per forward (the operators are layer
+ * invariant):
+ *   ell_val/ell_idx [B,E1,N,N]  t-major ELL rows of every operator channel, ell_max [B,E1];
+ *   gext [B,2] = {n_eff, k_eff}: operators / Q are identically zero beyond these extents;
+ *   tiles [B+2]: tiles[0] = T, tiles[1+t] = first graph of packed tile t (next-fit:
+ *                sum n_eff <= 128, sum ceil4(k_eff) <= 128, <= 32 graphs), tiles[1+T] = B.
+ * Skipping exact zeros / padded rows is exact.  write_pad != 0 also writes the constant rows
+ * act(bias) of padded nodes (needed when the full [B,N,H] tensor is read afterwards).
+ * Requirements of the fused kernel: N <= 128, Din % 32 == 0, K % 4 == 0, K <= 32, H % 4 == 0,
+ * H <= 128, E1 <= 16; W is [H, (S+E1)*Din].  Returns LNB_ERR_UNSUPPORTED otherwise (callers
+ * use the unfused ops).
  * ------------------------------------------------------------------------------------- */
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
-                      int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* qext);
+                      int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* gext,
+                      int32_t* tiles);
 int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q, const float* coeff,
                             const float* ell_val, const uint8_t* ell_idx, const int32_t* ell_max,
-                            const int32_t* qext, const float* W_hi, const float* W_lo,
-                            const float* bias, int B, int N, int Din, int E1, int K, int S, int H,
-                            int relu, float* out);
+                            const int32_t* gext, const int32_t* tiles, const float* W_hi,
+                            const float* W_lo, const float* bias, int B, int N, int Din, int E1,
+                            int K, int S, int H, int relu, int write_pad, float* out);
 
 /* ---------------------------------------------------------------------------------------
  * Embedding rows (model/lanczos_net.py:154): out[r, :] = table[idx[r], :].

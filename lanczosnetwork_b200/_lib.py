@@ -45,11 +45,11 @@ SIGNATURES = {
     'lnb_linear_tf32x3_grouped':
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_graph_prepare': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p,
-                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'lnb_spectral_conv_fused':
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
-                 ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int,
-                 c_int, c_int, c_f32p]),
+                 ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int,
+                 c_int, c_int, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_debug_set_prof': (c_int, [ctypes.c_void_p]),
     'lnb_embedding_rows': (c_int, [c_stream, ctypes.c_void_p, c_f32p, c_i64, c_int, c_int, c_f32p]),
     'lnb_ritz_power_table': (c_int, [c_stream, c_f32p, c_i64, ctypes.POINTER(c_int), c_int, c_f32p]),

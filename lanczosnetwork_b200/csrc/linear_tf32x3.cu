@@ -11,6 +11,7 @@
 namespace {
 
 struct RowLoadPolicy {
+  static constexpr int kStagesB = 3;
   // groups > 1: block-diagonal ("grouped") layer -- column block g of A [M, groups*K] times
   // W_g [N, K] (stacked [groups*N, K]) into column block g of C [M, groups*N].
   struct Params {
@@ -88,7 +89,7 @@ struct RowLoadPolicy {
   }
 };
 
-constexpr size_t SMEM_BYTES = tcg::CORE_SMEM + 1024;
+constexpr size_t SMEM_BYTES = tcg::core_smem(RowLoadPolicy::kStagesB) + 1024;
 
 }  // namespace
 

@@ -1,65 +1,76 @@
 // Fused spectral graph-convolution layer (reference: model/lanczos_net.py:157-182):
 //     msg = [ V diag(f_s) V^T X  (s < S) ] ++ [ L_e X  (e <= E) ];   X' = ReLU(cat(msg) W^T + b)
-// as ONE persistent tcgen05 kernel (skeleton: tc_gemm.cuh).  The [B*N, C*D] message matrix of
-// the unfused path (204 MB / layer at B=1024) never exists: producer warps compute each
-// 128 x 32 message tile on CUDA cores and store it straight into tensor memory, where the
-// tensor core multiplies it by the TMA-staged weight tile.
+// as ONE persistent tcgen05 kernel (skeleton: tc_gemm.cuh).  Nothing of the reference's
+// intermediate tensors exists in HBM: not the N x N filters, not the [B*N, C*D] message matrix.
 //
-// Tile = 128 rows = G graph slots of NS rows (NS = 32/64/128 >= N), so a warp never straddles
-// graphs: the right-hand sides X_g / U_g = V_g^T X_g are read from shared memory as warp-wide
-// broadcasts.  Edge-type operators are consumed through a per-forward ELL compression of the
-// dense L[B,N,N,E+1] (lnb_graph_prepare): the QM8 operators are ~4 % dense and skipping exact
-// zeros is exact, so the edge channels cost ~1/10 of the dense product and the kernel is bound
-// by the tensor pipe, not by message production.  Long-scale channels use the factored form
-// (V * f_s) (V^T X) with the Ritz extent k_eff (zero-padded pairs skipped, also exact).
+// Tiles are PACKED: lnb_graph_prepare measures every graph's real extent (n_eff rows/columns
+// of the operators that are not identically zero, k_eff non-zero Ritz vectors) and assigns
+// consecutive graphs to 128-row tiles by next-fit (sum n_eff <= 128, sum ceil4(k_eff) <= 128,
+// <= 32 graphs).  A QM8-shaped batch of 1024 molecules (16 real atoms on average, padded to 26)
+// becomes ~137 tiles -- one wave of the 148 SMs -- instead of 256 fixed-slot tiles.  Rows that
+// are pure padding are never multiplied; their (constant) output act(b) is written directly.
+// Dropping exact zeros is exact, so the result equals the dense reference for arbitrary inputs.
+//
+// Two accumulator lifetimes ("steps") per tile:
+//   step 0  Z = sum_s (f_s . U) W_s^T      rows = (graph, Ritz index): the producer only scales
+//           rows of U_g = V_g^T X_g (shared memory) by the filter coefficient; Z is drained to
+//           shared memory;
+//   step 1  E = sum_e (L_e X) W_e^T        rows = (graph, node): sparse ELL rows of the operators
+//           times X; epilogue: out = act(E + V Z + b), written back as full 512-byte rows.
+// Algebra: sum_s V diag(f_s) V^T X W_s^T = V [ sum_s diag(f_s) (V^T X) W_s^T ].
 #include "tc_gemm.cuh"
 
 namespace {
 
-constexpr int KMAX = 32;        // max Ritz pairs held per thread in the U = V^T X prologue
+constexpr int KMAX = 32;        // max Ritz pairs
+constexpr int GMAX = 32;        // max graphs per tile
+constexpr int RMAX = 128;       // rows per tile
+constexpr int EMAX = 16;        // max operator channels
+constexpr int FR = 8;           // filter coefficients held in registers per row
 
 // --------------------------------------------------------------------------------------------
-// Per-forward operator compression.
-//   ell_val/ell_idx [B, E1, N(t), N(n)]: the t-th non-zero of row n of channel e, stored
-//   t-major so a warp (consecutive n) reads consecutive addresses; zero-filled up to
-//   ell_max[b,e] = max non-zeros of any row.  qext[b] = {n_eff, k_eff}: Q[b] is zero outside
-//   its leading n_eff rows / k_eff columns.
+// Per-forward operator compression and extents.
+//   ell_val/ell_idx [B, E1, N(t), N(n)]: the t-th non-zero of row n of channel e (t-major so a
+//   warp of consecutive rows reads consecutive addresses); ell_max[b,e] = max non-zeros per row.
+//   gext[b] = {n_eff, k_eff}: the operators are zero outside their leading n_eff rows/columns,
+//   Q[b] is zero outside its leading n_eff rows / k_eff columns.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, int N, int E1, int K,
                      float* __restrict__ ell_val, uint8_t* __restrict__ ell_idx,
-                     int32_t* __restrict__ ell_max, int32_t* __restrict__ qext) {
-  __shared__ int s_max[64];
+                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext) {
+  __shared__ int s_max[EMAX];
   __shared__ int s_ext[2];
   const int b = blockIdx.x, tid = threadIdx.x;
-  if (tid < 64) s_max[tid] = 0;
+  if (tid < EMAX) s_max[tid] = 0;
   if (tid < 2) s_ext[tid] = 0;
   __syncthreads();
   const float* Lb = L + (int64_t)b * N * N * E1;
   const int pairs = N * E1;
-  // phase 1: compact every (row n, channel e); pair index p = n*E1 + e keeps the E1 channels of
-  // one row in adjacent threads -> their loads of L[b,n,i,:] coalesce.
+  // pair index p = n*E1 + e keeps the E1 channels of one row in adjacent threads -> their loads
+  // of L[b,n,i,:] coalesce.
+  int ne = 0;
   for (int p0 = 0; p0 < pairs; p0 += 256) {
     const int p = p0 + tid;
-    int cnt = 0;
     if (p < pairs) {
       const int n = p / E1, e = p % E1;
       float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
       uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
+      int cnt = 0;
       for (int i = 0; i < N; ++i) {
-        float v = Lb[((int64_t)n * N + i) * E1 + e];
+        const float v = Lb[((int64_t)n * N + i) * E1 + e];
         if (v != 0.f) {
           val[(int64_t)cnt * N] = v;
           idx[(int64_t)cnt * N] = (uint8_t)i;
           ++cnt;
+          ne = max(ne, max(n, i) + 1);
         }
       }
       atomicMax(&s_max[e], cnt);
     }
   }
-  // Q extents
   const float* Qb = Q + (int64_t)b * N * K;
-  int ne = 0, ke = 0;
+  int ke = 0;
   for (int i = tid; i < N * K; i += 256) {
     if (Qb[i] != 0.f) {
       ne = max(ne, i / K + 1);
@@ -69,36 +80,53 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
   if (ne) atomicMax(&s_ext[0], ne);
   if (ke) atomicMax(&s_ext[1], ke);
   __syncthreads();
-  // phase 2: zero-fill the tail of every row up to the channel maximum (recount = cheap)
-  for (int p0 = 0; p0 < pairs; p0 += 256) {
-    const int p = p0 + tid;
-    if (p < pairs) {
-      const int n = p / E1, e = p % E1;
-      int cnt = 0;
-      for (int i = 0; i < N; ++i) cnt += (Lb[((int64_t)n * N + i) * E1 + e] != 0.f) ? 1 : 0;
-      float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
-      uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
-      for (int t = cnt; t < s_max[e]; ++t) {
-        val[(int64_t)t * N] = 0.f;
-        idx[(int64_t)t * N] = 0;
-      }
-    }
-  }
   if (tid < E1) ell_max[b * E1 + tid] = s_max[tid];
-  if (tid < 2) qext[b * 2 + tid] = s_ext[tid];
+  if (tid < 2) gext[b * 2 + tid] = s_ext[tid];
+}
+
+// Next-fit assignment of consecutive graphs to tiles.  tiles[0] = T, tiles[1 + t] = first graph
+// of tile t, tiles[1 + T] = B.  One CTA; the extents are staged through shared memory in
+// chunks so the sequential scan runs on on-chip data.
+__global__ void __launch_bounds__(256)
+tile_assign_kernel(const int32_t* __restrict__ gext, int B, int32_t* __restrict__ tiles) {
+  constexpr int CH = 2048;
+  __shared__ int s_n[CH], s_k[CH];
+  __shared__ int st[4];   // rows, krows, count, T
+  const int tid = threadIdx.x;
+  if (tid == 0) { st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 0; tiles[1] = 0; }
+  __syncthreads();
+  for (int c0 = 0; c0 < B; c0 += CH) {
+    const int cn = min(CH, B - c0);
+    for (int i = tid; i < cn; i += 256) {
+      s_n[i] = gext[(c0 + i) * 2];
+      s_k[i] = (gext[(c0 + i) * 2 + 1] + 3) & ~3;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rows = st[0], kr = st[1], cnt = st[2], T = st[3];
+      for (int i = 0; i < cn; ++i) {
+        const int n = s_n[i], k = s_k[i];
+        if (cnt > 0 && (rows + n > RMAX || kr + k > RMAX || cnt == GMAX)) {
+          ++T;
+          tiles[1 + T] = c0 + i;
+          rows = 0; kr = 0; cnt = 0;
+        }
+        rows += n; kr += k; ++cnt;
+      }
+      st[0] = rows; st[1] = kr; st[2] = cnt; st[3] = T;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int T = st[3] + (st[2] > 0 ? 1 : 0);
+    tiles[0] = T;
+    tiles[1 + T] = B;
+  }
 }
 
 // --------------------------------------------------------------------------------------------
-// Two accumulator lifetimes ("steps") per tile of G graphs:
-//   step 0  Z_g = sum_s (f_s . U_g) W_s^T      rows = (graph, Ritz index k): the producer only
-//           scales rows of U_g = V_g^T X_g (staged in smem) by the filter coefficient -- the
-//           N x N filters and even the per-node long-scale messages never exist; the result
-//           (K x H per graph) is drained to shared memory;
-//   step 1  E = sum_e (L_e X_g) W_e^T          rows = (graph, node): sparse ELL rows times X_g;
-//           epilogue: out = ReLU(E + V_g Z_g + b).
-// Algebra: sum_s V diag(f_s) V^T X W_s^T = V [ sum_s diag(f_s) (V^T X) W_s^T ].
-// --------------------------------------------------------------------------------------------
 struct SpectralPolicy {
+  static constexpr int kStagesB = 2;      // two W stages: shared memory goes to the packed tile
   struct Params {
     const float* X;         // [B, N, Din]
     const float* Q;         // [B, N, K]
@@ -106,20 +134,19 @@ struct SpectralPolicy {
     const float* ell_val;   // [B, E1, N, N]
     const uint8_t* ell_idx; // [B, E1, N, N]
     const int32_t* ell_max; // [B, E1]
-    const int32_t* qext;    // [B, 2]
+    const int32_t* gext;    // [B, 2]
+    const int32_t* tiles;   // [B + 2]
     const float* bias;      // [H]
     float* out;             // [B, N, H]
-    int B, N, Din, E1, K, S, H, relu, NS;
-    int TCAP;               // ELL entries per (row, channel) staged in shared memory
+    int B, N, Din, E1, K, S, H, relu;
+    int LB;                 // ELL lines (channel, t) that fit in shared memory
+    int write_pad;          // also write the constant rows of padded nodes (needed by readers of
+                            // the full [B,N,H] tensor, i.e. after the last layer)
     int dbg;                // debug experiment flags (LNB_DBG), 0 in production
   };
-  static __device__ __forceinline__ int m_tiles(const Params& p) {
-    const int G = tcg::BM / p.NS;
-    return (p.B + G - 1) / G;
-  }
   static __device__ __forceinline__ int num_steps(const Params& p, int cta, int ncta) {
-    const int t = m_tiles(p);
-    const int mine = t > cta ? (t - cta + ncta - 1) / ncta : 0;
+    const int T = __ldg(p.tiles);
+    const int mine = T > cta ? (T - cta + ncta - 1) / ncta : 0;
     return p.S > 0 ? 2 * mine : mine;
   }
   static __device__ __forceinline__ void decode(const Params& p, int cta, int ncta, int it,
@@ -135,114 +162,160 @@ struct SpectralPolicy {
     row0 = 0;
   }
 
+  struct Tables {
+    int gs, ng, Rtot, Ztot, nquads, nlines;
+    int nbase[GMAX + 1], kbase[GMAX + 1], gn[GMAX], gk[GMAX];
+    int cnt_e[EMAX], base_e[EMAX], tmax_e[EMAX];
+    uint8_t emax[GMAX][EMAX];
+    uint8_t row_g[RMAX], row_n[RMAX], z_g[RMAX], z_k[RMAX];
+    uint8_t q_g[RMAX / 4 + GMAX], q_n0[RMAX / 4 + GMAX];
+    uint8_t line_e[256], line_t[256];
+  };
+
   const Params& p;
   const int tid, r;
-  const int N, Din, K, S, E1, H, NS, TCAP;   // hot parameters in registers
-  const int G, XP, UP, ZP, KP;               // slots per tile, padded row strides
-  float* Xs;                // X_g [G][N][XP]; reused for V_g Z_g after the edge k-loop
-  float* UZ;                // U_g [G][K][UP] during step 0, Z_g [G][K][ZP] afterwards
-  float* Qs;                // [G][N][KP]
-  float* Fs;                // [G][K][S]
-  int* Es;                  // [G][E1 + 2]  ell_max per channel, n_eff, k_eff
-  float* Ev;                // [G][E1][TCAP][NS] staged ELL values
-  uint8_t* Ei;              // [G][E1][TCAP][NS] staged ELL column indices
-  int b0;                   // first graph of the tile
+  const int N, Din, K, S, E1, H, XP;      // hot parameters in registers
+  float* Xs;                // X rows [RMAX][XP]; reused for V Z + the finished output rows
+  float* UZ;                // U rows (graph,k) [RMAX][XP] during step 0, Z afterwards
+  float* Qs;                // [RMAX][K]
+  Tables* tb;
+  float* Ev;                // [LB][RMAX] staged ELL values
+  uint8_t* Ei;              // [LB][RMAX] staged ELL columns as tile-local row indices
+  float fr[FR];             // this (graph, k) row's filter coefficients f[k, 0..S)
+
+  static __host__ __device__ constexpr size_t tables_bytes() { return (sizeof(Tables) + 15) & ~size_t(15); }
 
   __device__ SpectralPolicy(const Params& p_, uint8_t* smem, int tid_)
       : p(p_), tid(tid_), r(tid_ & 127), N(p_.N), Din(p_.Din), K(p_.K), S(p_.S), E1(p_.E1),
-        H(p_.H), NS(p_.NS), TCAP(p_.TCAP), G(tcg::BM / p_.NS),
-        XP((p_.Din > p_.H ? p_.Din : p_.H) + 4), UP(p_.Din + 4), ZP(p_.H + 4), KP(p_.K), b0(0) {
+        H(p_.H), XP((p_.Din > p_.H ? p_.Din : p_.H) + 4) {
     Xs = reinterpret_cast<float*>(smem);
-    UZ = Xs + (size_t)G * N * XP;
-    Qs = UZ + (size_t)G * K * ((Din > H ? Din : H) + 4);
-    Fs = Qs + (size_t)G * N * KP;
-    Es = reinterpret_cast<int*>(Fs + (size_t)G * K * S);
-    Ev = reinterpret_cast<float*>(Es + (size_t)G * (E1 + 2));
-    Ei = reinterpret_cast<uint8_t*>(Ev + (size_t)G * E1 * TCAP * NS);
+    UZ = Xs + (size_t)RMAX * XP;
+    Qs = UZ + (size_t)RMAX * XP;
+    uint8_t* t8 = reinterpret_cast<uint8_t*>(Qs + (size_t)RMAX * K);
+    tb = reinterpret_cast<Tables*>(t8);
+    Ev = reinterpret_cast<float*>(t8 + tables_bytes());
+    Ei = reinterpret_cast<uint8_t*>(Ev + (size_t)p.LB * RMAX);
   }
-
-  static size_t smem_bytes(int N, int Din, int K, int S, int E1, int H, int NS) {
-    const int G = tcg::BM / NS;
+  static size_t smem_fixed(int Din, int K, int H) {
     const int W = (Din > H ? Din : H) + 4;
-    size_t fl = (size_t)G * N * W + (size_t)G * K * W + (size_t)G * N * K + (size_t)G * K * S;
-    return fl * 4 + (size_t)G * (E1 + 2) * 4 + 16;
+    return (size_t)2 * RMAX * W * 4 + (size_t)RMAX * K * 4 + tables_bytes() + 16;
   }
-  static size_t ell_stage_bytes(int E1, int NS, int tcap) {
-    return (size_t)(tcg::BM / NS) * E1 * tcap * NS * 5;
+  static size_t ell_line_bytes() { return (size_t)RMAX * 5; }
+
+  // ------------------------------------------------------------------------------------------
+  __device__ void build_tables(int m_tile) {
+    // executed by warp 0: lane j <-> j-th graph of the tile
+    const int lane = tid & 31;
+    const int gs = __ldg(p.tiles + 1 + m_tile), ge = __ldg(p.tiles + 2 + m_tile);
+    const int ng = ge - gs;
+    int n = 0, k = 0;
+    if (lane < ng) {
+      n = __ldg(p.gext + (gs + lane) * 2);
+      k = __ldg(p.gext + (gs + lane) * 2 + 1);
+    }
+    const int kp = (k + 3) & ~3, nq = (n + 3) >> 2;
+    int pn = n, pk = kp, pq = nq;                     // inclusive prefix sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, pn, o), bq = __shfl_up_sync(0xffffffffu, pk, o);
+      const int c = __shfl_up_sync(0xffffffffu, pq, o);
+      if (lane >= o) { pn += a; pk += bq; pq += c; }
+    }
+    const int nb = pn - n, kb = pk - kp, qb = pq - nq;
+    if (lane < ng) {
+      tb->nbase[lane] = nb; tb->kbase[lane] = kb; tb->gn[lane] = n; tb->gk[lane] = k;
+      for (int i = 0; i < n; ++i) { tb->row_g[nb + i] = (uint8_t)lane; tb->row_n[nb + i] = (uint8_t)i; }
+      for (int i = 0; i < kp; ++i) { tb->z_g[kb + i] = (uint8_t)lane; tb->z_k[kb + i] = (uint8_t)i; }
+      for (int i = 0; i < nq; ++i) { tb->q_g[qb + i] = (uint8_t)lane; tb->q_n0[qb + i] = (uint8_t)(4 * i); }
+    }
+    const int Rtot = __shfl_sync(0xffffffffu, pn, 31), Ztot = __shfl_sync(0xffffffffu, pk, 31);
+    const int nquads = __shfl_sync(0xffffffffu, pq, 31);
+    // per-channel maximum row length over the tile's graphs, per-graph row lengths
+    for (int e = 0; e < E1; ++e) {
+      int m = (lane < ng) ? __ldg(p.ell_max + (gs + lane) * E1 + e) : 0;
+      if (lane < ng) tb->emax[lane][e] = (uint8_t)m;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) tb->tmax_e[e] = m;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      tb->gs = gs; tb->ng = ng; tb->Rtot = Rtot; tb->Ztot = Ztot; tb->nquads = nquads;
+      tb->nbase[ng] = Rtot; tb->kbase[ng] = Ztot;
+      int left = p.LB, base = 0;
+      for (int e = 0; e < E1; ++e) {            // staged lines per channel, in channel order
+        const int c = min(tb->tmax_e[e], left);
+        tb->cnt_e[e] = c; tb->base_e[e] = base;
+        for (int t = 0; t < c; ++t) { tb->line_e[base + t] = (uint8_t)e; tb->line_t[base + t] = (uint8_t)t; }
+        base += c; left -= c;
+      }
+      tb->nlines = base;
+    }
   }
 
   __device__ void step_begin(int m_tile, int sub, int /*kb_first*/, tcg::PhaseTimer& tm) {
-    tcg::producers_sync();              // previous step's smem readers / Z writers are done
+    tcg::producers_sync();              // previous step's smem readers / writers are done
     if (sub == 1 && S > 0) return;      // tile state was staged by step 0
-    b0 = m_tile * G;
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = tcg::PRODUCER_THREADS / 32;
-    // ---- phase A: asynchronous copies (cp.async), one warp per row, no div/mod per element --
+    if (warp == 0) build_tables(m_tile);
+    tcg::producers_sync();
+    const int gs = tb->gs, Rtot = tb->Rtot, Ztot = tb->Ztot;
+    // ---- phase A: asynchronous copies of the real rows of X and Q (one warp per row) --------
     const int dv = Din / 4;
-    for (int row = warp; row < G * N; row += NW) {
-      const int gg = row / N, nn = row - gg * N;
+    for (int row = warp; row < Rtot; row += NW) {
+      const int64_t src_row = (int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row];
+      const float* xsrc = p.X + src_row * Din;
       float* xd = Xs + (size_t)row * XP;
-      float* qd = Qs + (size_t)row * KP;
-      if (b0 + gg < p.B) {
-        const float* xsrc = p.X + ((int64_t)(b0 + gg) * N + nn) * Din;
-        for (int q4 = lane; q4 < dv; q4 += 32) tc05::cp_async_16(xd + 4 * q4, xsrc + 4 * q4);
-        const float* qsrc = p.Q + ((int64_t)(b0 + gg) * N + nn) * K;
-        for (int k = lane; k < K; k += 32) tc05::cp_async_4(qd + k, qsrc + k);
-      } else {
-        for (int q4 = lane; q4 < dv; q4 += 32)
-          *reinterpret_cast<float4*>(xd + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = lane; k < K; k += 32) qd[k] = 0.f;
-      }
+      for (int q4 = lane; q4 < dv; q4 += 32) tc05::cp_async_16(xd + 4 * q4, xsrc + 4 * q4);
+      const float* qsrc = p.Q + src_row * K;
+      float* qd = Qs + (size_t)row * K;
+      for (int k = lane; k < K; k += 32) tc05::cp_async_4(qd + k, qsrc + k);
     }
-    for (int e = tid; e < G * K * S; e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (K * S);
-      if (b0 + gg < p.B) tc05::cp_async_4(Fs + e, p.coeff + (int64_t)b0 * K * S + e);
-      else Fs[e] = 0.f;
-    }
-    for (int e = tid; e < G * (E1 + 2); e += tcg::PRODUCER_THREADS) {
-      const int gg = e / (E1 + 2), w = e % (E1 + 2);
-      int v = 0;
-      if (b0 + gg < p.B)
-        v = (w < E1) ? __ldg(p.ell_max + (b0 + gg) * E1 + w) : __ldg(p.qext + (b0 + gg) * 2 + (w - E1));
-      Es[e] = v;
-    }
-    // first TCAP ELL entries per (row, channel): one warp per (graph, channel, t) line of NS
-    // rows.  Loads are unconditional (the arrays are fully allocated) and masked afterwards;
-    // a batch of ELL_BATCH lines is loaded into registers before anything is consumed so the
-    // HBM / L2 latencies of the batch overlap.
-    constexpr int ELL_BATCH = 6;
-    const int nlines = G * E1 * TCAP;
-    for (int base = warp; base < nlines; base += NW * ELL_BATCH) {
-      for (int sub32 = 0; sub32 < NS; sub32 += 32) {
-        const int nn = sub32 + lane;
-        float vv[ELL_BATCH];
-        int ii[ELL_BATCH], tmx[ELL_BATCH];
+    // ---- staged ELL lines: line l <-> (channel e, entry t); a warp per line, batched loads ---
+    {
+      constexpr int ELL_BATCH = 4;
+      const int nlines = tb->nlines;
+      for (int base = warp; base < nlines; base += NW * ELL_BATCH) {
+        for (int r0 = 0; r0 < Rtot; r0 += 32) {
+          const int rr = r0 + lane;
+          float vv[ELL_BATCH];
+          int ii[ELL_BATCH];
 #pragma unroll
-        for (int u = 0; u < ELL_BATCH; ++u) {
-          const int line = base + u * NW;
-          vv[u] = 0.f; ii[u] = 0; tmx[u] = 0;
-          if (line < nlines) {
-            const int t = line % TCAP, gc = line / TCAP;     // gc = gg * E1 + ch
-            const int gg = gc / E1;
-            if (b0 + gg < p.B && t < N) {
-              tmx[u] = __ldg(p.ell_max + (int64_t)b0 * E1 + gc) - t;   // > 0  <=>  t < tmax
-              if (nn < N) {
-                const int64_t off = (((int64_t)b0 * E1 + gc) * N + t) * N + nn;
+          for (int u = 0; u < ELL_BATCH; ++u) {
+            const int line = base + u * NW;
+            vv[u] = 0.f; ii[u] = 0;
+            if (line < nlines && rr < Rtot) {
+              const int e = tb->line_e[line], t = tb->line_t[line];
+              const int g = tb->row_g[rr], n = tb->row_n[rr];
+              if (t < tb->emax[g][e]) {
+                const int64_t off = (((int64_t)(gs + g) * E1 + e) * N + t) * N + n;
                 vv[u] = __ldg(p.ell_val + off);
-                ii[u] = __ldg(p.ell_idx + off);
+                ii[u] = tb->nbase[g] + __ldg(p.ell_idx + off);
               }
             }
           }
-        }
 #pragma unroll
-        for (int u = 0; u < ELL_BATCH; ++u) {
-          const int line = base + u * NW;
-          if (line < nlines && nn < NS) {
-            const bool on = tmx[u] > 0;
-            Ev[(size_t)line * NS + nn] = on ? vv[u] : 0.f;
-            Ei[(size_t)line * NS + nn] = (uint8_t)(on ? ii[u] : 0);
+          for (int u = 0; u < ELL_BATCH; ++u) {
+            const int line = base + u * NW;
+            if (line < nlines && rr < Rtot) {
+              Ev[(size_t)line * RMAX + rr] = vv[u];
+              Ei[(size_t)line * RMAX + rr] = (uint8_t)ii[u];
+            }
           }
         }
+      }
+    }
+    // this thread's (graph, k) row: filter coefficients into registers
+#pragma unroll
+    for (int i = 0; i < FR; ++i) fr[i] = 0.f;
+    if (S > 0 && r < Ztot) {
+      const int g = tb->z_g[r], k = tb->z_k[r];
+      if (k < K) {
+        const float* f = p.coeff + ((int64_t)(gs + g) * K + k) * S;
+#pragma unroll
+        for (int i = 0; i < FR; ++i)
+          if (i < S) fr[i] = __ldg(f + i);
       }
     }
     tm.lap(0);
@@ -250,23 +323,22 @@ struct SpectralPolicy {
     tcg::producers_sync();
     tm.lap(1);
     if (S == 0) return;
-    // ---- phase B: U_g = Q_g^T X_g (K x Din per graph) in 4 x 4 register tiles ---------------
-    const int kq_n = K / 4;
-    for (int task = tid; task < G * kq_n * dv; task += tcg::PRODUCER_THREADS) {
-      const int dq = task % dv, gk = task / dv;          // gk = gg * kq_n + kq
-      const int gg = gk / kq_n, kq = gk - gg * kq_n;
-      const int n_eff = Es[gg * (E1 + 2) + E1];
+    // ---- phase B: U_g = Q_g^T X_g in 4 x 4 register tiles over (graph,k) rows x columns -----
+    for (int task = tid; task < (Ztot >> 2) * dv; task += tcg::PRODUCER_THREADS) {
+      const int dq = task % dv, zq = task / dv;
+      const int g = tb->z_g[4 * zq], k0 = tb->z_k[4 * zq];
+      const int n_g = tb->gn[g], nb = tb->nbase[g];
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      const float* xs = Xs + (size_t)gg * N * XP + 4 * dq;
-      const float* qs = Qs + (size_t)gg * N * KP + 4 * kq;
+      const float* xs = Xs + (size_t)nb * XP + 4 * dq;
+      const float* qs = Qs + (size_t)nb * K + k0;
 #pragma unroll 2
-      for (int nn = 0; nn < n_eff; ++nn) {
+      for (int nn = 0; nn < n_g; ++nn) {
         const float4 x4 = *reinterpret_cast<const float4*>(xs + (size_t)nn * XP);
-        const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)nn * KP);
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)nn * K);
         const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
         const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -276,78 +348,30 @@ struct SpectralPolicy {
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(UZ + ((size_t)gg * K + 4 * kq + i) * UP + 4 * dq) =
+        *reinterpret_cast<float4*>(UZ + (size_t)(4 * zq + i) * XP + 4 * dq) =
             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     tcg::producers_sync();
     tm.lap(2);
   }
 
-  // After the last k-block of the edge step: VZ_g = V_g Z_g (N x H per graph) in 4 x 4 register
-  // tiles into the (now dead) X_g buffer; overlaps with the tensor core draining its queue.
-  __device__ void pre_epilogue(int sub) {
-    if (sub == 0) return;
-    tcg::producers_sync();              // every producer is done reading X_g
-    if (S == 0) return;
-    const int hv = H / 4, nq_n = (N + 3) / 4;
-    for (int task = tid; task < G * nq_n * hv; task += tcg::PRODUCER_THREADS) {
-      const int hq = task % hv, gn = task / hv;          // gn = gg * nq_n + nq
-      const int gg = gn / nq_n, nq = gn - gg * nq_n;
-      const int k_eff = Es[gg * (E1 + 2) + E1 + 1];
-      float acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      const float* z = UZ + (size_t)gg * K * ZP + 4 * hq;
-      const float* q0 = Qs + ((size_t)gg * N + 4 * nq) * KP;
-      const int r1 = (4 * nq + 1 < N) ? 1 : 0, r2 = (4 * nq + 2 < N) ? 2 : 0, r3 = (4 * nq + 3 < N) ? 3 : 0;
-#pragma unroll 2
-      for (int k = 0; k < k_eff; ++k) {
-        const float4 z4 = *reinterpret_cast<const float4*>(z + (size_t)k * ZP);
-        const float av[4] = {q0[k], q0[r1 * KP + k], q0[r2 * KP + k], q0[r3 * KP + k]};
-        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], zv[j], acc[i][j]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (4 * nq + i < N)
-          *reinterpret_cast<float4*>(Xs + ((size_t)gg * N + 4 * nq + i) * XP + 4 * hq) =
-              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    }
-    tcg::producers_sync();
-  }
-
-  // Coalesced write-back of the tile's output rows (one warp per row, 16 bytes per lane).
-  __device__ void post_epilogue(int sub) {
-    if (sub == 0) return;
-    tcg::producers_sync();              // every chunk of every row is in shared memory
-    const int warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = tcg::PRODUCER_THREADS / 32;
-    const int hv = H / 4;
-    for (int row = warp; row < G * N; row += NW) {
-      const int gg = row / N, nn = row - gg * N;
-      if (b0 + gg >= p.B) continue;
-      const float4* src = reinterpret_cast<const float4*>(Xs + (size_t)row * XP);
-      float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)(b0 + gg) * N + nn) * H);
-      for (int q4 = lane; q4 < hv; q4 += 32) dst[q4] = src[q4];
-    }
-  }
-
   __device__ __forceinline__ void produce(int sub, int kb, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
     const int j0 = kb * tcg::BK;
+    const int c = j0 / Din, d0 = j0 - c * Din;
     if (sub == 0) {
-      // row = (graph r/32, Ritz index r%32): f[k,s] * U_g[k, d0:d0+32]
-      const int g0 = r >> 5, k = r & 31;
-      if (g0 >= G || b0 + g0 >= p.B || k >= K) return;
-      const int s = j0 / Din, d0 = j0 % Din;
-      const float f = Fs[((size_t)g0 * K + k) * S + s];
-      const float4* u4 = reinterpret_cast<const float4*>(UZ + ((size_t)g0 * K + k) * UP + d0);
+      // row = (graph, Ritz index): f[k, s] * U[row, d0:d0+32]
+      if (r >= tb->Ztot) return;
+      float f = 0.f;
+      if (S <= FR) {
+#pragma unroll
+        for (int i = 0; i < FR; ++i) f = (i == c) ? fr[i] : f;
+      } else {
+        const int g = tb->z_g[r], k = tb->z_k[r];
+        f = (k < K) ? __ldg(p.coeff + ((int64_t)(tb->gs + g) * K + k) * S + c) : 0.f;
+      }
+      const float4* u4 = reinterpret_cast<const float4*>(UZ + (size_t)r * XP + d0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 t = u4[q];
@@ -355,20 +379,17 @@ struct SpectralPolicy {
       }
       return;
     }
-    // edge type e: sparse row of L_e (ELL) times X_g[:, d0:d0+32]; row = (graph r/NS, node r%NS)
-    const int g = r / NS, n = r % NS;
-    const int b = b0 + g;
-    if (b >= p.B) return;                         // warp-uniform: a warp never straddles graphs
-    const int e = j0 / Din, d0 = j0 % Din;
-    const int tmax = Es[g * (E1 + 2) + e];
-    const float* xs = Xs + (size_t)g * N * XP + d0;
-    const int ts = tmax < TCAP ? tmax : TCAP;
-    const float* ev = Ev + ((size_t)(g * E1 + e) * TCAP) * NS + n;
-    const uint8_t* ei = Ei + ((size_t)(g * E1 + e) * TCAP) * NS + n;
+    // edge type e = c: sparse row of L_e (ELL) times X[:, d0:d0+32]; row = (graph, node)
+    if (r >= tb->Rtot) return;
+    const int e = c;
+    const float* xs = Xs + d0;
+    const int ts = tb->cnt_e[e], tmax = tb->tmax_e[e];
+    const float* ev = Ev + (size_t)tb->base_e[e] * RMAX + r;
+    const uint8_t* ei = Ei + (size_t)tb->base_e[e] * RMAX + r;
 #pragma unroll 2
     for (int t = 0; t < ts; ++t) {
-      const float a = ev[t * NS];
-      const int i = ei[t * NS];
+      const float a = ev[t * RMAX];
+      const int i = ei[t * RMAX];
       const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -379,13 +400,17 @@ struct SpectralPolicy {
         v[4 * q + 3] = fmaf(a, tt.w, v[4 * q + 3]);
       }
     }
-    if (ts < tmax) {                               // rows denser than the staged capacity
-      const int nn = (n < N) ? n : 0;
-      const float* val = p.ell_val + ((int64_t)(b * E1 + e) * N) * N + nn;
-      const uint8_t* idx = p.ell_idx + ((int64_t)(b * E1 + e) * N) * N + nn;
+    if (ts < tmax) {                               // lines that did not fit the staging budget
+      const int g = tb->row_g[r], n = tb->row_n[r];
+      const int my = tb->emax[g][e], nb = tb->nbase[g];
+      const int64_t off0 = (((int64_t)(tb->gs + g) * E1 + e) * N) * N + n;
       for (int t = ts; t < tmax; ++t) {
-        const float a = (n < N) ? __ldg(val + (int64_t)t * N) : 0.f;
-        const int i = __ldg(idx + (int64_t)t * N);
+        float a = 0.f;
+        int i = 0;
+        if (t < my) {
+          a = __ldg(p.ell_val + off0 + (int64_t)t * N);
+          i = nb + __ldg(p.ell_idx + off0 + (int64_t)t * N);
+        }
         const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -399,49 +424,109 @@ struct SpectralPolicy {
     }
   }
 
+  // After the last k-block of the edge step: (V Z)[row, :] for every real row in 4 x 4 register
+  // tiles into the (now dead) X buffer; overlaps with the tensor core draining its queue.
+  __device__ void pre_epilogue(int sub) {
+    if (sub == 0) return;
+    tcg::producers_sync();              // every producer is done reading X
+    if (S == 0) return;
+    const int hv = H / 4;
+    for (int task = tid; task < tb->nquads * hv; task += tcg::PRODUCER_THREADS) {
+      const int hq = task % hv, q = task / hv;
+      const int g = tb->q_g[q], n0 = tb->q_n0[q];
+      const int n_g = tb->gn[g], k_g = tb->gk[g];
+      const int r0 = tb->nbase[g] + n0;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      const float* z = UZ + (size_t)tb->kbase[g] * XP + 4 * hq;
+      const float* q0 = Qs + (size_t)r0 * K;
+      const int r1 = (n0 + 1 < n_g) ? 1 : 0, r2 = (n0 + 2 < n_g) ? 2 : 0, r3 = (n0 + 3 < n_g) ? 3 : 0;
+#pragma unroll 2
+      for (int k = 0; k < k_g; ++k) {
+        const float4 z4 = *reinterpret_cast<const float4*>(z + (size_t)k * XP);
+        const float av[4] = {q0[k], q0[r1 * K + k], q0[r2 * K + k], q0[r3 * K + k]};
+        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], zv[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n0 + i < n_g)
+          *reinterpret_cast<float4*>(Xs + (size_t)(r0 + i) * XP + 4 * hq) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    tcg::producers_sync();
+  }
+
   __device__ __forceinline__ void store(int sub, int col, float (&x)[32]) {
+    if (col >= H) return;
     if (sub == 0) {
-      // drain Z_g[k, col:col+32] to shared memory (overwrites U_g, which is dead by now)
-      const int g0 = r >> 5, k = r & 31;
-      if (g0 < G && k < K && col < H) {
-        float4* z4 = reinterpret_cast<float4*>(UZ + ((size_t)g0 * K + k) * ZP + col);
+      // drain Z[row, col:col+32] to shared memory (overwrites U, which is dead by now)
+      if (r < tb->Ztot) {
+        float4* z4 = reinterpret_cast<float4*>(UZ + (size_t)r * XP + col);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           z4[q] = make_float4(x[4 * q + 0], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
       }
       return;
     }
-    const int g = r / NS, n = r % NS;
-    const int b = b0 + g;
-    if (b >= p.B) return;
-    if (S > 0 && col < H && n < N) {
-      // long-scale part: + (V_g Z_g)[n, col:col+32], precomputed by pre_epilogue()
-      const float4* vz = reinterpret_cast<const float4*>(Xs + ((size_t)g * N + n) * XP + col);
+    if (r >= tb->Rtot) return;
+    float4* o4 = reinterpret_cast<float4*>(Xs + (size_t)r * XP + col);
+    const bool relu = p.relu != 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = vz[q];
-        x[4 * q + 0] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+    for (int q = 0; q < 8; ++q) {
+      float y[4] = {x[4 * q + 0], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]};
+      if (S > 0) {                                  // + (V Z)[row, col + 4q ..], from pre_epilogue()
+        const float4 t = o4[q];
+        y[0] += t.x; y[1] += t.y; y[2] += t.z; y[3] += t.w;
       }
-    }
-    // finished output chunk -> shared memory (in place over V Z / X); rows are written to HBM
-    // by post_epilogue() as full 512-byte lines
-    if (n < N && col < H) {
-      float4* o4 = reinterpret_cast<float4*>(Xs + ((size_t)g * N + n) * XP + col);
-      const bool relu = p.relu != 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float y[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = col + 4 * q + u;
-          float t = x[4 * q + u];
-          if (c < H) {
-            if (p.bias) t += __ldg(p.bias + c);
-            if (relu) t = fmaxf(t, 0.f);
-          }
-          y[u] = t;
+      for (int u = 0; u < 4; ++u) {
+        const int c = col + 4 * q + u;
+        if (c < H) {
+          if (p.bias) y[u] += __ldg(p.bias + c);
+          if (relu) y[u] = fmaxf(y[u], 0.f);
         }
-        o4[q] = make_float4(y[0], y[1], y[2], y[3]);
+      }
+      o4[q] = make_float4(y[0], y[1], y[2], y[3]);   // finished row chunk, written back below
+    }
+  }
+
+  // Coalesced write-back: real rows from shared memory (one warp per 512-byte row), plus the
+  // constant rows act(b) of padded nodes when requested.
+  __device__ void post_epilogue(int sub) {
+    if (sub == 0) return;
+    tcg::producers_sync();              // every chunk of every row is in shared memory
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = tcg::PRODUCER_THREADS / 32;
+    const int hv = H / 4, gs = tb->gs, Rtot = tb->Rtot;
+    for (int row = warp; row < Rtot; row += NW) {
+      const float4* src = reinterpret_cast<const float4*>(Xs + (size_t)row * XP);
+      float4* dst = reinterpret_cast<float4*>(
+          p.out + ((int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row]) * H);
+      for (int q4 = lane; q4 < hv; q4 += 32) dst[q4] = src[q4];
+    }
+    if (p.write_pad) {
+      const int npad = tb->ng * N - Rtot;
+      for (int i = warp; i < npad; i += NW) {
+        // i-th padded (graph, node) pair of the tile, found by walking the per-graph pad counts
+        int g = 0, rem = i;
+        while (rem >= N - tb->gn[g]) { rem -= N - tb->gn[g]; ++g; }
+        float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)(gs + g) * N + tb->gn[g] + rem) * H);
+        for (int q4 = lane; q4 < hv; q4 += 32) {
+          float y[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float t = p.bias ? __ldg(p.bias + 4 * q4 + u) : 0.f;
+            y[u] = (p.relu != 0) ? fmaxf(t, 0.f) : t;
+          }
+          dst[q4] = make_float4(y[0], y[1], y[2], y[3]);
+        }
       }
     }
   }
@@ -459,44 +544,45 @@ int lnb_debug_set_prof(unsigned long long* buf) {
 }
 
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
-                      int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* qext) {
-  LNB_REQUIRE(L && Q && ell_val && ell_idx && ell_max && qext, "graph_prepare: null pointer");
-  LNB_REQUIRE(B >= 0 && N >= 1 && N <= 255 && E1 >= 1 && E1 <= 64 && K >= 1,
+                      int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* gext,
+                      int32_t* tiles) {
+  LNB_REQUIRE(L && Q && ell_val && ell_idx && ell_max && gext && tiles, "graph_prepare: null pointer");
+  LNB_REQUIRE(B >= 0 && N >= 1 && N <= 255 && E1 >= 1 && E1 <= EMAX && K >= 1,
               "graph_prepare: bad dims B=%d N=%d E1=%d K=%d", B, N, E1, K);
   if (B == 0) return LNB_OK;
-  graph_prepare_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(L, Q, N, E1, K, ell_val, ell_idx,
-                                                            ell_max, qext);
-  lnb::count_launch();
+  cudaStream_t s = (cudaStream_t)stream;
+  graph_prepare_kernel<<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
+  tile_assign_kernel<<<1, 256, 0, s>>>(gext, B, tiles);
+  lnb::count_launch(2);
   return lnb::finish_launch("graph_prepare");
 }
 
 int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q, const float* coeff,
                             const float* ell_val, const uint8_t* ell_idx, const int32_t* ell_max,
-                            const int32_t* qext, const float* W_hi, const float* W_lo,
-                            const float* bias, int B, int N, int Din, int E1, int K, int S, int H,
-                            int relu, float* out) {
-  LNB_REQUIRE(X && Q && coeff && ell_val && ell_idx && ell_max && qext && W_hi && W_lo && out,
+                            const int32_t* gext, const int32_t* tiles, const float* W_hi,
+                            const float* W_lo, const float* bias, int B, int N, int Din, int E1,
+                            int K, int S, int H, int relu, int write_pad, float* out) {
+  LNB_REQUIRE(X && Q && ell_val && ell_idx && ell_max && gext && tiles && W_hi && W_lo && out &&
+                  (coeff || S == 0),
               "spectral_conv_fused: null pointer");
   LNB_REQUIRE(B >= 0 && N >= 1 && Din >= 1 && E1 >= 1 && K >= 1 && S >= 0 && H >= 1,
               "spectral_conv_fused: bad dims");
-  if (N > 128 || Din % 32 != 0 || K > KMAX || K % 4 != 0 || H % 4 != 0 || H > tcg::BN) {
-    lnb::set_err("spectral_conv_fused: unsupported shape N=%d Din=%d K=%d H=%d "
-                 "(needs N<=128, Din%%32==0, K%%4==0, K<=%d, H%%4==0, H<=128)", N, Din, K, H, KMAX);
+  if (N > RMAX || Din % 32 != 0 || K > KMAX || K % 4 != 0 || H % 4 != 0 || H > tcg::BN || E1 > EMAX) {
+    lnb::set_err("spectral_conv_fused: unsupported shape N=%d Din=%d K=%d H=%d E1=%d "
+                 "(needs N<=128, Din%%32==0, K%%4==0, K<=%d, H%%4==0, H<=128, E1<=%d)",
+                 N, Din, K, H, E1, KMAX, EMAX);
     return LNB_ERR_UNSUPPORTED;
   }
   if (B == 0) return LNB_OK;
-  const int NS = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-  size_t smem = tcg::CORE_SMEM + 1024 + SpectralPolicy::smem_bytes(N, Din, K, S, E1, H, NS);
-  int tcap = 0;
-  if (smem <= 227 * 1024) {
-    while (tcap < 8 && smem + SpectralPolicy::ell_stage_bytes(E1, NS, tcap + 1) <= 227 * 1024) ++tcap;
-    smem += SpectralPolicy::ell_stage_bytes(E1, NS, tcap);
-  }
+  size_t smem = tcg::core_smem(SpectralPolicy::kStagesB) + 1024 + SpectralPolicy::smem_fixed(Din, K, H);
   if (smem > 227 * 1024) {
-    lnb::set_err("spectral_conv_fused: tile state (N=%d, Din=%d, K=%d) needs %zu B of shared memory",
-                 N, Din, K, smem);
+    lnb::set_err("spectral_conv_fused: tile state (Din=%d, K=%d, H=%d) needs %zu B of shared memory",
+                 Din, K, H, smem);
     return LNB_ERR_UNSUPPORTED;
   }
+  int lb = (int)((227 * 1024 - smem) / SpectralPolicy::ell_line_bytes());
+  if (lb > 255) lb = 255;
+  smem += (size_t)lb * SpectralPolicy::ell_line_bytes();
   const int Kw = (S + E1) * Din;
   CUtensorMap map_hi, map_lo;
   int rc = tcg::make_weight_map(&map_hi, W_hi, H, Kw, "spectral_conv_fused");
@@ -505,11 +591,11 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
   if (rc != LNB_OK) return rc;
   auto kern = tcg::tc_gemm_kernel<SpectralPolicy>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  SpectralPolicy::Params p{X, Q, coeff, ell_val, ell_idx, ell_max, qext, bias, out,
-                           B, N, Din, E1, K, S, H, relu, NS, tcap, tcg::debug_flags()};
-  const int G = tcg::BM / NS;
-  const int tiles = lnb::ceil_div(B, G);
-  const int grid = tiles < tcg::sm_count() ? tiles : tcg::sm_count();
+  SpectralPolicy::Params p{X, Q, coeff, ell_val, ell_idx, ell_max, gext, tiles, bias, out,
+                           B, N, Din, E1, K, S, H, relu, lb, write_pad, tcg::debug_flags()};
+  // the tile count lives in device memory (no host sync): one persistent CTA per SM, bounded by
+  // the worst case of one graph per tile
+  const int grid = B < tcg::sm_count() ? B : tcg::sm_count();
   kern<<<grid, tcg::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
   lnb::count_launch();
   return lnb::finish_launch("spectral_conv_fused");

@@ -23,8 +23,7 @@
 namespace tcg {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int NSTAGES = 3;                         // pipeline stages == producer groups
-constexpr int NGROUPS = NSTAGES;                   // group g owns stage g (k-block kb -> kb % 3)
+constexpr int NGROUPS = 3;                         // producer groups == TMEM A stages (kb % 3)
 constexpr int TILE_B_BYTES = BN * BK * 4;          // 16 KB per hi or lo tile
 constexpr int STAGE_B_BYTES = 2 * TILE_B_BYTES;    // [W_hi tile | W_lo tile] = 256 rows x 128 B
 constexpr int TMEM_COLS = 512;
@@ -32,24 +31,30 @@ constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;   // A stage s: COL_A +
 constexpr int PRODUCER_THREADS = 128 * NGROUPS;
 constexpr int TMA_WARP = 4 * NGROUPS, MMA_WARP = 4 * NGROUPS + 1;
 constexpr int THREADS = PRODUCER_THREADS + 64;
-constexpr int CORE_SMEM = NSTAGES * STAGE_B_BYTES + 256;   // W ring + barriers/holder
+constexpr int MAX_B_STAGES = 3;
+// shared memory of the skeleton: W ring (Policy::kStagesB stages) + barriers / TMEM holder
+__host__ __device__ constexpr int core_smem(int stages_b) { return stages_b * STAGE_B_BYTES + 256; }
 
 struct Core {
-  uint8_t* Bst;        // [NSTAGES][hi 16 KB | lo 16 KB]
-  uint64_t* full;      // [NSTAGES]  4 producer-warp arrivals + 1 TMA arrive.expect_tx
-  uint64_t* empty;     // [NSTAGES]  1 tcgen05.commit
+  uint8_t* Bst;        // [kStagesB][hi 16 KB | lo 16 KB]
+  uint64_t* b_full;    // [kStagesB]  TMA arrive.expect_tx
+  uint64_t* b_empty;   // [kStagesB]  tcgen05.commit
+  uint64_t* a_full;    // [NGROUPS]   4 producer-warp arrivals
+  uint64_t* a_empty;   // [NGROUPS]   tcgen05.commit
   uint64_t* acc_full;  // [1]
   uint64_t* acc_empty; // [1]
   uint32_t* tmem_holder;
 };
 
-__device__ __forceinline__ Core carve(uint8_t* base) {
+__device__ __forceinline__ Core carve(uint8_t* base, int stages_b) {
   Core c;
   c.Bst = base;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + NSTAGES * STAGE_B_BYTES);
-  c.full = bars;
-  c.empty = c.full + NSTAGES;
-  c.acc_full = c.empty + NSTAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + stages_b * STAGE_B_BYTES);
+  c.b_full = bars;
+  c.b_empty = c.b_full + MAX_B_STAGES;
+  c.a_full = c.b_empty + MAX_B_STAGES;
+  c.a_empty = c.a_full + NGROUPS;
+  c.acc_full = c.a_empty + NGROUPS;
   c.acc_empty = c.acc_full + 1;
   c.tmem_holder = reinterpret_cast<uint32_t*>(c.acc_empty + 1);
   return c;
@@ -79,6 +84,7 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
 
 // Policy contract (all __device__).  A "step" is one accumulator lifetime: its k-blocks are
 // produced / multiplied, then the epilogue hands the 128 x 128 result to the policy.
+//   static constexpr int kStagesB                        depth of the W (shared memory) ring: 2 or 3
 //   struct Params;                                       kernel parameter block (by value)
 //   static int  num_steps(const Params&, int cta, int ncta)       steps this CTA runs
 //   static void decode(const Params&, int cta, int ncta, int it, int& m_tile, int& sub)
@@ -101,8 +107,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   // shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
   const uint32_t pad = (1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* base = smem_raw + pad;
-  Core c = carve(base);
-  uint8_t* policy_smem = base + CORE_SMEM;
+  constexpr int SB = Policy::kStagesB;
+  Core c = carve(base, SB);
+  uint8_t* policy_smem = base + core_smem(SB);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
@@ -114,7 +121,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   }
   if (warp == MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < NSTAGES; ++s) { tc05::mbar_init(&c.full[s], 5); tc05::mbar_init(&c.empty[s], 1); }
+      for (int s = 0; s < SB; ++s) { tc05::mbar_init(&c.b_full[s], 1); tc05::mbar_init(&c.b_empty[s], 1); }
+      for (int s = 0; s < NGROUPS; ++s) { tc05::mbar_init(&c.a_full[s], 4); tc05::mbar_init(&c.a_empty[s], 1); }
       tc05::mbar_init(c.acc_full, 1);
       tc05::mbar_init(c.acc_empty, 4 * NGROUPS);       // one arrival per producer warp
       tc05::fence_barrier_init();
@@ -149,7 +157,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       for (int kb = kb_first; kb < nkb; kb += NGROUPS, ++use) {
         float v[32];
         if (!(p.dbg & 8)) pol.produce(sub, kb, v);
-        tc05::mbar_wait(&c.empty[grp], (use & 1u) ^ 1u);
+        tc05::mbar_wait(&c.a_empty[grp], (use & 1u) ^ 1u);
         tc05::fence_after_thread_sync();
         if (!(p.dbg & 1)) {
           uint32_t part[32];
@@ -163,7 +171,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         }
         tc05::fence_before_thread_sync();
         __syncwarp();
-        if (lane == 0) tc05::mbar_arrive(&c.full[grp]);
+        if (lane == 0) tc05::mbar_arrive(&c.a_full[grp]);
       }
       tm.lap(3);
       pol.pre_epilogue(sub);
@@ -202,16 +210,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         int col0, row0;
         Policy::w_coords(p, sub, kb, col0, row0);
-        const uint32_t st = cnt % NSTAGES;
-        tc05::mbar_wait(&c.empty[st], ((cnt / NSTAGES) & 1u) ^ 1u);
+        const uint32_t st = cnt % SB;
+        tc05::mbar_wait(&c.b_empty[st], ((cnt / SB) & 1u) ^ 1u);
         if (tc05::elect_one()) {
           if (p.dbg & 4) {
-            tc05::mbar_arrive(&c.full[st]);
+            tc05::mbar_arrive(&c.b_full[st]);
           } else {
             uint8_t* dst = c.Bst + st * STAGE_B_BYTES;
-            tc05::mbar_arrive_expect_tx(&c.full[st], STAGE_B_BYTES);
-            tc05::tma_load_2d(dst, &map_hi, &c.full[st], col0, row0);
-            tc05::tma_load_2d(dst + TILE_B_BYTES, &map_lo, &c.full[st], col0, row0);
+            tc05::mbar_arrive_expect_tx(&c.b_full[st], STAGE_B_BYTES);
+            tc05::tma_load_2d(dst, &map_hi, &c.b_full[st], col0, row0);
+            tc05::tma_load_2d(dst + TILE_B_BYTES, &map_lo, &c.b_full[st], col0, row0);
           }
         }
         __syncwarp();
@@ -232,12 +240,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       tc05::mbar_wait(c.acc_empty, ((uint32_t)it & 1u) ^ 1u);   // previous epilogue done
       tc05::fence_after_thread_sync();
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-        const uint32_t st = cnt % NSTAGES;
-        tc05::mbar_wait(&c.full[st], (cnt / NSTAGES) & 1u);
+        const uint32_t sb = cnt % SB, sa = cnt % NGROUPS;
+        tc05::mbar_wait(&c.b_full[sb], (cnt / SB) & 1u);
+        tc05::mbar_wait(&c.a_full[sa], (cnt / NGROUPS) & 1u);
         tc05::fence_after_thread_sync();
         if (tc05::elect_one()) {
-          const uint32_t a_hi = tmem_base + COL_A + st * 64, a_lo = a_hi + 32;
-          const uint64_t dB = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Bst + st * STAGE_B_BYTES));
+          const uint32_t a_hi = tmem_base + COL_A + sa * 64, a_lo = a_hi + 32;
+          const uint64_t dB = tc05::umma_desc_kmajor_sw128(tc05::smem_u32(c.Bst + sb * STAGE_B_BYTES));
           if (!(p.dbg & 2)) {
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
@@ -246,7 +255,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
               tc05::umma_tf32_ts(d_corr, a_lo + 8 * k, dB + 2 * k, idesc128, 1u);
             }
           }
-          tc05::umma_commit(&c.empty[st]);
+          tc05::umma_commit(&c.a_empty[sa]);
+          tc05::umma_commit(&c.b_empty[sb]);
           if (kb == nkb - 1) tc05::umma_commit(c.acc_full);
         }
         __syncwarp();

@@ -53,5 +53,5 @@ class LanczosNet(SpectralNetBase):
         coeff = coeffs[tt] if coeffs is not None else table
       state = graph_conv_layer(state, ctx, coeff, False, self.short_diffusion_dist,
                                self.num_scale_long, self.filter[tt].weight, self.filter[tt].bias,
-                               self._wcache, 'filter.%d' % tt)
+                               self._wcache, 'filter.%d' % tt, last=(tt == self.num_layer - 1))
     return self._readout(state, mask)

@@ -121,8 +121,9 @@ def linear_tf32x3_grouped(x, w_hi, w_lo, bias, groups, relu=False):
 
 
 def graph_prepare(L, Q):
-  """Per-forward ELL compression of the dense operators L [B,N,N,E1] and the extents of Q
-  [B,N,K] for the fused convolution kernel.  Returns (ell_val, ell_idx, ell_max, qext)."""
+  """Per-forward compression of the dense operators L [B,N,N,E1] (ELL rows), the real extents
+  of every graph and the packed-tile assignment for the fused convolution kernel.
+  Returns (ell_val, ell_idx, ell_max, gext, tiles)."""
   _need_cuda(L, Q)
   L, Q = _f32c(L), _f32c(Q)
   B, N, _, E1 = L.shape
@@ -131,34 +132,39 @@ def graph_prepare(L, Q):
   ell_val = torch.empty((B, E1, N, N), device=dev, dtype=torch.float32)
   ell_idx = torch.empty((B, E1, N, N), device=dev, dtype=torch.uint8)
   ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
-  qext = torch.empty((B, 2), device=dev, dtype=torch.int32)
+  gext = torch.empty((B, 2), device=dev, dtype=torch.int32)
+  tiles = torch.empty((B + 2,), device=dev, dtype=torch.int32)
   with torch.cuda.device(dev):
     _lib.check(_lib.load().lnb_graph_prepare(_stream(L), _ptr(L), _ptr(Q), B, N, E1, K,
                                              _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),
-                                             _ptr(qext)), 'lnb_graph_prepare')
-  return ell_val, ell_idx, ell_max, qext
+                                             _ptr(gext), _ptr(tiles)), 'lnb_graph_prepare')
+  return ell_val, ell_idx, ell_max, gext, tiles
 
 
 def fused_conv_supported(N, Din, K, H, n_short, dense_filter, S=8, E1=7):
   """Shapes the fused tcgen05 convolution kernel handles (others use the unfused ops);
   mirrors the checks of lnb_spectral_conv_fused."""
-  if n_short or dense_filter or N > 128 or Din % 32 or K > 32 or K % 4 or H % 4 or H > 128:
+  if (n_short or dense_filter or N > 128 or Din % 32 or K > 32 or K % 4 or H % 4 or H > 128 or
+      E1 > 16):
     return False
-  G = 128 // (32 if N <= 32 else (64 if N <= 64 else 128))
-  smem = (98560 + 1024 + 4 * ((G * N + G * K) * (max(Din, H) + 4) + G * N * K + G * K * S) +
-          4 * G * (E1 + 2) + 16)
+  smem = 2 * 32768 + 256 + 1024 + 2 * 128 * (max(Din, H) + 4) * 4 + 128 * K * 4 + 4096
   return smem <= 227 * 1024
 
 
-def spectral_conv_fused(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True):
+def spectral_conv_fused(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True, write_pad=True):
   """One fused spectral convolution layer: X [B,N,Din], Q [B,N,K], coeff [B,K,S] diagonal
-  filter coefficients, prep = graph_prepare(L, Q), W [H, (S+E1)*Din] split -> [B,N,H]."""
+  filter coefficients (None when there are no long scales), prep = graph_prepare(L, Q),
+  W [H, (S+E1)*Din] split -> [B,N,H].  write_pad=False leaves the rows of padded nodes
+  unwritten (fine between layers: nothing reads them)."""
   _need_cuda(X, Q, coeff, w_hi, w_lo, bias)
-  X, Q, coeff = _f32c(X), _f32c(Q), _f32c(coeff)
-  ell_val, ell_idx, ell_max, qext = prep
+  X, Q = _f32c(X), _f32c(Q)
+  ell_val, ell_idx, ell_max, gext, tiles = prep
   B, N, Din = X.shape
   K = Q.shape[2]
-  S = coeff.shape[2]
+  S = 0
+  if coeff is not None:
+    coeff = _f32c(coeff)
+    S = coeff.shape[2]
   E1 = ell_val.shape[1]
   H = w_hi.shape[0]
   assert w_hi.shape[1] == (S + E1) * Din, (w_hi.shape, S, E1, Din)
@@ -166,8 +172,8 @@ def spectral_conv_fused(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True):
   with torch.cuda.device(X.device):
     _lib.check(_lib.load().lnb_spectral_conv_fused(
         _stream(X), _ptr(X), _ptr(Q), _ptr(coeff), _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),
-        _ptr(qext), _ptr(w_hi), _ptr(w_lo), _ptr(bias), B, N, Din, E1, K, S, H, int(bool(relu)),
-        _ptr(out)), 'lnb_spectral_conv_fused')
+        _ptr(gext), _ptr(tiles), _ptr(w_hi), _ptr(w_lo), _ptr(bias), B, N, Din, E1, K, S, H,
+        int(bool(relu)), int(bool(write_pad)), _ptr(out)), 'lnb_spectral_conv_fused')
   return out
 
 

@@ -124,7 +124,7 @@ class GraphContext(object):
 
 
 def graph_conv_layer(state, ctx, coeff, dense_filter, short_dist, num_long, weight, bias, cache,
-                     name):
+                     name, last=True):
   """One spectral convolution layer: the fused tcgen05 kernel when the shape allows it
   (LanczosNet-style diagonal filters), otherwise the unfused ops below."""
   L, Qv = ctx.L, ctx.Qv
@@ -133,7 +133,8 @@ def graph_conv_layer(state, ctx, coeff, dense_filter, short_dist, num_long, weig
       ops.fused_conv_supported(N, Din, Qv.shape[2], weight.shape[0], len(short_dist), dense_filter,
                                num_long, L.shape[3])):
     w_hi, w_lo = cache.split(name, weight)
-    return ops.spectral_conv_fused(state, Qv, coeff, ctx.prep(), w_hi, w_lo, bias, True)
+    return ops.spectral_conv_fused(state, Qv, coeff, ctx.prep(), w_hi, w_lo, bias, True,
+                                   write_pad=last)
   return graph_conv_layer_unfused(state, L, Qv, coeff, dense_filter, short_dist, num_long, weight,
                                   bias, cache, name)
 

@@ -323,14 +323,20 @@ def test_spectral_conv_fused_matches_fp64_and_unfused(B, N, Din, H, molecular):
   assert ops().fused_conv_supported(N, Din, K, H, 0, False, S, E1)
   prep = ops().graph_prepare(Lg, Vg)
   # the compression is exact: rebuilding dense rows from the ELL lists returns L bit-for-bit
-  ell_val, ell_idx, ell_max, qext = [t.cpu() for t in prep]
+  ell_val, ell_idx, ell_max, gext, tiles = [t.cpu() for t in prep]
   for b in range(min(B, 3)):
     for e in range(E1):
       dense = torch.zeros(N, N)
       for t in range(int(ell_max[b, e])):
         dense[torch.arange(N), ell_idx[b, e, t].long()] += ell_val[b, e, t]
       assert torch.equal(dense, L[b, :, :, e])
-    assert int(qext[b, 0]) == int((V[b].abs().sum(1) > 0).sum()) or True
+  # packed tiles: consecutive graph ranges covering [0, B) within the row / Ritz-row budgets
+  T = int(tiles[0])
+  starts = tiles[1:T + 2].tolist()
+  assert starts[0] == 0 and starts[-1] == B and all(a < b for a, b in zip(starts, starts[1:]))
+  for a, b in zip(starts, starts[1:]):
+    assert b - a <= 32 and int(gext[a:b, 0].sum()) <= 128
+    assert int(((gext[a:b, 1] + 3) // 4 * 4).sum()) <= 128
   w_hi, w_lo = ops().split_tf32(Wg)
   out = ops().spectral_conv_fused(Xg, Vg, cg, prep, w_hi, w_lo, bg, True)
   cache = sc.WeightCache()

@@ -39,7 +39,7 @@ X = torch.randn(1024, 26, 128, device=dev)
 coeff = torch.randn(1024, 20, 8, device=dev)
 prep = ops.graph_prepare(L, V)
 
-for flags in [0, 16, 32, 64, 128, 240, 15, 255]:
+for flags in [0, 8, 1, 2, 4, 15]:
   os.environ['LNB_DBG'] = str(flags)
   t_lin = timeit(lambda: ops.linear_tf32x3(x, w_hi, w_lo, bias, True))
   t_fus = timeit(lambda: ops.spectral_conv_fused(X, V, coeff, prep, w_hi, w_lo, bias, True))
