@@ -80,6 +80,22 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
   if (ne) atomicMax(&s_ext[0], ne);
   if (ke) atomicMax(&s_ext[1], ke);
   __syncthreads();
+  // zero-fill the tail of every row up to the channel maximum of this graph, so consumers can
+  // run all rows of a (graph, channel) to the same length without per-row guards
+  for (int p0 = 0; p0 < pairs; p0 += 256) {
+    const int p = p0 + tid;
+    if (p < pairs) {
+      const int n = p / E1, e = p % E1;
+      int cnt = 0;
+      for (int i = 0; i < N; ++i) cnt += (Lb[((int64_t)n * N + i) * E1 + e] != 0.f) ? 1 : 0;
+      float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
+      uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
+      for (int t = cnt; t < s_max[e]; ++t) {
+        val[(int64_t)t * N] = 0.f;
+        idx[(int64_t)t * N] = 0;
+      }
+    }
+  }
   if (tid < E1) ell_max[b * E1 + tid] = s_max[tid];
   if (tid < 2) gext[b * 2 + tid] = s_ext[tid];
 }
