@@ -124,7 +124,11 @@ class SpectralNetBase(nn.Module):
     return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
   def _graph_forward(self, impl, inputs):
-    """impl(*device_tensors) -> score; inputs: tuple of tensors / None (CPU or CUDA)."""
+    """impl(*device_tensors) -> score; inputs: tuple of tensors / None (CPU or CUDA).
+
+    Two graph slots with their own static buffers alternate, and the input copies run on a
+    dedicated copy stream: the H2D (or D2D) transfer of call i+1 overlaps the replay of call i
+    (the forward returns without synchronising), ordered by events only."""
     dev = self._device()
     eligible = (self.use_cuda_graph and not self.training and not torch.is_grad_enabled() and
                 not getattr(self, '_is_replica', False) and
@@ -135,34 +139,50 @@ class SpectralNetBase(nn.Module):
     cache = self.__dict__.setdefault('_graphs', {})
     entry = cache.get(key)
     sig = self._param_signature()
+    cur = torch.cuda.current_stream(dev)
     if entry is None or entry['sig'] != sig:
-      static_in = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev)
-                   for t in inputs]
-      for s_, t in zip(static_in, inputs):
-        if s_ is not None:
-          s_.copy_(t, non_blocking=True)
-      side = torch.cuda.Stream(device=dev)
-      side.wait_stream(torch.cuda.current_stream(dev))
-      with torch.cuda.stream(side):
-        impl(*static_in)                       # warm-up: fills the weight caches, autotunes nothing
-      torch.cuda.current_stream(dev).wait_stream(side)
-      torch.cuda.synchronize(dev)
-      graph = torch.cuda.CUDAGraph()
-      n0 = int(_lib.load().lnb_launch_count())
-      with torch.cuda.graph(graph):
-        static_out = impl(*static_in)
-      entry = {'sig': sig, 'graph': graph, 'in': static_in, 'out': static_out,
-               'kernels': int(_lib.load().lnb_launch_count()) - n0}
+      slots = []
+      for _ in range(2):
+        static_in = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev)
+                     for t in inputs]
+        for s_, t in zip(static_in, inputs):
+          if s_ is not None:
+            s_.copy_(t, non_blocking=True)
+        if not slots:
+          side = torch.cuda.Stream(device=dev)
+          side.wait_stream(cur)
+          with torch.cuda.stream(side):
+            impl(*static_in)                   # warm-up: fills the weight caches
+          cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        n0 = int(_lib.load().lnb_launch_count())
+        with torch.cuda.graph(graph):
+          static_out = impl(*static_in)
+        slots.append({'graph': graph, 'in': static_in, 'out': static_out,
+                      'kernels': int(_lib.load().lnb_launch_count()) - n0,
+                      'free': torch.cuda.Event(), 'ready': torch.cuda.Event()})
+        slots[-1]['free'].record(cur)
+      entry = {'sig': sig, 'slots': slots, 'next': 0, 'copy': torch.cuda.Stream(device=dev)}
       if len(cache) >= 8:                      # bound the number of live graphs
         cache.pop(next(iter(cache)))
       cache[key] = entry
-    else:
-      for s_, t in zip(entry['in'], inputs):
+    slot = entry['slots'][entry['next']]
+    entry['next'] ^= 1
+    copy = entry['copy']
+    copy.wait_event(slot['free'])              # the previous replay of this slot has consumed its inputs
+    if any(t is not None and t.is_cuda for t in inputs):
+      copy.wait_stream(cur)                    # device inputs produced on the caller's stream
+    with torch.cuda.stream(copy):
+      for s_, t in zip(slot['in'], inputs):
         if s_ is not None:
           s_.copy_(t, non_blocking=True)
-    entry['graph'].replay()
-    _lib.note_graph_replay(entry['kernels'])
-    return entry['out'].clone()
+      slot['ready'].record(copy)
+    cur.wait_event(slot['ready'])
+    slot['graph'].replay()
+    slot['free'].record(cur)
+    _lib.note_graph_replay(slot['kernels'])
+    return slot['out'].clone()
 
   def _filter_mlp_params(self):
     if not hasattr(self, 'spectral_filter'):
