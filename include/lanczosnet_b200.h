@@ -131,6 +131,24 @@ int lnb_ritz_power_table(lnb_stream_t stream, const float* D, int64_t rows, cons
                          int S, float* table /* [rows, S] */);
 
 /* ---------------------------------------------------------------------------------------
+ * Ritz-value filter MLPs of all layers in one persistent tcgen05 kernel
+ * (model/lanczos_net.py:47-58,109-113): coeff[l, r, :] = MLP_l(table[r, :]) for the rows r listed
+ * in rowmap (nrows[0] entries; both NULL = all Rall rows).  The four Linear stages of a
+ * (row tile, layer) item run back to back with the 128 x hidden activations kept in shared
+ * memory.  W_hi/W_lo: tf32 split of the stacked weights [L*(3*hidden+S), hidden]: per layer the
+ * rows of stage 0 (input columns zero-padded from S to hidden), stage 1, stage 2, stage 3
+ * (S rows); bias_all uses the same row indexing.  lnb_ritz_rowmap builds the compact row list
+ * {b*K + k : k < k_eff(b)} from the extents of lnb_graph_prepare (rows of zero-padded Ritz pairs
+ * multiply zero Ritz vectors downstream and are skipped; their coeff entries stay unwritten).
+ * Requirements: S <= 32, hidden % 32 == 0, hidden <= 128 (else LNB_ERR_UNSUPPORTED).
+ * ------------------------------------------------------------------------------------- */
+int lnb_ritz_rowmap(lnb_stream_t stream, const int32_t* gext, int B, int K, int32_t* rowmap,
+                    int32_t* nrows);
+int lnb_ritz_filter_mlp(lnb_stream_t stream, const float* table, const int32_t* rowmap,
+                        const int32_t* nrows, const float* W_hi, const float* W_lo,
+                        const float* bias_all, int Rall, int L, int S, int Hd, float* coeff);
+
+/* ---------------------------------------------------------------------------------------
  * Readout (model/lanczos_net.py:185-194, ada_lanczos_net.py:350-361):
  *   y[b,n,:] = (W_out state[b,n,:] + b_out) * sigmoid(w_att . state[b,n,:] + b_att)
  *   score[b,:] = mean over n with mask[b,n] != 0 (mask == NULL -> all n)

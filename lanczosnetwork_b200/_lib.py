@@ -50,6 +50,9 @@ SIGNATURES = {
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
                  ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int,
                  c_int, c_int, c_int, c_int, c_int, c_int, c_f32p]),
+    'lnb_ritz_rowmap': (c_int, [c_stream, ctypes.c_void_p, c_int, c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    'lnb_ritz_filter_mlp': (c_int, [c_stream, c_f32p, ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p,
+                                    c_f32p, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_debug_set_prof': (c_int, [ctypes.c_void_p]),
     'lnb_embedding_rows': (c_int, [c_stream, ctypes.c_void_p, c_f32p, c_i64, c_int, c_int, c_f32p]),
     'lnb_ritz_power_table': (c_int, [c_stream, c_f32p, c_i64, ctypes.POINTER(c_int), c_int, c_f32p]),

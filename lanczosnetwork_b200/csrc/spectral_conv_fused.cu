@@ -327,7 +327,7 @@ struct SpectralPolicy {
     for (int i = 0; i < FR; ++i) fr[i] = 0.f;
     if (S > 0 && r < Ztot) {
       const int g = tb->z_g[r], k = tb->z_k[r];
-      if (k < K) {
+      if (k < tb->gk[g]) {                       // rows beyond k_eff multiply zero rows of U
         const float* f = p.coeff + ((int64_t)(gs + g) * K + k) * S;
 #pragma unroll
         for (int i = 0; i < FR; ++i)
@@ -385,7 +385,7 @@ struct SpectralPolicy {
         for (int i = 0; i < FR; ++i) f = (i == c) ? fr[i] : f;
       } else {
         const int g = tb->z_g[r], k = tb->z_k[r];
-        f = (k < K) ? __ldg(p.coeff + ((int64_t)(tb->gs + g) * K + k) * S + c) : 0.f;
+        f = (k < tb->gk[g]) ? __ldg(p.coeff + ((int64_t)(tb->gs + g) * K + k) * S + c) : 0.f;
       }
       const float4* u4 = reinterpret_cast<const float4*>(UZ + (size_t)r * XP + d0);
 #pragma unroll

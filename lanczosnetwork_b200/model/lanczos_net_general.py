@@ -3,6 +3,7 @@ LanczosNet with float node features instead of an atom embedding (:156) and the 
 count taken from ``config.dataset.num_edge_type`` (:24)."""
 import torch
 
+from .. import ops
 from ..spectral_conv import GraphContext, graph_conv_layer, ritz_filter_coefficients
 from ._common import SpectralNetBase
 
@@ -44,7 +45,13 @@ class LanczosNetGeneral(SpectralNetBase):
     coeffs = table = None
     if self.num_scale_long > 0:
       mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
-      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache)
+      dims = [state.shape[2]] + list(self.hidden_dim)
+      all_fused = all(ops.fused_conv_supported(L.shape[1], dims[t], V.shape[2], dims[t + 1], 0,
+                                               False, self.num_scale_long, L.shape[3])
+                      for t in range(self.num_layer)) and not self.short_diffusion_dist
+      gext = ctx.prep()[3] if (mlp is not None and all_fused) else None
+      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache,
+                                               gext)
 
     for tt in range(self.num_layer):
       coeff = None

@@ -13,7 +13,7 @@ from ._lib import GemmDesc
 
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
-    'fused_conv_supported', 'embedding_rows', 'ritz_power_table', 'readout',
+    'fused_conv_supported', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
     'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
@@ -175,6 +175,35 @@ def spectral_conv_fused(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True, write_pa
         _ptr(gext), _ptr(tiles), _ptr(w_hi), _ptr(w_lo), _ptr(bias), B, N, Din, E1, K, S, H,
         int(bool(relu)), int(bool(write_pad)), _ptr(out)), 'lnb_spectral_conv_fused')
   return out
+
+
+def ritz_rowmap(gext, K):
+  """Compact list of the (graph, k) rows with k < k_eff(graph): (rowmap [B*K] int32, nrows [1])."""
+  _need_cuda(gext)
+  B = gext.shape[0]
+  rowmap = torch.empty((B * K,), device=gext.device, dtype=torch.int32)
+  nrows = torch.empty((1,), device=gext.device, dtype=torch.int32)
+  with torch.cuda.device(gext.device):
+    _lib.check(_lib.load().lnb_ritz_rowmap(_stream(gext), _ptr(gext), B, int(K), _ptr(rowmap),
+                                           _ptr(nrows)), 'lnb_ritz_rowmap')
+  return rowmap, nrows
+
+
+def ritz_filter_mlp(table, w_hi, w_lo, bias_all, num_layers, rowmap=None, nrows=None):
+  """coeff[l, r, :] = MLP_l(table[r, :]) for all layers in one persistent kernel.
+  table [R, S]; w_hi/w_lo [L*(3*Hd+S), Hd] stacked split weights; returns coeff [L, R, S]
+  (rows not listed in rowmap are left unwritten)."""
+  _need_cuda(table, w_hi, w_lo, bias_all, rowmap, nrows)
+  table = _f32c(table)
+  R, S = table.shape
+  Hd = w_hi.shape[1]
+  coeff = torch.empty((num_layers, R, S), device=table.device, dtype=torch.float32)
+  with torch.cuda.device(table.device):
+    _lib.check(_lib.load().lnb_ritz_filter_mlp(_stream(table), _ptr(table), _ptr(rowmap),
+                                               _ptr(nrows), _ptr(w_hi), _ptr(w_lo),
+                                               _ptr(bias_all), R, int(num_layers), S, Hd,
+                                               _ptr(coeff)), 'lnb_ritz_filter_mlp')
+  return coeff
 
 
 def embedding_rows(idx, table):

@@ -52,6 +52,28 @@ class WeightCache(object):
       self._store[key] = hit
     return hit[1], hit[2], hit[3]
 
+  def split_mlp_chain(self, name, mlp_layers):
+    """Stacked weights of the chain-fused filter MLP kernel: per layer the rows of stage 0
+    (input columns zero-padded to the hidden width), stage 1, stage 2 and stage 3; returns
+    (w_hi, w_lo, bias_all)."""
+    ws = [w for layer in mlp_layers for (_, w, _) in layer]
+    bs = [b for layer in mlp_layers for (_, _, b) in layer]
+    dev = ws[0].device
+    key = (name, dev.index)
+    tag = tuple((t.data_ptr(), t._version) for t in ws + bs)
+    hit = self._store.get(key)
+    if hit is None or hit[0] != tag:
+      hd = ws[1].shape[0]
+      rows = []
+      for layer in mlp_layers:
+        w0 = layer[0][1].detach()
+        rows.append(torch.nn.functional.pad(w0, (0, hd - w0.shape[1])))
+        rows += [layer[1][1].detach(), layer[2][1].detach(), layer[3][1].detach()]
+      hi, lo = ops.split_tf32(torch.cat(rows, dim=0).contiguous())
+      hit = (tag, hi, lo, torch.cat([b.detach() for b in bs], dim=0).contiguous())
+      self._store[key] = hit
+    return hit[1], hit[2], hit[3]
+
   def clear(self):
     self._store.clear()
 
@@ -73,7 +95,7 @@ def dense(x2d, weight, bias, relu, cache, name):
   return out
 
 
-def ritz_filter_coefficients(D, powers, mlp_layers, cache):
+def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
   """Per-layer multi-scale coefficients of the Ritz values (model/lanczos_net.py:109-113,
   146-149).  The MLP input does not depend on the layer state, so the power table is built once
   and every MLP stage runs for ALL layers in one launch: stage 0 as a dense layer with the
@@ -87,7 +109,17 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache):
     return None, table
   nl = len(mlp_layers)
   flat = table.reshape(B * K, S)
-  if S % 4 == 0 and mlp_layers[0][0][1].shape[0] % 4 == 0:
+  hd = mlp_layers[0][0][1].shape[0]
+  if S <= 32 and hd % 32 == 0 and hd <= 128:
+    # all layers, all four stages in ONE persistent kernel, activations on chip; with the
+    # extents of graph_prepare only the rows of non-zero Ritz vectors are evaluated
+    w_hi, w_lo, bias_all = cache.split_mlp_chain('spectral_filter.chain', mlp_layers)
+    rowmap = nrows = None
+    if gext is not None:
+      rowmap, nrows = ops.ritz_rowmap(gext, K)
+    coeff = ops.ritz_filter_mlp(flat, w_hi, w_lo, bias_all, nl, rowmap, nrows).reshape(nl, B, K, S)
+    return [coeff[l] for l in range(nl)], table
+  if S % 4 == 0 and hd % 4 == 0:
     h = flat
     for stage in range(4):
       ws = [mlp_layers[l][stage][1] for l in range(nl)]

@@ -369,3 +369,49 @@ def test_linear_grouped_block_diagonal():
                     + b2[i * N2:(i + 1) * N2].double() for i in range(G)], dim=1)
   assert out2.shape == (M, G * N2)
   assert (out2.double() - ref2).abs().max().item() <= 6e-6 * ref2.abs().max().item()
+
+
+def test_filter_mlp_chain_matches_fp64():
+  """All layers' Ritz-filter MLPs in one kernel vs an fp64 evaluation, with and without the
+  compact row list."""
+  from lanczosnetwork_b200 import spectral_conv as sc
+  g = torch.Generator().manual_seed(11)
+  B, K, S, Hd, L = 37, 20, 8, 128, 3
+  D = (torch.rand(B, K, generator=g) * 2 - 1)
+  keff = torch.randint(0, K + 1, (B,), generator=g)
+  for b in range(B):
+    D[b, keff[b]:] = 0
+  layers, ref_w = [], []
+  for l in range(L):
+    dims = [(Hd, S), (Hd, Hd), (Hd, Hd), (S, Hd)]
+    ps = []
+    for i, (o, k) in enumerate(dims):
+      w = (torch.randn(o, k, generator=g) / np.sqrt(k)).to(dev())
+      b_ = (torch.randn(o, generator=g) * 0.1).to(dev())
+      ps.append(('l%d.%d' % (l, i), w, b_))
+    layers.append(ps)
+  powers = [1, 2, 3, 5, 7, 10, 20, 30]
+  table = ops().ritz_power_table(D.to(dev()), powers)
+  ref = []
+  for ps in layers:
+    h = table.reshape(B * K, S).double()
+    for i, (_, w, b_) in enumerate(ps):
+      h = h @ w.double().t() + b_.double()
+      if i < 3:
+        h = torch.relu(h)
+    ref.append(h.reshape(B, K, S))
+  cache = sc.WeightCache()
+  out, _ = sc.ritz_filter_coefficients(D.to(dev()), powers, layers, cache)
+  for l in range(L):
+    err = (out[l].double() - ref[l]).abs().max().item()
+    assert err <= 5e-6 * ref[l].abs().max().item() + 1e-6, (l, err)
+  gext = torch.stack([torch.full((B,), 5), keff], dim=1).int().to(dev())
+  rowmap, nrows = ops().ritz_rowmap(gext, K)
+  assert int(nrows) == int(keff.sum())
+  want = torch.cat([torch.arange(int(keff[b])) + b * K for b in range(B)]).int()
+  assert torch.equal(rowmap[:int(nrows)].cpu(), want)
+  out2, _ = sc.ritz_filter_coefficients(D.to(dev()), powers, layers, cache, gext)
+  for l in range(L):
+    for b in range(B):
+      kk = int(keff[b])
+      assert torch.equal(out2[l][b, :kk], out[l][b, :kk])
