@@ -97,8 +97,9 @@ int lnb_linear_tf32x3_grouped(lnb_stream_t stream, const float* A, const float* 
  * invariant):
  *   ell_val/ell_idx [B,E1,N,N]  t-major ELL rows of every operator channel, ell_max [B,E1];
  *   gext [B,2] = {n_eff, k_eff}: operators / Q are identically zero beyond these extents;
- *   tiles [B+2]: tiles[0] = T, tiles[1+t] = first graph of packed tile t (next-fit:
- *                sum n_eff <= 128, sum ceil4(k_eff) <= 128, <= 32 graphs), tiles[1+T] = B.
+ *   tiles [4B+2]: tiles[0] = T, tiles[1+t] = first graph of packed tile t (next-fit:
+ *                sum n_eff <= 128, sum ceil4(k_eff) <= 128, <= 32 graphs), tiles[1+T] = B;
+ *                entries [B+2, 4B+2) are scratch of the assignment kernel.
  * Skipping exact zeros / padded rows is exact.  write_pad != 0 also writes the constant rows
  * act(bias) of padded nodes (needed when the full [B,N,H] tensor is read afterwards).
  * Requirements of the fused kernel: N <= 128, Din % 32 == 0, K % 4 == 0, K <= 32, H % 4 == 0,

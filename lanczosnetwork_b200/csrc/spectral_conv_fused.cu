@@ -101,40 +101,63 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
 }
 
 // Next-fit assignment of consecutive graphs to tiles.  tiles[0] = T, tiles[1 + t] = first graph
-// of tile t, tiles[1 + T] = B.  One CTA; the extents are staged through shared memory in
-// chunks so the sequential scan runs on on-chip data.
-__global__ void __launch_bounds__(256)
-tile_assign_kernel(const int32_t* __restrict__ gext, int B, int32_t* __restrict__ tiles) {
-  constexpr int CH = 2048;
-  __shared__ int s_n[CH], s_k[CH];
-  __shared__ int st[4];   // rows, krows, count, T
-  const int tid = threadIdx.x;
-  if (tid == 0) { st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 0; tiles[1] = 0; }
+// of tile t, tiles[1 + T] = B.  One CTA.  Parallel part: inclusive prefix sums of the row /
+// Ritz-row counts and, for every graph i, the end of the tile that would start at i (a window
+// of <= 32 graphs); sequential part: one thread follows that jump table (T hops, not B steps).
+__global__ void __launch_bounds__(1024)
+tile_assign_kernel(const int32_t* __restrict__ gext, int B, int32_t* __restrict__ tiles,
+                   int32_t* __restrict__ scratch /* [3 * B] */) {
+  __shared__ int warp_n[32], warp_k[32];
+  __shared__ int run_n, run_k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* PN = scratch;            // inclusive prefix of n_eff
+  int32_t* PK = scratch + B;        // inclusive prefix of ceil4(k_eff)
+  int32_t* NX = scratch + 2 * B;    // end (exclusive) of the tile starting at i
+  if (tid == 0) { run_n = 0; run_k = 0; }
   __syncthreads();
-  for (int c0 = 0; c0 < B; c0 += CH) {
-    const int cn = min(CH, B - c0);
-    for (int i = tid; i < cn; i += 256) {
-      s_n[i] = gext[(c0 + i) * 2];
-      s_k[i] = (gext[(c0 + i) * 2 + 1] + 3) & ~3;
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    const int n = (b < B) ? gext[b * 2] : 0;
+    const int k = (b < B) ? ((gext[b * 2 + 1] + 3) & ~3) : 0;
+    int in = n, ik = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tn = __shfl_up_sync(0xffffffffu, in, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
+      if (lane >= o) { in += tn; ik += tk; }
+    }
+    if (lane == 31) { warp_n[warp] = in; warp_k[warp] = ik; }
+    __syncthreads();
+    if (warp == 0) {
+      int wn = warp_n[lane], wk = warp_k[lane], sn = wn, sk = wk;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tn = __shfl_up_sync(0xffffffffu, sn, o), tk = __shfl_up_sync(0xffffffffu, sk, o);
+        if (lane >= o) { sn += tn; sk += tk; }
+      }
+      warp_n[lane] = sn - wn;
+      warp_k[lane] = sk - wk;
     }
     __syncthreads();
-    if (tid == 0) {
-      int rows = st[0], kr = st[1], cnt = st[2], T = st[3];
-      for (int i = 0; i < cn; ++i) {
-        const int n = s_n[i], k = s_k[i];
-        if (cnt > 0 && (rows + n > RMAX || kr + k > RMAX || cnt == GMAX)) {
-          ++T;
-          tiles[1 + T] = c0 + i;
-          rows = 0; kr = 0; cnt = 0;
-        }
-        rows += n; kr += k; ++cnt;
-      }
-      st[0] = rows; st[1] = kr; st[2] = cnt; st[3] = T;
+    if (b < B) {
+      PN[b] = run_n + warp_n[warp] + in;
+      PK[b] = run_k + warp_k[warp] + ik;
     }
+    __syncthreads();
+    if (tid == 1023) { run_n += warp_n[31] + in; run_k += warp_k[31] + ik; }
     __syncthreads();
   }
+  __threadfence_block();
+  for (int i = tid; i < B; i += 1024) {
+    const int pn0 = i ? PN[i - 1] : 0, pk0 = i ? PK[i - 1] : 0;
+    int j = i + 1;                                   // the first graph always fits (n_eff <= 128)
+    const int jmax = min(B, i + GMAX);
+    while (j < jmax && PN[j] - pn0 <= RMAX && PK[j] - pk0 <= RMAX) ++j;
+    NX[i] = j;
+  }
+  __syncthreads();
   if (tid == 0) {
-    const int T = st[3] + (st[2] > 0 ? 1 : 0);
+    int T = 0, i = 0;
+    while (i < B) { tiles[1 + T] = i; ++T; i = NX[i]; }
     tiles[0] = T;
     tiles[1 + T] = B;
   }
@@ -561,14 +584,14 @@ int lnb_debug_set_prof(unsigned long long* buf) {
 
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
                       int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* gext,
-                      int32_t* tiles) {
+                      int32_t* tiles /* [4*B + 2]: B + 2 tile table followed by 3*B scratch */) {
   LNB_REQUIRE(L && Q && ell_val && ell_idx && ell_max && gext && tiles, "graph_prepare: null pointer");
   LNB_REQUIRE(B >= 0 && N >= 1 && N <= 255 && E1 >= 1 && E1 <= EMAX && K >= 1,
               "graph_prepare: bad dims B=%d N=%d E1=%d K=%d", B, N, E1, K);
   if (B == 0) return LNB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   graph_prepare_kernel<<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
-  tile_assign_kernel<<<1, 256, 0, s>>>(gext, B, tiles);
+  tile_assign_kernel<<<1, 1024, 0, s>>>(gext, B, tiles, tiles + B + 2);
   lnb::count_launch(2);
   return lnb::finish_launch("graph_prepare");
 }

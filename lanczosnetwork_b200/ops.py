@@ -133,7 +133,7 @@ def graph_prepare(L, Q):
   ell_idx = torch.empty((B, E1, N, N), device=dev, dtype=torch.uint8)
   ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
   gext = torch.empty((B, 2), device=dev, dtype=torch.int32)
-  tiles = torch.empty((B + 2,), device=dev, dtype=torch.int32)
+  tiles = torch.empty((4 * B + 2,), device=dev, dtype=torch.int32)   # tile table + scratch
   with torch.cuda.device(dev):
     _lib.check(_lib.load().lnb_graph_prepare(_stream(L), _ptr(L), _ptr(Q), B, N, E1, K,
                                              _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),

@@ -334,6 +334,10 @@ def test_spectral_conv_fused_matches_fp64_and_unfused(B, N, Din, H, molecular):
   T = int(tiles[0])
   starts = tiles[1:T + 2].tolist()
   assert starts[0] == 0 and starts[-1] == B and all(a < b for a, b in zip(starts, starts[1:]))
+  # next-fit: a tile is closed only because the next graph would not fit
+  for a, b in zip(starts[:-1], starts[1:-1]):
+    assert (b - a == 32 or int(gext[a:b + 1, 0].sum()) > 128 or
+            int(((gext[a:b + 1, 1] + 3) // 4 * 4).sum()) > 128)
   for a, b in zip(starts, starts[1:]):
     assert b - a <= 32 and int(gext[a:b, 0].sum()) <= 128
     assert int(((gext[a:b, 1] + 3) // 4 * 4).sum()) <= 128
