@@ -419,3 +419,31 @@ def test_filter_mlp_chain_matches_fp64():
     for b in range(B):
       kk = int(keff[b])
       assert torch.equal(out2[l][b, :kk], out[l][b, :kk])
+
+
+@pytest.mark.parametrize('N,K,B', [(200, 40, 5), (256, 40, 3), (129, 20, 4), (33, 40, 9)])
+def test_lanczos_resident_operator_vs_oracle(N, K, B):
+  """Resident-operator kernel (32 < N <= 256) against the fp64 oracle with the fp32 oracle's own
+  error as the yardstick (no reference output exists at these sizes in the goldens)."""
+  import networkx as nx
+  from lanczosnetwork_b200 import data
+  rng = np.random.RandomState(N + K)
+  A = np.zeros((B, N, N), np.float32)
+  mask = np.zeros((B, N), np.uint8)
+  for b in range(B):
+    n = N if b == 0 else int(rng.randint(N // 2, N + 1))
+    g = nx.fast_gnp_random_graph(n, min(0.5, 8.0 / n), seed=int(rng.randint(10 ** 6)))
+    A[b, :n, :n] = data.get_laplacian(np.asarray(nx.to_numpy_array(g)))
+    mask[b, :n] = 1
+  q1 = rng.randn(B, N).astype(np.float32)
+  out = ops().lanczos_tridiag(torch.from_numpy(A).to(dev()), torch.from_numpy(mask).to(dev()),
+                              torch.from_numpy(q1).to(dev()), K)
+  o64 = orc.lanczos_tridiagonalise(torch.from_numpy(A).double(), torch.from_numpy(mask),
+                                   torch.from_numpy(q1).double(), K)
+  o32 = orc.lanczos_tridiagonalise(torch.from_numpy(A), torch.from_numpy(mask),
+                                   torch.from_numpy(q1), K)
+  assert np.array_equal(out['idx'].cpu().numpy(), o64['idx'].numpy())
+  eT = np.abs(o32['T'].numpy() - o64['T'].numpy()).max()
+  eQ = np.abs(o32['Q'].numpy() - o64['Q'].numpy()).max()
+  assert np.abs(out['T'].cpu().numpy() - o64['T'].numpy()).max() <= max(4 * eT, 2e-5)
+  assert np.abs(out['Q'].cpu().numpy() - o64['Q'].numpy()).max() <= max(4 * eQ, 2e-4)

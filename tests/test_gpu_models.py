@@ -180,3 +180,28 @@ def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates():
     assert not torch.equal(shifted, eager)
     mod.use_cuda_graph = False
     assert torch.equal(mod(*args, mask=mask), shifted)
+
+
+def test_ada_full_qm8_config_vs_oracle():
+  """AdaLanczosNet at the full QM8 config (K=20, 7 layers, 4096-wide learned filter, 351 M
+  parameters) against the fp32 CPU oracle on a small batch, same start vector."""
+  cfg = configs.qm8_ada_lanczos_net()
+  mod = AdaLanczosNet(cfg)
+  params = deterministic_state_dict(mod, 2024)
+  mod.load_state_dict(params)
+  mod = mod.to(dev()).eval()
+  batch = data.synthetic_qm8_batch(6, seed=17)
+  B, N = batch['node_feat'].shape
+  torch.manual_seed(5)
+  q1 = torch.randn(B, N, 1)
+  spec = oracle_spec(mod, 'AdaLanczosNet')
+  ref, aux = orc.ada_lanczos_net_forward(params, spec, batch['node_feat'], batch['L'],
+                                         batch['node_mask'], q1[:, :, 0], return_aux=True)
+  torch.manual_seed(5)
+  with torch.no_grad():
+    out = mod(_t(batch['node_feat']).to(dev()), _t(batch['L']).to(dev()),
+              mask=_t(batch['node_mask']).to(dev()))
+  lz = mod.last_lanczos
+  assert np.array_equal(lz['idx'].cpu().numpy(), aux['idx'].numpy())
+  np.testing.assert_allclose(lz['T'].cpu().numpy(), aux['T'].numpy(), atol=5e-5)
+  np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4)
