@@ -317,17 +317,17 @@ lanczos_resident_kernel(const float* __restrict__ A, const uint8_t* __restrict__
   const int g = blockIdx.x * GPC + grp;
   const int iters = N < K ? N : K;
   // per-graph shared layout
-  const int per_graph = (iters + 1) * NP + 2 * NP + 3 * K + (K + 1) + 32 + TPG * ASP;
+  const int per_graph = ((iters + 1) * NP + 2 * NP + 3 * K + (K + 1) + 32 + TPG * ASP + 3) & ~3;
   float* base = smem_l + (size_t)grp * per_graph;
   float* Qs = base;                            // (iters+1) x NP   Krylov basis
   float* qs = Qs + (size_t)(iters + 1) * NP;   // NP               current q (matvec operand)
   float* zs = qs + NP;                         // NP               z for the projection pass
-  float* al = zs + NP;                         // K
+  float* As = zs + NP;                         // TPG x ASP        (16-byte aligned: float4 reads)
+  float* al = As + (size_t)TPG * ASP;          // K
   float* be = al + K;                          // K
   float* cs = be + K;                          // K                projection coefficients
   float* qq = cs + K;                          // K+1
   float* red = qq + (K + 1);                   // 32
-  float* As = red + 32;                        // TPG x ASP
   const bool live = g < B;                     // whole groups are live or dead together
   const int r = t / TPR, p = t % TPR;          // operator row, column part
   int flip = 0;
@@ -447,7 +447,7 @@ template <int NP, int TPG>
 size_t resident_smem(int N, int K) {
   const int iters = N < K ? N : K;
   constexpr int TPR = TPG / NP, CW = NP / TPR, CS = CW > 64 ? CW - 64 : 0, ASP = CS ? CS + 4 : 0;
-  const size_t per_graph = (size_t)(iters + 1) * NP + 2 * NP + 3 * K + (K + 1) + 32 + (size_t)TPG * ASP;
+  const size_t per_graph = ((size_t)(iters + 1) * NP + 2 * NP + 3 * K + (K + 1) + 32 + (size_t)TPG * ASP + 3) & ~size_t(3);
   return per_graph * (512 / TPG) * sizeof(float);
 }
 
