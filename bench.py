@@ -271,29 +271,29 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop()
 
-    # dominant kernel: the fused spectral-conv layer (messages on-chip + [B*N,1920]x[1920,128]
-    # 3xTF32 GEMM on tcgen05, layers 1..6), timed per launch with CUDA events on the launching
-    # stream.
+    # dominant kernel: the whole 7-layer spectral-conv stack + readout as ONE persistent tcgen05
+    # kernel (K-depth 960 + 6 x 1920 per row), timed per launch with CUDA events on the
+    # launching stream.
     events = []
-    orig = ops.spectral_conv_fused
+    orig = ops.spectral_stack_forward
 
-    def probed(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True, **kw):
-      if w_hi.shape[1] >= 1920:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = orig(X, Q, coeff, prep, w_hi, w_lo, bias, relu, **kw)
-        b.record()
-        events.append((a, b, X.shape[0] * X.shape[1], w_hi.shape[0], w_hi.shape[1]))
-        return r
-      return orig(X, Q, coeff, prep, w_hi, w_lo, bias, relu, **kw)
+    def probed(prep, Q, w_hi, w_lo, bias, dins, H, S, **kw):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      r = orig(prep, Q, w_hi, w_lo, bias, dins, H, S, **kw)
+      b.record()
+      E1 = prep[0].shape[1]
+      kdim = sum((S + E1) * d for d in dins)          # summed GEMM depth of all layers
+      events.append((a, b, Q.shape[0] * Q.shape[1], H, kdim))
+      return r
 
-    ops.spectral_conv_fused = probed
+    ops.spectral_stack_forward = probed
     mod.use_cuda_graph = False            # eager launches so the events bracket single kernels
     for i in range(min(args.steps, 5)):
       step_resident(i)
     torch.cuda.synchronize(dev)
     mod.use_cuda_graph = True
-    ops.spectral_conv_fused = orig
+    ops.spectral_stack_forward = orig
 
   peaks = load_peaks()
   roof = None
@@ -315,13 +315,13 @@ def main():
     real_rows = int(prep[3][:, 0].sum().item())
     executed = 3.0 * 2.0 * n_tiles * 128 * N * K / (avg_ms * 1e-3) / 1e12
     roof = {
-        'bound': 'tensor', 'kernel': 'tc_gemm_kernel<SpectralPolicy> (lnb_spectral_conv_fused)',
+        'bound': 'tensor', 'kernel': 'tc_gemm_kernel<SpectralPolicy> (lnb_spectral_stack_forward, 7 layers + readout)',
         'achieved': achieved, 'peak': peak_tf32, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf32,
         'traffic': traffic, 'avg_ms_per_launch': avg_ms, 'launch_shape': [M, N, K],
         'executed_tensor_tflops': executed, 'frac_executed': executed / peak_tf32,
         'useful_tflops': 2.0 * real_rows * N * K / (avg_ms * 1e-3) / 1e12,
         'packed_tiles': n_tiles, 'real_rows': real_rows,
-        'note': 'achieved = ALGORITHMIC fp32-equivalent GEMM flops 2*(B*N)*H*(C*D) of the padded '
+        'note': 'achieved = ALGORITHMIC fp32-equivalent GEMM flops 2*(B*N)*H*sum_l(C*D_l) of the padded '
                 'reference formulation / CUDA-event time per launch. The kernel drops padded rows '
                 '(packed tiles) and issues 3 TF32 MMAs per product (3xTF32): executed_tensor_tflops '
                 '= 3*2*(tiles*128)*H*(C*D)/t is what the tensor pipe does; useful_tflops counts real '

@@ -116,6 +116,32 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
                             int K, int S, int H, int relu, int write_pad, float* out);
 
 /* ---------------------------------------------------------------------------------------
+ * The whole convolution stack (and optionally the embedding gather in front and the readout
+ * behind it) in ONE persistent kernel: every CTA keeps its packed tile's state in shared memory
+ * across layers, so between layers nothing touches HBM.  Layer l uses rows [l*H, (l+1)*H) of
+ * the stacked split weights W_hi / W_lo [num_layers*H, Kw] (columns beyond (S+E1)*Din[l] zero),
+ * bias + l*H and coeff + l*coeff_layer_stride.  Input: X [B,N,Din[0]] or node_ids [B,N] +
+ * emb_table [emb_rows, Din[0]] (model/lanczos_net.py:154).  Outputs: out_state [B,N,H] (may be
+ * NULL) and / or score [B,P] from the fused readout (model/lanczos_net.py:185-194; mask may be
+ * NULL = mean over all N nodes).  Same shape limits as lnb_spectral_conv_fused, plus
+ * Din[l>0] == H and num_layers <= 8.
+ * ------------------------------------------------------------------------------------- */
+typedef struct lnb_spectral_stack {
+  const float* X; const int64_t* node_ids; const float* emb_table;
+  const float* Q; const float* coeff; int64_t coeff_layer_stride;
+  const float* ell_val; const uint8_t* ell_idx; const int32_t* ell_max; const int32_t* gext;
+  const int32_t* tiles;
+  const float* W_hi; const float* W_lo; const float* bias;
+  float* out_state;
+  const float* W_out; const float* b_out; const float* w_att; const float* b_att;
+  const uint8_t* mask; float* score;
+  int32_t Din[8];
+  int32_t num_layers, Kw, emb_rows, P, write_pad;
+  int32_t B, N, E1, K, S, H, relu;
+} lnb_spectral_stack;
+int lnb_spectral_stack_forward(lnb_stream_t stream, const lnb_spectral_stack* desc /* host */);
+
+/* ---------------------------------------------------------------------------------------
  * Embedding rows (model/lanczos_net.py:154): out[r, :] = table[idx[r], :].
  * ------------------------------------------------------------------------------------- */
 int lnb_embedding_rows(lnb_stream_t stream, const int64_t* idx, const float* table,

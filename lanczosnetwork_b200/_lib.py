@@ -29,6 +29,25 @@ class GemmDesc(ctypes.Structure):
   ]
 
 
+class SpectralStack(ctypes.Structure):
+  """lnb_spectral_stack (include/lanczosnet_b200.h)."""
+  _fields_ = [
+      ('X', ctypes.c_void_p), ('node_ids', ctypes.c_void_p), ('emb_table', ctypes.c_void_p),
+      ('Q', ctypes.c_void_p), ('coeff', ctypes.c_void_p), ('coeff_layer_stride', c_i64),
+      ('ell_val', ctypes.c_void_p), ('ell_idx', ctypes.c_void_p), ('ell_max', ctypes.c_void_p),
+      ('gext', ctypes.c_void_p), ('tiles', ctypes.c_void_p),
+      ('W_hi', ctypes.c_void_p), ('W_lo', ctypes.c_void_p), ('bias', ctypes.c_void_p),
+      ('out_state', ctypes.c_void_p),
+      ('W_out', ctypes.c_void_p), ('b_out', ctypes.c_void_p), ('w_att', ctypes.c_void_p),
+      ('b_att', ctypes.c_void_p), ('mask', ctypes.c_void_p), ('score', ctypes.c_void_p),
+      ('Din', ctypes.c_int32 * 8),
+      ('num_layers', ctypes.c_int32), ('Kw', ctypes.c_int32), ('emb_rows', ctypes.c_int32),
+      ('P', ctypes.c_int32), ('write_pad', ctypes.c_int32),
+      ('B', ctypes.c_int32), ('N', ctypes.c_int32), ('E1', ctypes.c_int32), ('K', ctypes.c_int32),
+      ('S', ctypes.c_int32), ('H', ctypes.c_int32), ('relu', ctypes.c_int32),
+  ]
+
+
 # name -> (restype, argtypes): every symbol include/lanczosnet_b200.h declares
 SIGNATURES = {
     'lnb_abi_version': (c_int, []),
@@ -50,6 +69,7 @@ SIGNATURES = {
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
                  ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int,
                  c_int, c_int, c_int, c_int, c_int, c_int, c_f32p]),
+    'lnb_spectral_stack_forward': (c_int, [c_stream, ctypes.POINTER(SpectralStack)]),
     'lnb_ritz_rowmap': (c_int, [c_stream, ctypes.c_void_p, c_int, c_int, ctypes.c_void_p, ctypes.c_void_p]),
     'lnb_ritz_filter_mlp': (c_int, [c_stream, c_f32p, ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p,
                                     c_f32p, c_int, c_int, c_int, c_int, c_f32p]),

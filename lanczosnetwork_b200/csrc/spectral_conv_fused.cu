@@ -166,39 +166,55 @@ tile_assign_kernel(const int32_t* __restrict__ gext, int B, int32_t* __restrict_
 // --------------------------------------------------------------------------------------------
 struct SpectralPolicy {
   static constexpr int kStagesB = 2;      // two W stages: shared memory goes to the packed tile
+  static constexpr int LMAX = 8;          // layers run by one launch
   struct Params {
-    const float* X;         // [B, N, Din]
+    const float* X;         // [B, N, Din0] input state, or nullptr with node_ids/emb (embedding)
+    const int64_t* node_ids;// [B, N]
+    const float* emb;       // [emb_rows, Din0]
     const float* Q;         // [B, N, K]
-    const float* coeff;     // [B, K, S]
+    const float* coeff;     // layer l: coeff + l * coeff_stride -> [B, K, S]
+    int64_t coeff_stride;
     const float* ell_val;   // [B, E1, N, N]
     const uint8_t* ell_idx; // [B, E1, N, N]
     const int32_t* ell_max; // [B, E1]
     const int32_t* gext;    // [B, 2]
     const int32_t* tiles;   // [B + 2]
-    const float* bias;      // [H]
-    float* out;             // [B, N, H]
-    int B, N, Din, E1, K, S, H, relu;
+    const float* bias;      // layer l: bias + l * H (may be null)
+    float* out;             // [B, N, H] final state (may be null when the readout is fused)
+    // fused readout (model/lanczos_net.py:185-194); score == nullptr disables it
+    const float* W_out;     // [P, H]
+    const float* b_out;     // [P]
+    const float* w_att;     // [H]
+    const float* b_att;     // [1]
+    const uint8_t* mask;    // [B, N] or null (mean over all N nodes)
+    float* score;           // [B, P]
+    int P, emb_rows;
+    int L;                  // number of layers in this launch
+    int Din[LMAX];          // input width of each layer (Din[l>0] == H)
+    int B, N, E1, K, S, H, relu;
     int LB;                 // ELL lines (channel, t) that fit in shared memory
-    int write_pad;          // also write the constant rows of padded nodes (needed by readers of
-                            // the full [B,N,H] tensor, i.e. after the last layer)
+    int write_pad;          // also write the constant rows of padded nodes of `out`
     int dbg;                // debug experiment flags (LNB_DBG), 0 in production
   };
+  // sub = layer * 2 + step  (step 0: Z accumulation, step 1: edge accumulation + epilogue)
   static __device__ __forceinline__ int num_steps(const Params& p, int cta, int ncta) {
     const int T = __ldg(p.tiles);
     const int mine = T > cta ? (T - cta + ncta - 1) / ncta : 0;
-    return p.S > 0 ? 2 * mine : mine;
+    return (p.S > 0 ? 2 : 1) * p.L * mine;
   }
   static __device__ __forceinline__ void decode(const Params& p, int cta, int ncta, int it,
                                                 int& m_tile, int& sub) {
-    if (p.S > 0) { m_tile = cta + (it >> 1) * ncta; sub = it & 1; }
-    else { m_tile = cta + it * ncta; sub = 1; }
+    const int per = (p.S > 0 ? 2 : 1) * p.L;
+    const int rem = it % per;
+    m_tile = cta + (it / per) * ncta;
+    sub = p.S > 0 ? rem : rem * 2 + 1;
   }
   static __device__ __forceinline__ int num_kblocks(const Params& p, int sub) {
-    return (sub == 0 ? p.S : p.E1) * p.Din / tcg::BK;
+    return ((sub & 1) == 0 ? p.S : p.E1) * p.Din[sub >> 1] / tcg::BK;
   }
   static __device__ __forceinline__ void w_coords(const Params& p, int sub, int kb, int& col0, int& row0) {
-    col0 = (sub == 0 ? 0 : p.S * p.Din) + kb * tcg::BK;
-    row0 = 0;
+    col0 = ((sub & 1) == 0 ? 0 : p.S * p.Din[sub >> 1]) + kb * tcg::BK;
+    row0 = (sub >> 1) * p.H;
   }
 
   struct Tables {
@@ -213,7 +229,8 @@ struct SpectralPolicy {
 
   const Params& p;
   const int tid, r;
-  const int N, Din, K, S, E1, H, XP;      // hot parameters in registers
+  const int N, K, S, E1, H, XP;           // hot parameters in registers
+  int Din;                                // input width of the current layer
   float* Xs;                // X rows [RMAX][XP]; reused for V Z + the finished output rows
   float* UZ;                // U rows (graph,k) [RMAX][XP] during step 0, Z afterwards
   float* Qs;                // [RMAX][K]
@@ -225,8 +242,8 @@ struct SpectralPolicy {
   static __host__ __device__ constexpr size_t tables_bytes() { return (sizeof(Tables) + 15) & ~size_t(15); }
 
   __device__ SpectralPolicy(const Params& p_, uint8_t* smem, int tid_)
-      : p(p_), tid(tid_), r(tid_ & 127), N(p_.N), Din(p_.Din), K(p_.K), S(p_.S), E1(p_.E1),
-        H(p_.H), XP((p_.Din > p_.H ? p_.Din : p_.H) + 4) {
+      : p(p_), tid(tid_), r(tid_ & 127), N(p_.N), K(p_.K), S(p_.S), E1(p_.E1),
+        H(p_.H), XP((p_.Din[0] > p_.H ? p_.Din[0] : p_.H) + 4), Din(p_.Din[0]) {
     Xs = reinterpret_cast<float*>(smem);
     UZ = Xs + (size_t)RMAX * XP;
     Qs = UZ + (size_t)RMAX * XP;
@@ -294,17 +311,27 @@ struct SpectralPolicy {
 
   __device__ void step_begin(int m_tile, int sub, int /*kb_first*/, tcg::PhaseTimer& tm) {
     tcg::producers_sync();              // previous step's smem readers / writers are done
-    if (sub == 1 && S > 0) return;      // tile state was staged by step 0
+    const int layer = sub >> 1, step = sub & 1;
+    if (step == 1 && S > 0) return;     // tile state was staged by step 0 of this layer
+    Din = p.Din[layer];
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = tcg::PRODUCER_THREADS / 32;
+    const int dv = Din / 4;
+    if (layer == 0) {
     if (warp == 0) build_tables(m_tile);
     tcg::producers_sync();
-    const int gs = tb->gs, Rtot = tb->Rtot, Ztot = tb->Ztot;
+    const int gs = tb->gs, Rtot = tb->Rtot;
     // ---- phase A: asynchronous copies of the real rows of X and Q (one warp per row) --------
-    const int dv = Din / 4;
     for (int row = warp; row < Rtot; row += NW) {
       const int64_t src_row = (int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row];
-      const float* xsrc = p.X + src_row * Din;
+      const float* xsrc;
+      if (p.X) {
+        xsrc = p.X + src_row * Din;
+      } else {                                  // embedding rows (model/lanczos_net.py:154)
+        int64_t id = __ldg(p.node_ids + src_row);
+        id = id < 0 ? 0 : (id >= p.emb_rows ? p.emb_rows - 1 : id);
+        xsrc = p.emb + id * Din;
+      }
       float* xd = Xs + (size_t)row * XP;
       for (int q4 = lane; q4 < dv; q4 += 32) tc05::cp_async_16(xd + 4 * q4, xsrc + 4 * q4);
       const float* qsrc = p.Q + src_row * K;
@@ -345,13 +372,15 @@ struct SpectralPolicy {
         }
       }
     }
-    // this thread's (graph, k) row: filter coefficients into registers
+    }  // layer == 0: tile state staged once, reused by every layer
+    const int gs = tb->gs, Ztot = tb->Ztot;
+    // this thread's (graph, k) row: filter coefficients of this layer into registers
 #pragma unroll
     for (int i = 0; i < FR; ++i) fr[i] = 0.f;
     if (S > 0 && r < Ztot) {
       const int g = tb->z_g[r], k = tb->z_k[r];
       if (k < tb->gk[g]) {                       // rows beyond k_eff multiply zero rows of U
-        const float* f = p.coeff + ((int64_t)(gs + g) * K + k) * S;
+        const float* f = p.coeff + layer * p.coeff_stride + ((int64_t)(gs + g) * K + k) * S;
 #pragma unroll
         for (int i = 0; i < FR; ++i)
           if (i < S) fr[i] = __ldg(f + i);
@@ -399,7 +428,7 @@ struct SpectralPolicy {
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
     const int j0 = kb * tcg::BK;
     const int c = j0 / Din, d0 = j0 - c * Din;
-    if (sub == 0) {
+    if ((sub & 1) == 0) {
       // row = (graph, Ritz index): f[k, s] * U[row, d0:d0+32]
       if (r >= tb->Ztot) return;
       float f = 0.f;
@@ -408,7 +437,7 @@ struct SpectralPolicy {
         for (int i = 0; i < FR; ++i) f = (i == c) ? fr[i] : f;
       } else {
         const int g = tb->z_g[r], k = tb->z_k[r];
-        f = (k < tb->gk[g]) ? __ldg(p.coeff + ((int64_t)(tb->gs + g) * K + k) * S + c) : 0.f;
+        f = (k < tb->gk[g]) ? __ldg(p.coeff + (sub >> 1) * p.coeff_stride + ((int64_t)(tb->gs + g) * K + k) * S + c) : 0.f;
       }
       const float4* u4 = reinterpret_cast<const float4*>(UZ + (size_t)r * XP + d0);
 #pragma unroll
@@ -466,7 +495,7 @@ struct SpectralPolicy {
   // After the last k-block of the edge step: (V Z)[row, :] for every real row in 4 x 4 register
   // tiles into the (now dead) X buffer; overlaps with the tensor core draining its queue.
   __device__ void pre_epilogue(int sub) {
-    if (sub == 0) return;
+    if ((sub & 1) == 0) return;
     tcg::producers_sync();              // every producer is done reading X
     if (S == 0) return;
     const int hv = H / 4;
@@ -504,7 +533,7 @@ struct SpectralPolicy {
 
   __device__ __forceinline__ void store(int sub, int col, float (&x)[32]) {
     if (col >= H) return;
-    if (sub == 0) {
+    if ((sub & 1) == 0) {
       // drain Z[row, col:col+32] to shared memory (overwrites U, which is dead by now)
       if (r < tb->Ztot) {
         float4* z4 = reinterpret_cast<float4*>(UZ + (size_t)r * XP + col);
@@ -517,6 +546,7 @@ struct SpectralPolicy {
     if (r >= tb->Rtot) return;
     float4* o4 = reinterpret_cast<float4*>(Xs + (size_t)r * XP + col);
     const bool relu = p.relu != 0;
+    const float* bias = p.bias ? p.bias + (sub >> 1) * H : nullptr;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float y[4] = {x[4 * q + 0], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]};
@@ -528,45 +558,96 @@ struct SpectralPolicy {
       for (int u = 0; u < 4; ++u) {
         const int c = col + 4 * q + u;
         if (c < H) {
-          if (p.bias) y[u] += __ldg(p.bias + c);
+          if (bias) y[u] += __ldg(bias + c);
           if (relu) y[u] = fmaxf(y[u], 0.f);
         }
       }
-      o4[q] = make_float4(y[0], y[1], y[2], y[3]);   // finished row chunk, written back below
+      o4[q] = make_float4(y[0], y[1], y[2], y[3]);   // finished row chunk = next layer's X row
     }
   }
 
-  // Coalesced write-back: real rows from shared memory (one warp per 512-byte row), plus the
-  // constant rows act(b) of padded nodes when requested.
+  // After the last layer: coalesced write-back of the final state (real rows from shared
+  // memory, one warp per 512-byte row, plus the constant rows act(b) of padded nodes when
+  // requested) and / or the fused readout.  Between layers the state never leaves the SM.
   __device__ void post_epilogue(int sub) {
-    if (sub == 0) return;
+    if ((sub & 1) == 0 || (sub >> 1) != p.L - 1) return;
     tcg::producers_sync();              // every chunk of every row is in shared memory
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = tcg::PRODUCER_THREADS / 32;
     const int hv = H / 4, gs = tb->gs, Rtot = tb->Rtot;
-    for (int row = warp; row < Rtot; row += NW) {
-      const float4* src = reinterpret_cast<const float4*>(Xs + (size_t)row * XP);
-      float4* dst = reinterpret_cast<float4*>(
-          p.out + ((int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row]) * H);
-      for (int q4 = lane; q4 < hv; q4 += 32) dst[q4] = src[q4];
-    }
-    if (p.write_pad) {
-      const int npad = tb->ng * N - Rtot;
-      for (int i = warp; i < npad; i += NW) {
-        // i-th padded (graph, node) pair of the tile, found by walking the per-graph pad counts
-        int g = 0, rem = i;
-        while (rem >= N - tb->gn[g]) { rem -= N - tb->gn[g]; ++g; }
-        float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)(gs + g) * N + tb->gn[g] + rem) * H);
-        for (int q4 = lane; q4 < hv; q4 += 32) {
-          float y[4];
+    const float* bias = p.bias ? p.bias + (p.L - 1) * H : nullptr;
+    if (p.out) {
+      for (int row = warp; row < Rtot; row += NW) {
+        const float4* src = reinterpret_cast<const float4*>(Xs + (size_t)row * XP);
+        float4* dst = reinterpret_cast<float4*>(
+            p.out + ((int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row]) * H);
+        for (int q4 = lane; q4 < hv; q4 += 32) dst[q4] = src[q4];
+      }
+      if (p.write_pad) {
+        const int npad = tb->ng * N - Rtot;
+        for (int i = warp; i < npad; i += NW) {
+          // i-th padded (graph, node) pair of the tile, found by walking the per-graph pad counts
+          int g = 0, rem = i;
+          while (rem >= N - tb->gn[g]) { rem -= N - tb->gn[g]; ++g; }
+          float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)(gs + g) * N + tb->gn[g] + rem) * H);
+          for (int q4 = lane; q4 < hv; q4 += 32) {
+            float y[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float t = p.bias ? __ldg(p.bias + 4 * q4 + u) : 0.f;
-            y[u] = (p.relu != 0) ? fmaxf(t, 0.f) : t;
+            for (int u = 0; u < 4; ++u) {
+              float t = bias ? __ldg(bias + 4 * q4 + u) : 0.f;
+              y[u] = (p.relu != 0) ? fmaxf(t, 0.f) : t;
+            }
+            dst[q4] = make_float4(y[0], y[1], y[2], y[3]);
           }
-          dst[q4] = make_float4(y[0], y[1], y[2], y[3]);
         }
       }
+    }
+    if (p.score) readout(bias);
+  }
+
+  // Fused readout (model/lanczos_net.py:185-194): y = (W_out x + b_out) * sigmoid(w_att.x + b_att)
+  // per node, masked mean over the nodes of each graph.  Rows of padded nodes are the constant
+  // act(b_last); they count only where the mask says so (or when there is no mask).
+  __device__ void readout(const float* bias_last) {
+    const int P = p.P, P1 = p.P + 1, HP = H + 1;
+    float* Wr = UZ;                                  // [(P+1)][HP]  (Z is dead by now)
+    float* Yr = Wr + (size_t)P1 * HP;                // [RMAX + 1][P1]  per-row gated outputs; last = pad row
+    float* cx = Yr + (size_t)(RMAX + 1) * P1;        // [H] constant padded-node state
+    for (int e = tid; e < P1 * H; e += tcg::PRODUCER_THREADS) {
+      const int o = e / H, h = e - o * H;
+      Wr[o * HP + h] = (o < P) ? __ldg(p.W_out + o * H + h) : __ldg(p.w_att + h);
+    }
+    for (int h = tid; h < H; h += tcg::PRODUCER_THREADS) {
+      float t = bias_last ? __ldg(bias_last + h) : 0.f;
+      cx[h] = (p.relu != 0) ? fmaxf(t, 0.f) : t;
+    }
+    tcg::producers_sync();
+    const int Rtot = tb->Rtot;
+    // one thread per (row, output); row RMAX stands for the constant padded-node row
+    for (int e = tid; e < (Rtot + 1) * P1; e += tcg::PRODUCER_THREADS) {
+      const int rr = e / P1, o = e - rr * P1;
+      const float* x = (rr < Rtot) ? Xs + (size_t)rr * XP : cx;
+      const float* w = Wr + o * HP;
+      float acc = 0.f;
+      for (int h = 0; h < H; ++h) acc = fmaf(x[h], w[h], acc);
+      acc += (o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att);
+      Yr[(rr < Rtot ? rr : RMAX) * P1 + o] = acc;
+    }
+    tcg::producers_sync();
+    for (int e = tid; e < tb->ng * P; e += tcg::PRODUCER_THREADS) {
+      const int g = e / P, o = e - g * P;
+      const int nb = tb->nbase[g], n_g = tb->gn[g];
+      const uint8_t* m = p.mask ? p.mask + (int64_t)(tb->gs + g) * N : nullptr;
+      float acc = 0.f;
+      int cnt = 0;
+      for (int n = 0; n < N; ++n) {
+        if (m && m[n] == 0) continue;
+        const float* y = Yr + (n < n_g ? nb + n : RMAX) * P1;
+        const float gate = 1.f / (1.f + expf(-y[P]));
+        acc += gate * y[o];
+        ++cnt;
+      }
+      p.score[(int64_t)(tb->gs + g) * P + o] = acc / (float)cnt;
     }
   }
 };
@@ -596,48 +677,81 @@ int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B
   return lnb::finish_launch("graph_prepare");
 }
 
-int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q, const float* coeff,
-                            const float* ell_val, const uint8_t* ell_idx, const int32_t* ell_max,
-                            const int32_t* gext, const int32_t* tiles, const float* W_hi,
-                            const float* W_lo, const float* bias, int B, int N, int Din, int E1,
-                            int K, int S, int H, int relu, int write_pad, float* out) {
-  LNB_REQUIRE(X && Q && ell_val && ell_idx && ell_max && gext && tiles && W_hi && W_lo && out &&
-                  (coeff || S == 0),
-              "spectral_conv_fused: null pointer");
-  LNB_REQUIRE(B >= 0 && N >= 1 && Din >= 1 && E1 >= 1 && K >= 1 && S >= 0 && H >= 1,
-              "spectral_conv_fused: bad dims");
-  if (N > RMAX || Din % 32 != 0 || K > KMAX || K % 4 != 0 || H % 4 != 0 || H > tcg::BN || E1 > EMAX) {
-    lnb::set_err("spectral_conv_fused: unsupported shape N=%d Din=%d K=%d H=%d E1=%d "
-                 "(needs N<=128, Din%%32==0, K%%4==0, K<=%d, H%%4==0, H<=128, E1<=%d)",
-                 N, Din, K, H, E1, KMAX, EMAX);
+static int launch_stack(lnb_stream_t stream, const lnb_spectral_stack& d, const char* who) {
+  LNB_REQUIRE((d.X || (d.node_ids && d.emb_table)) && d.Q && d.ell_val && d.ell_idx && d.ell_max &&
+                  d.gext && d.tiles && d.W_hi && d.W_lo && (d.out_state || d.score) &&
+                  (d.coeff || d.S == 0),
+              "%s: null pointer", who);
+  LNB_REQUIRE(d.B >= 0 && d.N >= 1 && d.E1 >= 1 && d.K >= 1 && d.S >= 0 && d.H >= 1 &&
+                  d.num_layers >= 1 && d.num_layers <= SpectralPolicy::LMAX,
+              "%s: bad dims", who);
+  LNB_REQUIRE(!d.score || (d.W_out && d.b_out && d.w_att && d.b_att && d.P >= 1 && d.P <= 64),
+              "%s: readout needs W_out, b_out, w_att, b_att and 1 <= P <= 64", who);
+  int dmax = 0;
+  bool ok = d.N <= RMAX && d.K <= KMAX && d.K % 4 == 0 && d.H % 4 == 0 && d.H <= tcg::BN && d.E1 <= EMAX;
+  for (int l = 0; l < d.num_layers; ++l) {
+    ok = ok && d.Din[l] % 32 == 0 && d.Din[l] >= 32 && (l == 0 || d.Din[l] == d.H);
+    dmax = d.Din[l] > dmax ? d.Din[l] : dmax;
+  }
+  ok = ok && (d.S + d.E1) * dmax <= d.Kw;
+  if (!ok) {
+    lnb::set_err("%s: unsupported shape N=%d K=%d H=%d E1=%d (needs N<=128, Din%%32==0, inner "
+                 "layers Din==H, K%%4==0, K<=%d, H%%4==0, H<=128, E1<=%d)", who, d.N, d.K, d.H, d.E1,
+                 KMAX, EMAX);
     return LNB_ERR_UNSUPPORTED;
   }
-  if (B == 0) return LNB_OK;
-  size_t smem = tcg::core_smem(SpectralPolicy::kStagesB) + 1024 + SpectralPolicy::smem_fixed(Din, K, H);
+  if (d.B == 0) return LNB_OK;
+  size_t smem = tcg::core_smem(SpectralPolicy::kStagesB) + 1024 + SpectralPolicy::smem_fixed(dmax, d.K, d.H);
   if (smem > 227 * 1024) {
-    lnb::set_err("spectral_conv_fused: tile state (Din=%d, K=%d, H=%d) needs %zu B of shared memory",
-                 Din, K, H, smem);
+    lnb::set_err("%s: tile state (Din=%d, K=%d, H=%d) needs %zu B of shared memory", who, dmax, d.K,
+                 d.H, smem);
     return LNB_ERR_UNSUPPORTED;
   }
   int lb = (int)((227 * 1024 - smem) / SpectralPolicy::ell_line_bytes());
   if (lb > 255) lb = 255;
   smem += (size_t)lb * SpectralPolicy::ell_line_bytes();
-  const int Kw = (S + E1) * Din;
   CUtensorMap map_hi, map_lo;
-  int rc = tcg::make_weight_map(&map_hi, W_hi, H, Kw, "spectral_conv_fused");
+  int rc = tcg::make_weight_map(&map_hi, d.W_hi, d.num_layers * d.H, d.Kw, who);
   if (rc != LNB_OK) return rc;
-  rc = tcg::make_weight_map(&map_lo, W_lo, H, Kw, "spectral_conv_fused");
+  rc = tcg::make_weight_map(&map_lo, d.W_lo, d.num_layers * d.H, d.Kw, who);
   if (rc != LNB_OK) return rc;
   auto kern = tcg::tc_gemm_kernel<SpectralPolicy>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  SpectralPolicy::Params p{X, Q, coeff, ell_val, ell_idx, ell_max, gext, tiles, bias, out,
-                           B, N, Din, E1, K, S, H, relu, lb, write_pad, tcg::debug_flags()};
+  SpectralPolicy::Params p{};
+  p.X = d.X; p.node_ids = d.node_ids; p.emb = d.emb_table; p.Q = d.Q;
+  p.coeff = d.coeff; p.coeff_stride = d.coeff_layer_stride;
+  p.ell_val = d.ell_val; p.ell_idx = d.ell_idx; p.ell_max = d.ell_max; p.gext = d.gext; p.tiles = d.tiles;
+  p.bias = d.bias; p.out = d.out_state;
+  p.W_out = d.W_out; p.b_out = d.b_out; p.w_att = d.w_att; p.b_att = d.b_att; p.mask = d.mask;
+  p.score = d.score; p.P = d.P; p.emb_rows = d.emb_rows; p.L = d.num_layers;
+  for (int l = 0; l < d.num_layers; ++l) p.Din[l] = d.Din[l];
+  p.B = d.B; p.N = d.N; p.E1 = d.E1; p.K = d.K; p.S = d.S; p.H = d.H; p.relu = d.relu;
+  p.LB = lb; p.write_pad = d.write_pad; p.dbg = tcg::debug_flags();
   // the tile count lives in device memory (no host sync): one persistent CTA per SM, bounded by
   // the worst case of one graph per tile
-  const int grid = B < tcg::sm_count() ? B : tcg::sm_count();
+  const int grid = d.B < tcg::sm_count() ? d.B : tcg::sm_count();
   kern<<<grid, tcg::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
   lnb::count_launch();
-  return lnb::finish_launch("spectral_conv_fused");
+  return lnb::finish_launch(who);
+}
+
+int lnb_spectral_stack_forward(lnb_stream_t stream, const lnb_spectral_stack* desc) {
+  LNB_REQUIRE(desc, "spectral_stack_forward: null descriptor");
+  return launch_stack(stream, *desc, "spectral_stack_forward");
+}
+
+int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q, const float* coeff,
+                            const float* ell_val, const uint8_t* ell_idx, const int32_t* ell_max,
+                            const int32_t* gext, const int32_t* tiles, const float* W_hi,
+                            const float* W_lo, const float* bias, int B, int N, int Din, int E1,
+                            int K, int S, int H, int relu, int write_pad, float* out) {
+  lnb_spectral_stack d{};
+  d.X = X; d.Q = Q; d.coeff = coeff; d.coeff_layer_stride = 0;
+  d.ell_val = ell_val; d.ell_idx = ell_idx; d.ell_max = ell_max; d.gext = gext; d.tiles = tiles;
+  d.W_hi = W_hi; d.W_lo = W_lo; d.Kw = (S + E1) * Din; d.bias = bias;
+  d.Din[0] = Din; d.num_layers = 1; d.out_state = out; d.write_pad = write_pad;
+  d.B = B; d.N = N; d.E1 = E1; d.K = K; d.S = S; d.H = H; d.relu = relu;
+  return launch_stack(stream, d, "spectral_conv_fused");
 }
 
 }  // extern "C"

@@ -12,7 +12,8 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from ..data import check_dist
-from ..spectral_conv import WeightCache
+from ..spectral_conv import (GraphContext, WeightCache, graph_conv_layer,
+                             ritz_filter_coefficients)
 
 
 def _opt(obj, name, default):
@@ -192,6 +193,65 @@ class SpectralNetBase(nn.Module):
       out.append([('spectral_filter.%d.%d' % (l, i), seq[i].weight, seq[i].bias)
                   for i in (0, 2, 4, 6)])
     return out
+
+  def _ritz_conv_stack(self, state, node_ids, L, D, V, mask):
+    """Convolution stack + readout of the Ritz-pair models (LanczosNet, LanczosNetGeneral).
+
+    Consecutive layers the fused kernel supports run as ONE persistent launch (embedding gather
+    in front when every layer qualifies, readout behind); a leading layer with an unsupported
+    input width (e.g. LanczosNetGeneral's 10 features) runs through the unfused ops first."""
+    S, nl = self.num_scale_long, self.num_layer
+    N, K, E1 = L.shape[1], V.shape[2], L.shape[3]
+    din0 = self.embedding.weight.shape[1] if node_ids is not None else state.shape[2]
+    dims = [din0] + list(self.hidden_dim)
+    ok = [ops.fused_conv_supported(N, dims[t], K, dims[t + 1], len(self.short_diffusion_dist),
+                                   False, S, E1) and (t == 0 or dims[t] == dims[t + 1] or True)
+          for t in range(nl)]
+    H = dims[1]
+    uniform = all(d == H for d in dims[1:])
+    first = 0
+    while first < nl and not ok[first]:
+      first += 1
+    stack_ok = uniform and first < nl and all(ok[first:]) and nl - first <= 8
+    ctx = GraphContext(L, V)
+    coeffs = table = None
+    if S > 0:
+      mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
+      gext = ctx.prep()[3] if (mlp is not None and stack_ok and first == 0) else None
+      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache, gext)
+
+    def layer_coeff(t):
+      if S == 0:
+        return None
+      return coeffs[t] if coeffs is not None else table
+
+    if node_ids is not None and not (stack_ok and first == 0):
+      state = ops.embedding_rows(node_ids, self.embedding.weight)
+    for t in range(first if stack_ok else nl):           # unfused / single-layer prefix
+      state = graph_conv_layer(state, ctx, layer_coeff(t), False, self.short_diffusion_dist, S,
+                               self.filter[t].weight, self.filter[t].bias, self._wcache,
+                               'filter.%d' % t, last=(t == nl - 1))
+    if not stack_ok:
+      return self._readout(state, mask)
+    layers = list(range(first, nl))
+    kw = (S + E1) * max(dims[t] for t in layers)
+    w_hi, w_lo, bias = self._wcache.split_conv_stack(
+        'filter.stack.%d' % first, [self.filter[t].weight for t in layers],
+        [self.filter[t].bias for t in layers], kw)
+    if S == 0:
+      coeff, stride = None, 0
+    elif coeffs is not None:
+      coeff, stride = coeffs[first], coeffs.stride(0)
+    else:
+      coeff, stride = table, 0
+    head, att = self.filter[nl], self.att_func[0]
+    _, score = ops.spectral_stack_forward(
+        ctx.prep(), V, w_hi, w_lo, bias, [dims[t] for t in layers], H, S, coeff=coeff,
+        coeff_stride=stride, X=None if (node_ids is not None and first == 0) else state,
+        node_ids=node_ids if first == 0 else None,
+        emb=self.embedding.weight if (node_ids is not None and first == 0) else None,
+        readout=(head.weight, head.bias, att.weight.reshape(-1), att.bias), mask=mask)
+    return score
 
   def _readout(self, state, mask):
     head = self.filter[self.num_layer]

@@ -9,11 +9,11 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GemmDesc
+from ._lib import GemmDesc, SpectralStack
 
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
-    'fused_conv_supported', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
+    'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
     'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
@@ -175,6 +175,62 @@ def spectral_conv_fused(X, Q, coeff, prep, w_hi, w_lo, bias, relu=True, write_pa
         _ptr(gext), _ptr(tiles), _ptr(w_hi), _ptr(w_lo), _ptr(bias), B, N, Din, E1, K, S, H,
         int(bool(relu)), int(bool(write_pad)), _ptr(out)), 'lnb_spectral_conv_fused')
   return out
+
+
+def spectral_stack_forward(prep, Q, w_hi, w_lo, bias, dins, H, S, coeff=None, coeff_stride=0,
+                           X=None, node_ids=None, emb=None, want_state=False, write_pad=True,
+                           readout=None, mask=None, relu=True):
+  """All convolution layers (+ optional embedding gather and readout) in one persistent kernel.
+
+  prep = graph_prepare(L, Q); w_hi/w_lo [len(dins)*H, Kw] stacked split weights, bias
+  [len(dins)*H]; dins = input width per layer; coeff = tensor whose layer l block starts at
+  element l*coeff_stride (None when S == 0); X [B,N,dins[0]] or node_ids [B,N] + emb;
+  readout = (W_out [P,H], b_out [P], w_att [H], b_att [1]) -> score [B,P].
+  Returns (state or None, score or None)."""
+  ell_val, ell_idx, ell_max, gext, tiles = prep
+  _need_cuda(Q, w_hi, w_lo, bias, coeff, X, node_ids, emb, mask)
+  Q = _f32c(Q)
+  B, N, K = Q.shape
+  E1 = ell_val.shape[1]
+  dev = Q.device
+  d = SpectralStack()
+  if X is not None:
+    X = _f32c(X)
+    d.X = X.data_ptr()
+  else:
+    node_ids = node_ids.contiguous().long()
+    emb = _f32c(emb)
+    d.node_ids, d.emb_table, d.emb_rows = node_ids.data_ptr(), emb.data_ptr(), emb.shape[0]
+  d.Q = Q.data_ptr()
+  if coeff is not None:
+    d.coeff, d.coeff_layer_stride = coeff.data_ptr(), int(coeff_stride)
+  d.ell_val, d.ell_idx, d.ell_max = ell_val.data_ptr(), ell_idx.data_ptr(), ell_max.data_ptr()
+  d.gext, d.tiles = gext.data_ptr(), tiles.data_ptr()
+  d.W_hi, d.W_lo = w_hi.data_ptr(), w_lo.data_ptr()
+  d.bias = bias.data_ptr() if bias is not None else None
+  state = score = None
+  if want_state or readout is None:
+    state = torch.empty((B, N, H), device=dev, dtype=torch.float32)
+    d.out_state = state.data_ptr()
+  keep = []
+  if readout is not None:
+    W_out, b_out, w_att, b_att = [_f32c(t) for t in readout]
+    keep += [W_out, b_out, w_att, b_att]
+    score = torch.empty((B, W_out.shape[0]), device=dev, dtype=torch.float32)
+    d.W_out, d.b_out, d.w_att, d.b_att = (W_out.data_ptr(), b_out.data_ptr(), w_att.data_ptr(),
+                                          b_att.data_ptr())
+    d.score, d.P = score.data_ptr(), W_out.shape[0]
+    if mask is not None:
+      mask = (mask != 0).to(torch.uint8).contiguous()
+      d.mask = mask.data_ptr()
+  for i, v in enumerate(dins):
+    d.Din[i] = int(v)
+  d.num_layers, d.Kw, d.write_pad = len(dins), int(w_hi.shape[1]), int(bool(write_pad))
+  d.B, d.N, d.E1, d.K, d.S, d.H, d.relu = B, N, E1, K, int(S), int(H), int(bool(relu))
+  with torch.cuda.device(dev):
+    _lib.check(_lib.load().lnb_spectral_stack_forward(_stream(Q), ctypes.byref(d)),
+               'lnb_spectral_stack_forward')
+  return state, score
 
 
 def ritz_rowmap(gext, K):

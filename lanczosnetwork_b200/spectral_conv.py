@@ -74,6 +74,21 @@ class WeightCache(object):
       self._store[key] = hit
     return hit[1], hit[2], hit[3]
 
+  def split_conv_stack(self, name, weights, biases, kw):
+    """Stacked convolution weights of consecutive layers for the one-kernel stack: rows
+    [l*H, (l+1)*H) = layer l's filter weight, columns zero-padded to kw; returns
+    (w_hi, w_lo, bias [L*H])."""
+    dev = weights[0].device
+    key = (name, dev.index)
+    tag = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases)) + (kw,)
+    hit = self._store.get(key)
+    if hit is None or hit[0] != tag:
+      rows = [torch.nn.functional.pad(w.detach(), (0, kw - w.shape[1])) for w in weights]
+      hi, lo = ops.split_tf32(torch.cat(rows, dim=0).contiguous())
+      hit = (tag, hi, lo, torch.cat([b.detach() for b in biases], dim=0).contiguous())
+      self._store[key] = hit
+    return hit[1], hit[2], hit[3]
+
   def clear(self):
     self._store.clear()
 
@@ -101,7 +116,7 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
   and every MLP stage runs for ALL layers in one launch: stage 0 as a dense layer with the
   layers' first weights stacked along the output dimension, stages 1-3 as block-diagonal
   (grouped) dense layers.  mlp_layers: list over layers of [(name, W, b) x 4] or None for the
-  plain-power filter.  Returns (list over layers of [B,K,S] tensors or None, table [B,K,S])."""
+  plain-power filter.  Returns (coeff [layers,B,K,S] or None, table [B,K,S])."""
   B, K = D.shape
   S = len(powers)
   table = ops.ritz_power_table(D, powers)            # [B,K,S]
@@ -118,7 +133,7 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
     if gext is not None:
       rowmap, nrows = ops.ritz_rowmap(gext, K)
     coeff = ops.ritz_filter_mlp(flat, w_hi, w_lo, bias_all, nl, rowmap, nrows).reshape(nl, B, K, S)
-    return [coeff[l] for l in range(nl)], table
+    return coeff, table
   if S % 4 == 0 and hd % 4 == 0:
     h = flat
     for stage in range(4):
@@ -130,14 +145,14 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
       else:
         h = ops.linear_tf32x3_grouped(h, w_hi, w_lo, bias, nl, stage < 3)
     coeff = h.reshape(B, K, nl, S).permute(2, 0, 1, 3).contiguous()     # [layers,B,K,S]
-    return [coeff[l] for l in range(nl)], table
+    return coeff, table
   out = []
   for params in mlp_layers:
     h = flat
     for i, (name, w, b) in enumerate(params):
       h = dense(h, w, b, i < len(params) - 1, cache, name)
     out.append(h.reshape(B, K, S))
-  return out, table
+  return torch.stack(out, dim=0), table
 
 
 class GraphContext(object):

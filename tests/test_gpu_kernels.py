@@ -447,3 +447,46 @@ def test_lanczos_resident_operator_vs_oracle(N, K, B):
   eQ = np.abs(o32['Q'].numpy() - o64['Q'].numpy()).max()
   assert np.abs(out['T'].cpu().numpy() - o64['T'].numpy()).max() <= max(4 * eT, 2e-5)
   assert np.abs(out['Q'].cpu().numpy() - o64['Q'].numpy()).max() <= max(4 * eQ, 2e-4)
+
+
+def test_spectral_stack_equals_layer_by_layer():
+  """The one-kernel stack (state kept in shared memory across layers, embedding gather in front,
+  readout behind) reproduces the per-layer fused kernel bit-for-bit and the readout kernel to
+  rounding."""
+  from lanczosnetwork_b200 import spectral_conv as sc
+  B, N, K, S, E1, H, L = 37, 26, 20, 8, 7, 128, 3
+  X, Lop, V, coeff, W, bias = _conv_case(B, N, 64, H, K, S, E1, 4242, True)
+  d = dev()
+  g = torch.Generator().manual_seed(3)
+  ids = torch.randint(0, 70, (B, N), generator=g)
+  emb = torch.randn(70, 64, generator=g)
+  dins = [64, H, H]
+  Ws = [(torch.randn(H, (S + E1) * dd, generator=g) / np.sqrt((S + E1) * dd)).to(d) for dd in dins]
+  bs = [torch.randn(H, generator=g).to(d) for _ in dins]
+  coeffs = torch.randn(L, B, K, S, generator=g).to(d)
+  Lg, Vg = Lop.to(d), V.to(d)
+  prep = ops().graph_prepare(Lg, Vg)
+  # layer by layer through the single-layer entry point
+  state = emb.to(d)[ids.to(d)]
+  for l in range(L):
+    hi, lo = ops().split_tf32(Ws[l])
+    state = ops().spectral_conv_fused(state, Vg, coeffs[l], prep, hi, lo, bs[l], True, write_pad=True)
+  cache = sc.WeightCache()
+  kw = (S + E1) * H
+  w_hi, w_lo, ball = cache.split_conv_stack('t', Ws, bs, kw)
+  mask = (torch.arange(N)[None, :] < torch.randint(1, N + 1, (B, 1), generator=g)).to(torch.uint8).to(d)
+  W_out, b_out = torch.randn(16, H, generator=g).to(d) * 0.1, torch.randn(16, generator=g).to(d)
+  w_att, b_att = torch.randn(H, generator=g).to(d) * 0.1, torch.randn(1, generator=g).to(d)
+  st, score = ops().spectral_stack_forward(prep, Vg, w_hi, w_lo, ball, dins, H, S, coeff=coeffs,
+                                           coeff_stride=coeffs.stride(0), node_ids=ids.to(d),
+                                           emb=emb.to(d), want_state=True,
+                                           readout=(W_out, b_out, w_att, b_att), mask=mask)
+  assert torch.equal(st, state)
+  ref = ops().readout(state, W_out, b_out, w_att, b_att, mask)
+  torch.testing.assert_close(score, ref, rtol=1e-5, atol=1e-6)
+  # no mask: mean over all N nodes, padded ones included
+  _, score2 = ops().spectral_stack_forward(prep, Vg, w_hi, w_lo, ball, dins, H, S, coeff=coeffs,
+                                           coeff_stride=coeffs.stride(0), X=emb.to(d)[ids.to(d)],
+                                           readout=(W_out, b_out, w_att, b_att), mask=None)
+  torch.testing.assert_close(score2, ops().readout(state, W_out, b_out, w_att, b_att, None),
+                             rtol=1e-5, atol=1e-6)
