@@ -76,14 +76,14 @@ struct MlpChainPolicy {
   }
   __device__ __forceinline__ void pre_epilogue(int) {}
   __device__ __forceinline__ void post_epilogue(int) {}
-  __device__ __forceinline__ void store(int sub, int col, float (&x)[32]) {
+  __device__ __forceinline__ void store(int sub, int col, float (&x)[tcg::EW]) {
     const int stage = sub & 3;
     const float* bias = p.bias_all + row_off(p, sub);
     if (stage < 3) {
       if (col >= p.Hd) return;
       float4* o4 = reinterpret_cast<float4*>(Act + (size_t)r * AP + col);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < tcg::EW / 4; ++q) {
         float y[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -97,7 +97,7 @@ struct MlpChainPolicy {
     if (src < 0 || col >= p.S) return;
     float* dst = p.coeff + ((int64_t)(sub >> 2) * p.Rall + src) * p.S;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < tcg::EW; ++j)
       if (col + j < p.S) dst[col + j] = x[j] + __ldg(bias + col + j);
   }
 };

@@ -80,7 +80,7 @@ struct RowLoadPolicy {
   }
   __device__ __forceinline__ void pre_epilogue(int) {}
   __device__ __forceinline__ void post_epilogue(int) {}
-  __device__ __forceinline__ void store(int sub, int col, const float (&x)[32]) {
+  __device__ __forceinline__ void store(int sub, int col, const float (&x)[tcg::EW]) {
     const int left = p.N - (sub % tiles_per_group(p)) * tcg::BN;
     const int w0 = w_row0(p, sub);
     tcg::store_row_chunk(row_ok ? p.C + (int64_t)row * ldc + w0 : nullptr,

@@ -457,6 +457,7 @@ struct SpectralPolicy {
 #pragma unroll 2
     for (int t = 0; t < ts; ++t) {
       const float a = ev[t * RMAX];
+      if (a == 0.f) continue;                        // zero fill up to the tile's longest row
       const int i = ei[t * RMAX];
       const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
 #pragma unroll
@@ -479,6 +480,7 @@ struct SpectralPolicy {
           a = __ldg(p.ell_val + off0 + (int64_t)t * N);
           i = nb + __ldg(p.ell_idx + off0 + (int64_t)t * N);
         }
+        if (a == 0.f) continue;
         const float4* x4 = reinterpret_cast<const float4*>(xs + (size_t)i * XP);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -531,14 +533,14 @@ struct SpectralPolicy {
     tcg::producers_sync();
   }
 
-  __device__ __forceinline__ void store(int sub, int col, float (&x)[32]) {
+  __device__ __forceinline__ void store(int sub, int col, float (&x)[tcg::EW]) {
     if (col >= H) return;
     if ((sub & 1) == 0) {
       // drain Z[row, col:col+32] to shared memory (overwrites U, which is dead by now)
       if (r < tb->Ztot) {
         float4* z4 = reinterpret_cast<float4*>(UZ + (size_t)r * XP + col);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < tcg::EW / 4; ++q)
           z4[q] = make_float4(x[4 * q + 0], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
       }
       return;
@@ -548,18 +550,26 @@ struct SpectralPolicy {
     const bool relu = p.relu != 0;
     const float* bias = p.bias ? p.bias + (sub >> 1) * H : nullptr;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < tcg::EW / 4; ++q) {
       float y[4] = {x[4 * q + 0], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]};
       if (S > 0) {                                  // + (V Z)[row, col + 4q ..], from pre_epilogue()
         const float4 t = o4[q];
         y[0] += t.x; y[1] += t.y; y[2] += t.z; y[3] += t.w;
       }
+      if (col + 4 * q + 3 < H) {
+        if (bias) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + q);
+          y[0] += b4.x; y[1] += b4.y; y[2] += b4.z; y[3] += b4.w;
+        }
+        if (relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = col + 4 * q + u;
-        if (c < H) {
-          if (bias) y[u] += __ldg(bias + c);
-          if (relu) y[u] = fmaxf(y[u], 0.f);
+        for (int u = 0; u < 4; ++u) {
+          const int c = col + 4 * q + u;
+          if (c < H) {
+            if (bias) y[u] += __ldg(bias + c);
+            if (relu) y[u] = fmaxf(y[u], 0.f);
+          }
         }
       }
       o4[q] = make_float4(y[0], y[1], y[2], y[3]);   // finished row chunk = next layer's X row
@@ -699,6 +709,10 @@ static int launch_stack(lnb_stream_t stream, const lnb_spectral_stack& d, const 
                  "layers Din==H, K%%4==0, K<=%d, H%%4==0, H<=128, E1<=%d)", who, d.N, d.K, d.H, d.E1,
                  KMAX, EMAX);
     return LNB_ERR_UNSUPPORTED;
+  }
+  if (d.bias && (reinterpret_cast<uintptr_t>(d.bias) & 15)) {
+    lnb::set_err("%s: bias must be 16-byte aligned", who);
+    return LNB_ERR_ARG;
   }
   if (d.B == 0) return LNB_OK;
   size_t smem = tcg::core_smem(SpectralPolicy::kStagesB) + 1024 + SpectralPolicy::smem_fixed(dmax, d.K, d.H);

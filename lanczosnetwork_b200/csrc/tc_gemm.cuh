@@ -26,6 +26,7 @@ constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int NGROUPS = 3;                         // producer groups == TMEM A stages (kb % 3)
 constexpr int TILE_B_BYTES = BN * BK * 4;          // 16 KB per hi or lo tile
 constexpr int STAGE_B_BYTES = 2 * TILE_B_BYTES;    // [W_hi tile | W_lo tile] = 256 rows x 128 B
+constexpr int EW = 16;                             // epilogue unit: 16 accumulator columns
 constexpr int TMEM_COLS = 512;
 constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;   // A stage s: COL_A + 64 s (hi), +32 (lo)
 constexpr int PRODUCER_THREADS = 128 * NGROUPS;
@@ -61,7 +62,8 @@ __device__ __forceinline__ Core carve(uint8_t* base, int stages_b) {
 }
 
 // Optional phase timers (profiling aid): when a buffer is registered with lnb_debug_set_prof,
-// thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*8 + phase]:
+// thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*16 + phase]
+// (slots 8 / 9: k-loop / accumulator wait of odd sub-steps):
 //   0 staging issue  1 staging wait  2 U = V^T X   (policy)   3 k-loop  4 pre_epilogue
 //   5 wait for the accumulator  6 tcgen05.ld  7 epilogue store
 __device__ unsigned long long* g_prof = nullptr;
@@ -70,7 +72,7 @@ struct PhaseTimer {          // thread 0 of the CTA only; no-op unless a buffer 
   unsigned long long* buf;
   long long t0;
   __device__ __forceinline__ void start(int cta, int tid) {
-    buf = (tid == 0 && g_prof) ? g_prof + cta * 8 : nullptr;
+    buf = (tid == 0 && g_prof) ? g_prof + cta * 16 : nullptr;
     if (buf) t0 = clock64();
   }
   __device__ __forceinline__ void lap(int slot) {
@@ -96,7 +98,7 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
 //   void produce(int sub, int kb, float (&v)[32])         the 32 A values of this thread's row
 //   void pre_epilogue(int sub)                            after the step's last produce()
 //   void post_epilogue(int sub)                           after the step's last store()
-//   void store(int sub, int col, float (&x)[32])          accumulator columns [col, col+32) of
+//   void store(int sub, int col, float (&x)[EW])          accumulator columns [col, col+EW) of
 //                                                         this thread's row (main + corr summed)
 template <class Policy>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -173,24 +175,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
         __syncwarp();
         if (lane == 0) tc05::mbar_arrive(&c.a_full[grp]);
       }
-      tm.lap(3);
+      tm.lap((sub & 1) ? 8 : 3);
       pol.pre_epilogue(sub);
       tm.lap(4);
-      // ---- epilogue: 32-column chunk cc belongs to group cc % NGROUPS ----
+      // ---- epilogue: 16-column unit cc belongs to group cc % NGROUPS ----
       tc05::mbar_wait(c.acc_full, (uint32_t)it & 1u);
       tc05::fence_after_thread_sync();
-      tm.lap(5);
+      tm.lap((sub & 1) ? 9 : 5);
 #pragma unroll 1
-      for (int cc = grp; cc < BN / 32; cc += NGROUPS) {
-        const int col = cc * 32;
-        uint32_t vm[32], vc[32];
-        tc05::tmem_ld_32x32(lane_addr + COL_MAIN + col, vm);
-        tc05::tmem_ld_32x32(lane_addr + COL_CORR + col, vc);
+      for (int cc = grp; cc < BN / EW; cc += NGROUPS) {   // 8 units over 3 groups: 3 / 3 / 2
+        const int col = cc * EW;
+        uint32_t vm[EW], vc[EW];
+        tc05::tmem_ld_32x16(lane_addr + COL_MAIN + col, vm);
+        tc05::tmem_ld_32x16(lane_addr + COL_CORR + col, vc);
         tc05::tmem_wait_ld();
         tm.lap(6);
-        float x[32];
+        float x[EW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+        for (int j = 0; j < EW; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
         pol.store(sub, col, x);
         tm.lap(7);
       }
@@ -272,13 +274,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   }
 }
 
-// Epilogue helper: bias / ReLU / bounds-checked store of 32 accumulator columns of one row.
+// Epilogue helper: bias / ReLU / bounds-checked store of EW accumulator columns of one row.
 __device__ __forceinline__ void store_row_chunk(float* orow, int ncols, const float* bias, bool relu,
-                                                int col, const float (&x)[32]) {
+                                                int col, const float (&x)[EW]) {
   if (orow == nullptr || col >= ncols) return;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(orow + col) & 15) == 0;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < EW; j += 4) {
     float o[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {

@@ -203,5 +203,14 @@ def test_ada_full_qm8_config_vs_oracle():
               mask=_t(batch['node_mask']).to(dev()))
   lz = mod.last_lanczos
   assert np.array_equal(lz['idx'].cpu().numpy(), aux['idx'].numpy())
-  np.testing.assert_allclose(lz['T'].cpu().numpy(), aux['T'].numpy(), atol=5e-5)
+  # the learned Laplacian agrees with the oracle's to summation-order rounding ...
+  from lanczosnetwork_b200 import ops
+  state = ops.embedding_rows(_t(batch['node_feat']).to(dev()).long(), mod.embedding.weight)
+  Le = ops.gaussian_laplacian(state, _t(batch['L']).to(dev()).float().contiguous()).cpu()
+  np.testing.assert_allclose(Le.numpy(), aux['Le'].numpy(), atol=2e-5)
+  # ... and the tridiagonalisation is compared on the SAME operator: Lanczos amplifies a 1e-5
+  # operator perturbation to 1e-3 in the late coefficients, which made the end-to-end T
+  # comparison depend on the host CPU's summation order in the oracle
+  lz_ref = orc.lanczos_tridiagonalise(Le, _t(batch['node_mask']), q1[:, :, 0], spec['K'])
+  np.testing.assert_allclose(lz['T'].cpu().numpy(), lz_ref['T'].numpy(), atol=5e-5)
   np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4)
