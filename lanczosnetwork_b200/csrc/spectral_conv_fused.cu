@@ -105,47 +105,57 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
 // Ritz-row counts and, for every graph i, the end of the tile that would start at i (a window
 // of <= 32 graphs); sequential part: one thread follows that jump table (T hops, not B steps).
 __global__ void __launch_bounds__(1024)
-tile_assign_kernel(const int32_t* __restrict__ gext, int B, int32_t* __restrict__ tiles,
-                   int32_t* __restrict__ scratch /* [3 * B] */) {
-  __shared__ int warp_n[32], warp_k[32];
-  __shared__ int run_n, run_k;
+tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __restrict__ tiles,
+                   int32_t* __restrict__ scratch /* [3 * B] */, int32_t* __restrict__ rowmap,
+                   int32_t* __restrict__ nrows) {
+  __shared__ int warp_n[32], warp_k[32], warp_r[32];
+  __shared__ int run_n, run_k, run_r;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int32_t* PN = scratch;            // inclusive prefix of n_eff
   int32_t* PK = scratch + B;        // inclusive prefix of ceil4(k_eff)
   int32_t* NX = scratch + 2 * B;    // end (exclusive) of the tile starting at i
-  if (tid == 0) { run_n = 0; run_k = 0; }
+  if (tid == 0) { run_n = 0; run_k = 0; run_r = 0; }
   __syncthreads();
   for (int b0 = 0; b0 < B; b0 += 1024) {
     const int b = b0 + tid;
     const int n = (b < B) ? gext[b * 2] : 0;
+    const int kr = (b < B) ? min(gext[b * 2 + 1], K) : 0;      // rows of the compact Ritz row list
     const int k = (b < B) ? ((gext[b * 2 + 1] + 3) & ~3) : 0;
-    int in = n, ik = k;
+    int in = n, ik = k, ir = kr;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int tn = __shfl_up_sync(0xffffffffu, in, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
-      if (lane >= o) { in += tn; ik += tk; }
+      const int tr = __shfl_up_sync(0xffffffffu, ir, o);
+      if (lane >= o) { in += tn; ik += tk; ir += tr; }
     }
-    if (lane == 31) { warp_n[warp] = in; warp_k[warp] = ik; }
+    if (lane == 31) { warp_n[warp] = in; warp_k[warp] = ik; warp_r[warp] = ir; }
     __syncthreads();
     if (warp == 0) {
-      int wn = warp_n[lane], wk = warp_k[lane], sn = wn, sk = wk;
+      int wn = warp_n[lane], wk = warp_k[lane], wr = warp_r[lane], sn = wn, sk = wk, sr = wr;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int tn = __shfl_up_sync(0xffffffffu, sn, o), tk = __shfl_up_sync(0xffffffffu, sk, o);
-        if (lane >= o) { sn += tn; sk += tk; }
+        const int tr = __shfl_up_sync(0xffffffffu, sr, o);
+        if (lane >= o) { sn += tn; sk += tk; sr += tr; }
       }
       warp_n[lane] = sn - wn;
       warp_k[lane] = sk - wk;
+      warp_r[lane] = sr - wr;
     }
     __syncthreads();
     if (b < B) {
       PN[b] = run_n + warp_n[warp] + in;
       PK[b] = run_k + warp_k[warp] + ik;
+      if (rowmap) {                       // {b*K + k : k < k_eff(b)}, see lnb_ritz_rowmap
+        const int base = run_r + warp_r[warp] + ir - kr;
+        for (int i = 0; i < kr; ++i) rowmap[base + i] = b * K + i;
+      }
     }
     __syncthreads();
-    if (tid == 1023) { run_n += warp_n[31] + in; run_k += warp_k[31] + ik; }
+    if (tid == 1023) { run_n += warp_n[31] + in; run_k += warp_k[31] + ik; run_r += warp_r[31] + ir; }
     __syncthreads();
   }
+  if (tid == 0 && nrows) nrows[0] = run_r;
   __threadfence_block();
   for (int i = tid; i < B; i += 1024) {
     const int pn0 = i ? PN[i - 1] : 0, pk0 = i ? PK[i - 1] : 0;
@@ -403,7 +413,7 @@ struct SpectralPolicy {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
       const float* xs = Xs + (size_t)nb * XP + 4 * dq;
       const float* qs = Qs + (size_t)nb * K + k0;
-#pragma unroll 2
+#pragma unroll 4
       for (int nn = 0; nn < n_g; ++nn) {
         const float4 x4 = *reinterpret_cast<const float4*>(xs + (size_t)nn * XP);
         const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)nn * K);
@@ -514,15 +524,23 @@ struct SpectralPolicy {
       const float* z = UZ + (size_t)tb->kbase[g] * XP + 4 * hq;
       const float* q0 = Qs + (size_t)r0 * K;
       const int r1 = (n0 + 1 < n_g) ? 1 : 0, r2 = (n0 + 2 < n_g) ? 2 : 0, r3 = (n0 + 3 < n_g) ? 3 : 0;
-#pragma unroll 2
-      for (int k = 0; k < k_g; ++k) {
-        const float4 z4 = *reinterpret_cast<const float4*>(z + (size_t)k * XP);
-        const float av[4] = {q0[k], q0[r1 * K + k], q0[r2 * K + k], q0[r3 * K + k]};
-        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+      // four Ritz indices per trip: Q columns and Z rows in [k_eff, ceil4(k_eff)) are zero
+      for (int k = 0; k < k_g; k += 4) {
+        const float4 a0 = *reinterpret_cast<const float4*>(q0 + k);
+        const float4 a1 = *reinterpret_cast<const float4*>(q0 + r1 * K + k);
+        const float4 a2 = *reinterpret_cast<const float4*>(q0 + r2 * K + k);
+        const float4 a3 = *reinterpret_cast<const float4*>(q0 + r3 * K + k);
+        const float av[4][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w},
+                                {a2.x, a2.y, a2.z, a2.w}, {a3.x, a3.y, a3.z, a3.w}};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 z4 = *reinterpret_cast<const float4*>(z + (size_t)(k + kk) * XP);
+          const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], zv[j], acc[i][j]);
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i][kk], zv[j], acc[i][j]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -675,14 +693,16 @@ int lnb_debug_set_prof(unsigned long long* buf) {
 
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
                       int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* gext,
-                      int32_t* tiles /* [4*B + 2]: B + 2 tile table followed by 3*B scratch */) {
+                      int32_t* tiles /* [4*B + 2]: B + 2 tile table followed by 3*B scratch */,
+                      int32_t* rowmap, int32_t* nrows) {
   LNB_REQUIRE(L && Q && ell_val && ell_idx && ell_max && gext && tiles, "graph_prepare: null pointer");
+  LNB_REQUIRE((rowmap == nullptr) == (nrows == nullptr), "graph_prepare: rowmap and nrows go together");
   LNB_REQUIRE(B >= 0 && N >= 1 && N <= 255 && E1 >= 1 && E1 <= EMAX && K >= 1,
               "graph_prepare: bad dims B=%d N=%d E1=%d K=%d", B, N, E1, K);
   if (B == 0) return LNB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   graph_prepare_kernel<<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
-  tile_assign_kernel<<<1, 1024, 0, s>>>(gext, B, tiles, tiles + B + 2);
+  tile_assign_kernel<<<1, 1024, 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
   lnb::count_launch(2);
   return lnb::finish_launch("graph_prepare");
 }

@@ -217,8 +217,20 @@ class SpectralNetBase(nn.Module):
     coeffs = table = None
     if S > 0:
       mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
-      gext = ctx.prep()[3] if (mlp is not None and stack_ok and first == 0) else None
-      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache, gext)
+      # the power table does not depend on graph_prepare: fork it onto a side stream so the
+      # two run concurrently (also inside the captured graph)
+      cur = torch.cuda.current_stream(D.device)
+      side = self.__dict__.setdefault('_side_streams', {}).get(D.device.index)
+      if side is None:
+        side = self._side_streams[D.device.index] = torch.cuda.Stream(device=D.device)
+      side.wait_stream(cur)
+      with torch.cuda.stream(side):
+        table = ops.ritz_power_table(D, self.long_diffusion_dist)
+      table.record_stream(cur)
+      gext = ctx.prep() if (mlp is not None and stack_ok and first == 0) else None
+      cur.wait_stream(side)
+      coeffs, table = ritz_filter_coefficients(D, self.long_diffusion_dist, mlp, self._wcache, gext,
+                                               table=table)
 
     def layer_coeff(t):
       if S == 0:

@@ -120,10 +120,17 @@ def linear_tf32x3_grouped(x, w_hi, w_lo, bias, groups, relu=False):
   return out
 
 
+class GraphPrep(tuple):
+  """(ell_val, ell_idx, ell_max, gext, tiles) plus the compact Ritz row list of the same pass
+  (attributes rowmap [B*K] int32, nrows [1] int32; see ritz_rowmap)."""
+  rowmap = None
+  nrows = None
+
+
 def graph_prepare(L, Q):
   """Per-forward compression of the dense operators L [B,N,N,E1] (ELL rows), the real extents
-  of every graph and the packed-tile assignment for the fused convolution kernel.
-  Returns (ell_val, ell_idx, ell_max, gext, tiles)."""
+  of every graph, the packed-tile assignment for the fused convolution kernel and the compact
+  list of non-zero Ritz rows.  Returns GraphPrep(ell_val, ell_idx, ell_max, gext, tiles)."""
   _need_cuda(L, Q)
   L, Q = _f32c(L), _f32c(Q)
   B, N, _, E1 = L.shape
@@ -134,11 +141,16 @@ def graph_prepare(L, Q):
   ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
   gext = torch.empty((B, 2), device=dev, dtype=torch.int32)
   tiles = torch.empty((4 * B + 2,), device=dev, dtype=torch.int32)   # tile table + scratch
+  rowmap = torch.empty((B * K,), device=dev, dtype=torch.int32)
+  nrows = torch.empty((1,), device=dev, dtype=torch.int32)
   with torch.cuda.device(dev):
     _lib.check(_lib.load().lnb_graph_prepare(_stream(L), _ptr(L), _ptr(Q), B, N, E1, K,
                                              _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),
-                                             _ptr(gext), _ptr(tiles)), 'lnb_graph_prepare')
-  return ell_val, ell_idx, ell_max, gext, tiles
+                                             _ptr(gext), _ptr(tiles), _ptr(rowmap), _ptr(nrows)),
+               'lnb_graph_prepare')
+  prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
+  prep.rowmap, prep.nrows = rowmap, nrows
+  return prep
 
 
 def fused_conv_supported(N, Din, K, H, n_short, dense_filter, S=8, E1=7):

@@ -110,7 +110,7 @@ def dense(x2d, weight, bias, relu, cache, name):
   return out
 
 
-def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
+def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None, table=None):
   """Per-layer multi-scale coefficients of the Ritz values (model/lanczos_net.py:109-113,
   146-149).  The MLP input does not depend on the layer state, so the power table is built once
   and every MLP stage runs for ALL layers in one launch: stage 0 as a dense layer with the
@@ -119,7 +119,8 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
   plain-power filter.  Returns (coeff [layers,B,K,S] or None, table [B,K,S])."""
   B, K = D.shape
   S = len(powers)
-  table = ops.ritz_power_table(D, powers)            # [B,K,S]
+  if table is None:
+    table = ops.ritz_power_table(D, powers)          # [B,K,S]
   if mlp_layers is None:
     return None, table
   nl = len(mlp_layers)
@@ -130,7 +131,9 @@ def ritz_filter_coefficients(D, powers, mlp_layers, cache, gext=None):
     # extents of graph_prepare only the rows of non-zero Ritz vectors are evaluated
     w_hi, w_lo, bias_all = cache.split_mlp_chain('spectral_filter.chain', mlp_layers)
     rowmap = nrows = None
-    if gext is not None:
+    if isinstance(gext, ops.GraphPrep):              # row list came with graph_prepare
+      rowmap, nrows = gext.rowmap, gext.nrows
+    elif gext is not None:
       rowmap, nrows = ops.ritz_rowmap(gext, K)
     coeff = ops.ritz_filter_mlp(flat, w_hi, w_lo, bias_all, nl, rowmap, nrows).reshape(nl, B, K, S)
     return coeff, table
