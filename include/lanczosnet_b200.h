@@ -125,8 +125,8 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
  * bias + l*H and coeff + l*coeff_layer_stride.  Input: X [B,N,Din[0]] or node_ids [B,N] +
  * emb_table [emb_rows, Din[0]] (model/lanczos_net.py:154).  Outputs: out_state [B,N,H] (may be
  * NULL) and / or score [B,P] from the fused readout (model/lanczos_net.py:185-194; mask may be
- * NULL = mean over all N nodes).  Same shape limits as lnb_spectral_conv_fused, plus
- * Din[l>0] == H and num_layers <= 8.
+ * NULL = mean over all N nodes; P <= 48).  Same shape limits as lnb_spectral_conv_fused, plus
+ * Din[l>0] == H, num_layers <= 8 and a 16-byte aligned bias.
  * ------------------------------------------------------------------------------------- */
 typedef struct lnb_spectral_stack {
   const float* X; const int64_t* node_ids; const float* emb_table;

@@ -332,13 +332,18 @@ struct SpectralPolicy {
     tcg::producers_sync();
     const int gs = tb->gs, Rtot = tb->Rtot;
     // ---- phase A: asynchronous copies of the real rows of X and Q (one warp per row) --------
-    for (int row = warp; row < Rtot; row += NW) {
+    int64_t my_id = 0;                           // lane j: embedding id of this warp's j-th row
+    if (!p.X && warp + lane * NW < Rtot) {
+      const int row = warp + lane * NW;
+      my_id = __ldg(p.node_ids + (int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row]);
+    }
+    for (int row = warp, j = 0; row < Rtot; row += NW, ++j) {
       const int64_t src_row = (int64_t)(gs + tb->row_g[row]) * N + tb->row_n[row];
       const float* xsrc;
       if (p.X) {
         xsrc = p.X + src_row * Din;
       } else {                                  // embedding rows (model/lanczos_net.py:154)
-        int64_t id = __ldg(p.node_ids + src_row);
+        int64_t id = __shfl_sync(0xffffffffu, my_id, j);
         id = id < 0 ? 0 : (id >= p.emb_rows ? p.emb_rows - 1 : id);
         xsrc = p.emb + id * Din;
       }
@@ -637,13 +642,13 @@ struct SpectralPolicy {
   // per node, masked mean over the nodes of each graph.  Rows of padded nodes are the constant
   // act(b_last); they count only where the mask says so (or when there is no mask).
   __device__ void readout(const float* bias_last) {
-    const int P = p.P, P1 = p.P + 1, HP = H + 1;
-    float* Wr = UZ;                                  // [(P+1)][HP]  (Z is dead by now)
-    float* Yr = Wr + (size_t)P1 * HP;                // [RMAX + 1][P1]  per-row gated outputs; last = pad row
-    float* cx = Yr + (size_t)(RMAX + 1) * P1;        // [H] constant padded-node state
-    for (int e = tid; e < P1 * H; e += tcg::PRODUCER_THREADS) {
+    const int P = p.P, P1 = p.P + 1, PQ = (P1 + 3) >> 2, HP = H + 4;
+    float* Wr = UZ;                                  // [4 PQ][HP]  W_out rows, w_att, zero rows (Z is dead)
+    float* Yr = Wr + (size_t)4 * PQ * HP;            // [RMAX + 1][P1]  per-row outputs; last = pad row
+    float* cx = Yr + (size_t)(RMAX + 1) * P1 + ((4 - ((RMAX + 1) * P1 & 3)) & 3);   // [H], 16 B aligned
+    for (int e = tid; e < 4 * PQ * H; e += tcg::PRODUCER_THREADS) {
       const int o = e / H, h = e - o * H;
-      Wr[o * HP + h] = (o < P) ? __ldg(p.W_out + o * H + h) : __ldg(p.w_att + h);
+      Wr[o * HP + h] = (o < P) ? __ldg(p.W_out + o * H + h) : (o == P ? __ldg(p.w_att + h) : 0.f);
     }
     for (int h = tid; h < H; h += tcg::PRODUCER_THREADS) {
       float t = bias_last ? __ldg(bias_last + h) : 0.f;
@@ -651,15 +656,28 @@ struct SpectralPolicy {
     }
     tcg::producers_sync();
     const int Rtot = tb->Rtot;
-    // one thread per (row, output); row RMAX stands for the constant padded-node row
-    for (int e = tid; e < (Rtot + 1) * P1; e += tcg::PRODUCER_THREADS) {
-      const int rr = e / P1, o = e - rr * P1;
-      const float* x = (rr < Rtot) ? Xs + (size_t)rr * XP : cx;
-      const float* w = Wr + o * HP;
-      float acc = 0.f;
-      for (int h = 0; h < H; ++h) acc = fmaf(x[h], w[h], acc);
-      acc += (o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att);
-      Yr[(rr < Rtot ? rr : RMAX) * P1 + o] = acc;
+    // one thread per (row, 4 outputs); row Rtot stands for the constant padded-node row
+    for (int e = tid; e < (Rtot + 1) * PQ; e += tcg::PRODUCER_THREADS) {
+      const int rr = e / PQ, oq = e - rr * PQ;
+      const float4* x4 = reinterpret_cast<const float4*>((rr < Rtot) ? Xs + (size_t)rr * XP : cx);
+      const float4* w4 = reinterpret_cast<const float4*>(Wr + (size_t)4 * oq * HP);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int h4 = 0; h4 < H / 4; ++h4) {
+        const float4 x = x4[h4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = w4[j * (HP / 4) + h4];
+          acc[j] = fmaf(x.x, w.x, acc[j]); acc[j] = fmaf(x.y, w.y, acc[j]);
+          acc[j] = fmaf(x.z, w.z, acc[j]); acc[j] = fmaf(x.w, w.w, acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = 4 * oq + j;
+        if (o < P1)
+          Yr[(rr < Rtot ? rr : RMAX) * P1 + o] = acc[j] + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+      }
     }
     tcg::producers_sync();
     for (int e = tid; e < tb->ng * P; e += tcg::PRODUCER_THREADS) {
@@ -715,8 +733,8 @@ static int launch_stack(lnb_stream_t stream, const lnb_spectral_stack& d, const 
   LNB_REQUIRE(d.B >= 0 && d.N >= 1 && d.E1 >= 1 && d.K >= 1 && d.S >= 0 && d.H >= 1 &&
                   d.num_layers >= 1 && d.num_layers <= SpectralPolicy::LMAX,
               "%s: bad dims", who);
-  LNB_REQUIRE(!d.score || (d.W_out && d.b_out && d.w_att && d.b_att && d.P >= 1 && d.P <= 64),
-              "%s: readout needs W_out, b_out, w_att, b_att and 1 <= P <= 64", who);
+  LNB_REQUIRE(!d.score || (d.W_out && d.b_out && d.w_att && d.b_att && d.P >= 1 && d.P <= 48),
+              "%s: readout needs W_out, b_out, w_att, b_att and 1 <= P <= 48", who);
   int dmax = 0;
   bool ok = d.N <= RMAX && d.K <= KMAX && d.K % 4 == 0 && d.H % 4 == 0 && d.H <= tcg::BN && d.E1 <= EMAX;
   for (int l = 0; l < d.num_layers; ++l) {

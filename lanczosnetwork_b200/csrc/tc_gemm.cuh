@@ -63,7 +63,7 @@ __device__ __forceinline__ Core carve(uint8_t* base, int stages_b) {
 
 // Optional phase timers (profiling aid): when a buffer is registered with lnb_debug_set_prof,
 // thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*16 + phase]
-// (slots 8 / 9: k-loop / accumulator wait of odd sub-steps):
+// (slots 8 / 9: k-loop / accumulator wait of odd sub-steps, 10: post_epilogue):
 //   0 staging issue  1 staging wait  2 U = V^T X   (policy)   3 k-loop  4 pre_epilogue
 //   5 wait for the accumulator  6 tcgen05.ld  7 epilogue store
 __device__ unsigned long long* g_prof = nullptr;
@@ -116,6 +116,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int nsteps = Policy::num_steps(p, cta, ncta);
+  unsigned long long prof_ns0 = 0;                  // whole-CTA wall time / cycles (slots 11, 12)
+  long long prof_c0 = 0;
+  if (tid == 0 && g_prof) {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(prof_ns0));
+    prof_c0 = clock64();
+  }
 
   if (warp == TMA_WARP && lane == 0) {
     tc05::tma_prefetch_desc(&map_hi);
@@ -200,6 +206,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       __syncwarp();
       if (lane == 0) tc05::mbar_arrive(c.acc_empty);    // accumulators are free again
       pol.post_epilogue(sub);
+      tm.lap(10);
     }
   } else if (warp == TMA_WARP) {
     // ================================ TMA producer (W tiles) ==============================
@@ -271,6 +278,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   if (warp == MMA_WARP) {
     __syncwarp();
     tc05::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (tid == 0 && g_prof) {
+    unsigned long long ns1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+    atomicAdd(&g_prof[cta * 16 + 11], ns1 - prof_ns0);
+    atomicAdd(&g_prof[cta * 16 + 12], (unsigned long long)(clock64() - prof_c0));
+    g_prof[cta * 16 + 13] = prof_ns0;               // CTA start (ns), for launch skew
   }
 }
 

@@ -257,6 +257,14 @@ class SpectralNetBase(nn.Module):
     else:
       coeff, stride = table, 0
     head, att = self.filter[nl], self.att_func[0]
+    if head.weight.shape[0] > 48:                        # fused readout holds <= 48 outputs
+      state, _ = ops.spectral_stack_forward(
+          ctx.prep(), V, w_hi, w_lo, bias, [dims[t] for t in layers], H, S, coeff=coeff,
+          coeff_stride=stride, X=None if (node_ids is not None and first == 0) else state,
+          node_ids=node_ids if first == 0 else None,
+          emb=self.embedding.weight if (node_ids is not None and first == 0) else None,
+          want_state=True)
+      return self._readout(state, mask)
     _, score = ops.spectral_stack_forward(
         ctx.prep(), V, w_hi, w_lo, bias, [dims[t] for t in layers], H, S, coeff=coeff,
         coeff_stride=stride, X=None if (node_ids is not None and first == 0) else state,
