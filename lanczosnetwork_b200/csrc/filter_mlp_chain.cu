@@ -1,106 +1,312 @@
 // Ritz-value filter MLPs of ALL layers in one persistent tcgen05 kernel
 // (reference: model/lanczos_net.py:47-58 the per-layer Sequential, :109-113 its application to
-// the B*K rows of Ritz-value powers).  The four Linear stages of one (row tile, layer) item run
-// back to back as four accumulator lifetimes of the tc_gemm.cuh skeleton; the 128 x 128
-// activations stay in shared memory between stages (the previous epilogue writes bias + ReLU
-// output there, the next stage's producers read it as their A operand), so nothing but the
-// final [rows, S] coefficients touches HBM.  Only rows (graph, k) with k < k_eff(graph) are
-// evaluated: zero-padded Ritz pairs multiply zero Ritz vectors downstream (exact).
+// the B*K rows of Ritz-value powers).
+//
+// An item is (128-row tile, layer): four Linear stages S -> Hd -> Hd -> Hd -> S, each one
+// accumulator lifetime ("step") of 3xTF32 MMAs with the A operand in tensor memory.  The
+// activations NEVER leave tensor memory / registers: the epilogue of stage s reads the accumulator
+// (tcgen05.ld), applies bias + ReLU, splits into tf32 hi / lo and writes the result straight
+// into the A ring (tcgen05.st) as the k-blocks of stage s+1 -- output chunk cc of stage s IS
+// k-block cc of stage s+1 for the same thread (row <-> TMEM lane in both).
+//
+// Every CTA walks a contiguous range of items two at a time (A, B) with the steps interleaved
+// A0 B0 A1 B1 A2 B2 A3 B3: while the CUDA cores turn A.s into the operand of A.(s+1), the tensor
+// core runs B.s, so the MMA pipe only idles while an accumulator is drained to registers.
+// Only rows (graph, k) with k < k_eff(graph) are evaluated (rowmap): zero-padded Ritz pairs
+// multiply zero Ritz vectors downstream (exact).
+//
+// Warps: 0-11 workers (group g = warp / 4 owns k-block G when G % 3 == g, G = CTA-global k-block
+// count; lane quarter = warp % 4), 12 TMA (W tiles, 3-stage shared-memory ring), 13 MMA issue.
+// TMEM: [0,128) D_main, [128,256) D_corr, [256,512) A ring of 4 slots x (32 hi + 32 lo).
 #include "tc_gemm.cuh"
 
 namespace {
 
-struct MlpChainPolicy {
-  static constexpr int kStagesB = 3;
-  struct Params {
-    const float* table;     // [Rall, S]  powers of the Ritz values
-    const int32_t* rowmap;  // [Rall]     compact list of rows to evaluate (nullptr: all rows)
-    const int32_t* nrows;   // [1]        number of valid entries in rowmap (nullptr: Rall)
-    const float* bias_all;  // [L * (3*Hd + S)]
-    float* coeff;           // [L, Rall, S]
-    int Rall, L, S, Hd;
-    int dbg;
-  };
-  static __device__ __forceinline__ int rows(const Params& p) { return p.nrows ? __ldg(p.nrows) : p.Rall; }
-  static __device__ __forceinline__ int num_steps(const Params& p, int cta, int ncta) {
-    const int items = ((rows(p) + tcg::BM - 1) / tcg::BM) * p.L;
-    return 4 * (items > cta ? (items - cta + ncta - 1) / ncta : 0);
-  }
-  static __device__ __forceinline__ void decode(const Params& p, int cta, int ncta, int it,
-                                                int& m_tile, int& sub) {
-    const int item = cta + (it >> 2) * ncta;
-    m_tile = item / p.L;
-    sub = (item % p.L) * 4 + (it & 3);          // (layer, stage)
-  }
-  static __device__ __forceinline__ int num_kblocks(const Params& p, int sub) {
-    return (sub & 3) == 0 ? 1 : p.Hd / tcg::BK;
-  }
-  static __device__ __forceinline__ int row_off(const Params& p, int sub) {
-    return (sub >> 2) * (3 * p.Hd + p.S) + (sub & 3) * p.Hd;
-  }
-  static __device__ __forceinline__ void w_coords(const Params& p, int sub, int kb, int& col0, int& row0) {
-    col0 = kb * tcg::BK;
-    row0 = row_off(p, sub);
-  }
+namespace chain {
 
-  const Params& p;
-  const int r, AP;
-  float* Act;               // [128][Hd + 4]
-  int src;                  // dense row index b*K + k of this thread's row (or -1)
+constexpr int NSLOT = 4;                 // A ring slots in tensor memory
+constexpr int NSTB = 3;                  // W ring stages in shared memory
+constexpr int NGRP = 3;
+constexpr int WORKER_WARPS = 4 * NGRP;
+constexpr int TMA_WARP = WORKER_WARPS, MMA_WARP = WORKER_WARPS + 1;
+constexpr int THREADS = (WORKER_WARPS + 2) * 32;
+constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;
+constexpr int SMEM_BYTES = NSTB * tcg::STAGE_B_BYTES + 256;
 
-  __device__ MlpChainPolicy(const Params& p_, uint8_t* smem, int tid)
-      : p(p_), r(tid & 127), AP(p_.Hd + 4), Act(reinterpret_cast<float*>(smem)), src(-1) {}
-  static size_t smem_bytes(int Hd) { return (size_t)tcg::BM * (Hd + 4) * 4; }
-
-  __device__ __forceinline__ void step_begin(int m_tile, int sub, int, tcg::PhaseTimer&) {
-    tcg::producers_sync();      // the previous stage's activations are complete / fully consumed
-    if ((sub & 3) == 0) {
-      const int i = m_tile * tcg::BM + r;
-      src = -1;
-      if (i < rows(p)) src = p.rowmap ? __ldg(p.rowmap + i) : i;
-    }
-  }
-  __device__ __forceinline__ void produce(int sub, int kb, float (&v)[32]) {
-    if ((sub & 3) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        v[j] = (src >= 0 && j < p.S) ? __ldg(p.table + (int64_t)src * p.S + j) : 0.f;
-      return;
-    }
-    const float4* a4 = reinterpret_cast<const float4*>(Act + (size_t)r * AP + kb * tcg::BK);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 t = a4[q];
-      v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
-  }
-  __device__ __forceinline__ void pre_epilogue(int) {}
-  __device__ __forceinline__ void post_epilogue(int) {}
-  __device__ __forceinline__ void store(int sub, int col, float (&x)[tcg::EW]) {
-    const int stage = sub & 3;
-    const float* bias = p.bias_all + row_off(p, sub);
-    if (stage < 3) {
-      if (col >= p.Hd) return;
-      float4* o4 = reinterpret_cast<float4*>(Act + (size_t)r * AP + col);
-#pragma unroll
-      for (int q = 0; q < tcg::EW / 4; ++q) {
-        float y[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = col + 4 * q + u;
-          y[u] = (c < p.Hd) ? fmaxf(x[4 * q + u] + __ldg(bias + c), 0.f) : 0.f;
-        }
-        o4[q] = make_float4(y[0], y[1], y[2], y[3]);
-      }
-      return;
-    }
-    if (src < 0 || col >= p.S) return;
-    float* dst = p.coeff + ((int64_t)(sub >> 2) * p.Rall + src) * p.S;
-#pragma unroll
-    for (int j = 0; j < tcg::EW; ++j)
-      if (col + j < p.S) dst[col + j] = x[j] + __ldg(bias + col + j);
-  }
+struct Params {
+  const float* table;     // [Rall, S]  powers of the Ritz values
+  const int32_t* rowmap;  // [Rall]     compact list of rows to evaluate (nullptr: all rows)
+  const int32_t* nrows;   // [1]        number of valid entries in rowmap (nullptr: Rall)
+  const float* bias_all;  // [L * (3*Hd + S)]
+  float* coeff;           // [L, Rall, S]
+  int Rall, L, S, Hd;
 };
+
+// The step sequence every role of the CTA walks in the same order.
+struct Walk {
+  int rows, i0, i1, n;                   // valid rows, item range [i0, i1), k-blocks per hidden stage
+  __device__ Walk(const Params& p, int cta, int ncta) {
+    rows = p.nrows ? __ldg(p.nrows) : p.Rall;
+    const long long items = (long long)((rows + tcg::BM - 1) / tcg::BM) * p.L;
+    i0 = (int)(items * cta / ncta);
+    i1 = (int)(items * (cta + 1) / ncta);
+    n = p.Hd / tcg::BK;
+  }
+  __device__ __forceinline__ int npairs() const { return (i1 - i0 + 1) >> 1; }
+};
+
+__device__ __forceinline__ int w_row0(const Params& p, int layer, int stage) {
+  return layer * (3 * p.Hd + p.S) + stage * p.Hd;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                 const Params p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* Bst = smem_raw + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + NSTB * tcg::STAGE_B_BYTES);
+  uint64_t* b_full = bars;                 // [NSTB]
+  uint64_t* b_empty = b_full + NSTB;       // [NSTB]
+  uint64_t* a_full = b_empty + NSTB;       // [NSLOT]  4 warp arrivals
+  uint64_t* a_empty = a_full + NSLOT;      // [NSLOT]  tcgen05.commit
+  uint64_t* acc_full = a_empty + NSLOT;    // tcgen05.commit
+  uint64_t* acc_empty = acc_full + 1;      // 12 warp arrivals
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Walk w(p, blockIdx.x, gridDim.x);
+  const int n = w.n;
+  const int ksteps0 = (p.S + 7) >> 3;      // tf32 k-steps of the S-wide first stage
+
+  if (warp == TMA_WARP && lane == 0) {
+    tc05::tma_prefetch_desc(&map_hi);
+    tc05::tma_prefetch_desc(&map_lo);
+  }
+  if (warp == MMA_WARP) {
+    if (lane == 0) {
+      for (int i = 0; i < NSTB; ++i) { tc05::mbar_init(&b_full[i], 1); tc05::mbar_init(&b_empty[i], 1); }
+      for (int i = 0; i < NSLOT; ++i) { tc05::mbar_init(&a_full[i], 4); tc05::mbar_init(&a_empty[i], 1); }
+      tc05::mbar_init(acc_full, 1);
+      tc05::mbar_init(acc_empty, WORKER_WARPS);
+      tc05::fence_barrier_init();
+    }
+    __syncwarp();
+    tc05::tmem_alloc(tmem_holder, tcg::TMEM_COLS);
+  }
+  tc05::fence_before_thread_sync();
+  __syncthreads();
+  tc05::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp < WORKER_WARPS) {
+    // ================================ workers ============================================
+    const int grp = warp >> 2, wq = warp & 3;
+    const int r = wq * 32 + lane;                              // row of the tile <-> TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+
+    // write 32 fp32 values of this row as k-block G of the A ring (tf32 hi | lo)
+    auto emit = [&](int G, float (&y)[32]) {
+      const int slot = G % NSLOT;
+      const uint32_t a_addr = lane_addr + COL_A + slot * 64;
+      tc05::mbar_wait(&a_empty[slot], (((uint32_t)G / NSLOT) & 1u) ^ 1u);
+      tc05::fence_after_thread_sync();
+      uint32_t part[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(y[j]);
+      tc05::tmem_st_32x32(a_addr, part);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[j] = tc05::tf32_rna_bits(y[j] - __uint_as_float(part[j]));
+      tc05::tmem_st_32x32(a_addr + 32, part);
+      tc05::tmem_wait_st();
+      tc05::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) tc05::mbar_arrive(&a_full[slot]);
+    };
+    // accumulator columns [32 cc, 32 cc + 32) of this row: main part, then + correction
+    auto ld_main = [&](int cc, uint32_t (&u)[32]) {
+      tc05::tmem_ld_32x32(lane_addr + COL_MAIN + cc * 32, u);
+    };
+    auto add_corr = [&](int cc, const uint32_t (&u)[32], float (&x)[32]) {
+      uint32_t vc[32];
+      tc05::tmem_ld_32x32(lane_addr + COL_CORR + cc * 32, vc);
+      tc05::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(u[j]) + __uint_as_float(vc[j]);
+    };
+    auto bias_relu = [&](const float* bias, float (&x)[32]) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j] + __ldg(bias + j), 0.f);
+    };
+    auto release_acc = [&]() {
+      tc05::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) tc05::mbar_arrive(acc_empty);
+    };
+
+    uint32_t nstep = 0;
+    int Gp = 0;                                               // k-block count at the pair start
+    for (int pr = 0; pr < w.npairs(); ++pr) {
+      const int item[2] = {w.i0 + 2 * pr, w.i0 + 2 * pr + 1};
+      const bool vb = item[1] < w.i1;
+      // first k-block of step (X, s) in the interleaved order A0 B0 A1 B1 ... (or A0 A1 A2 A3)
+      auto base = [&](int X, int s) {
+        return vb ? Gp + (s == 0 ? X : 2 + 2 * n * (s - 1) + X * n) : Gp + (s == 0 ? 0 : 1 + n * (s - 1));
+      };
+      int src[2] = {-1, -1}, layer[2] = {0, 0};
+#pragma unroll
+      for (int X = 0; X < 2; ++X) {
+        if (X == 1 && !vb) break;
+        layer[X] = item[X] % p.L;
+        const int i = (item[X] / p.L) * tcg::BM + r;
+        if (i < w.rows) src[X] = p.rowmap ? __ldg(p.rowmap + i) : i;
+      }
+      // stage-0 operands: the S powers of this row's Ritz value
+#pragma unroll
+      for (int X = 0; X < 2; ++X) {
+        if (X == 1 && !vb) break;
+        const int G = base(X, 0);
+        if (G % NGRP == grp) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = (src[X] >= 0 && j < p.S) ? __ldg(p.table + (int64_t)src[X] * p.S + j) : 0.f;
+          emit(G, v);
+        }
+      }
+      const int nst = vb ? 8 : 4;
+      for (int j = 0; j < nst; ++j, ++nstep) {
+        const int X = vb ? (j & 1) : 0, s = vb ? (j >> 1) : j;
+        const float* bias = p.bias_all + w_row0(p, layer[X], s);
+        tc05::mbar_wait(acc_full, nstep & 1u);
+        tc05::fence_after_thread_sync();
+        if (s < 3) {
+          // chunk cc of this stage becomes k-block nb + cc of the next one; its owner drains it
+          const int nb = base(X, s + 1);
+          const int c0 = (grp + NGRP - nb % NGRP) % NGRP, c1 = c0 + NGRP;
+          if (c1 < n) {                                       // two chunks: c0 and c0 + 3
+            uint32_t ua[32], ub[32];
+            float xa[32], xb[32];
+            ld_main(c0, ua);
+            ld_main(c1, ub);
+            add_corr(c0, ua, xa);                             // its wait::ld covers the loads above
+            add_corr(c1, ub, xb);
+            release_acc();                                    // the next step may overwrite D now
+            bias_relu(bias + c0 * 32, xa);
+            emit(nb + c0, xa);
+            bias_relu(bias + c1 * 32, xb);
+            emit(nb + c1, xb);
+          } else if (c0 < n) {
+            uint32_t ua[32];
+            float xa[32];
+            ld_main(c0, ua);
+            add_corr(c0, ua, xa);
+            release_acc();
+            bias_relu(bias + c0 * 32, xa);
+            emit(nb + c0, xa);
+          } else {
+            release_acc();
+          }
+        } else {
+          const bool mine = (int)(nstep % NGRP) == grp;      // rotate the output work over groups
+          float x[32];
+          if (mine) { uint32_t u[32]; ld_main(0, u); add_corr(0, u, x); }
+          release_acc();
+          if (mine && src[X] >= 0) {
+            float* dst = p.coeff + ((int64_t)layer[X] * p.Rall + src[X]) * p.S;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < p.S) dst[c] = x[c] + __ldg(bias + c);
+          }
+        }
+      }
+      Gp += vb ? 2 + 6 * n : 1 + 3 * n;
+    }
+  } else if (warp == TMA_WARP) {
+    // ================================ TMA producer (W tiles) ==============================
+    uint32_t G = 0;
+    for (int pr = 0; pr < w.npairs(); ++pr) {
+      const int item[2] = {w.i0 + 2 * pr, w.i0 + 2 * pr + 1};
+      const bool vb = item[1] < w.i1;
+      const int nst = vb ? 8 : 4;
+      for (int j = 0; j < nst; ++j) {
+        const int X = vb ? (j & 1) : 0, s = vb ? (j >> 1) : j;
+        const int row0 = w_row0(p, item[X] % p.L, s);
+        const int nkb = s == 0 ? 1 : n;
+        for (int kb = 0; kb < nkb; ++kb, ++G) {
+          const uint32_t st = G % NSTB;
+          tc05::mbar_wait(&b_empty[st], ((G / NSTB) & 1u) ^ 1u);
+          if (tc05::elect_one()) {
+            uint8_t* dst = Bst + st * tcg::STAGE_B_BYTES;
+            tc05::mbar_arrive_expect_tx(&b_full[st], tcg::STAGE_B_BYTES);
+            tc05::tma_load_2d(dst, &map_hi, &b_full[st], kb * tcg::BK, row0);
+            tc05::tma_load_2d(dst + tcg::TILE_B_BYTES, &map_lo, &b_full[st], kb * tcg::BK, row0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================================ MMA issuer ==========================================
+    constexpr uint32_t idesc256 = tc05::umma_idesc_tf32(tcg::BM, 2 * tcg::BN);
+    constexpr uint32_t idesc128 = tc05::umma_idesc_tf32(tcg::BM, tcg::BN);
+    constexpr uint32_t idesc32 = tc05::umma_idesc_tf32(tcg::BM, 32);
+    const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
+    uint32_t G = 0, nstep = 0;
+    for (int pr = 0; pr < w.npairs(); ++pr) {
+      const bool vb = w.i0 + 2 * pr + 1 < w.i1;
+      const int nst = vb ? 8 : 4;
+      for (int j = 0; j < nst; ++j, ++nstep) {
+        const int s = vb ? (j >> 1) : j;
+        const int nkb = s == 0 ? 1 : n;
+        const int ksteps = s == 0 ? ksteps0 : tcg::BK / 8;
+        tc05::mbar_wait(acc_empty, (nstep & 1u) ^ 1u);       // previous accumulator drained
+        tc05::fence_after_thread_sync();
+        for (int kb = 0; kb < nkb; ++kb, ++G) {
+          const uint32_t st = G % NSTB, slot = G % NSLOT;
+          tc05::mbar_wait(&b_full[st], (G / NSTB) & 1u);
+          tc05::mbar_wait(&a_full[slot], (G / NSLOT) & 1u);
+          tc05::fence_after_thread_sync();
+          if (tc05::elect_one()) {
+            const uint32_t a_hi = tmem_base + COL_A + slot * 64, a_lo = a_hi + 32;
+            const uint32_t b_addr = tc05::smem_u32(Bst + st * tcg::STAGE_B_BYTES);
+            const uint64_t dB = tc05::umma_desc_kmajor_sw128(b_addr);
+            if (s < 3) {
+              // [D_main | D_corr] += A_hi [W_hi ; W_lo]^T (N = 256),  D_corr += A_lo W_hi^T
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                tc05::umma_tf32_ts(d_main, a_hi + 8 * k, dB + 2 * k, idesc256, acc);
+                tc05::umma_tf32_ts(d_corr, a_lo + 8 * k, dB + 2 * k, idesc128, 1u);
+              }
+            } else {
+              // S <= 32 outputs: three N = 32 products
+              const uint64_t dBl = tc05::umma_desc_kmajor_sw128(b_addr + tcg::TILE_B_BYTES);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                tc05::umma_tf32_ts(d_main, a_hi + 8 * k, dB + 2 * k, idesc32, acc);
+                tc05::umma_tf32_ts(d_corr, a_lo + 8 * k, dB + 2 * k, idesc32, acc);
+                tc05::umma_tf32_ts(d_corr, a_hi + 8 * k, dBl + 2 * k, idesc32, 1u);
+              }
+            }
+            tc05::umma_commit(&a_empty[slot]);
+            tc05::umma_commit(&b_empty[st]);
+            if (kb == nkb - 1) tc05::umma_commit(acc_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  tc05::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    __syncwarp();
+    tc05::tmem_dealloc(tmem_base, tcg::TMEM_COLS);
+  }
+}
+
+}  // namespace chain
 
 // Compact list of the (graph, k) rows whose Ritz vector is not identically zero.
 __global__ void __launch_bounds__(1024)
@@ -171,13 +377,12 @@ int lnb_ritz_filter_mlp(lnb_stream_t stream, const float* table, const int32_t* 
   if (rc != LNB_OK) return rc;
   rc = tcg::make_weight_map(&map_lo, W_lo, wrows, Hd, "ritz_filter_mlp");
   if (rc != LNB_OK) return rc;
-  const size_t smem = tcg::core_smem(MlpChainPolicy::kStagesB) + 1024 + MlpChainPolicy::smem_bytes(Hd);
-  auto kern = tcg::tc_gemm_kernel<MlpChainPolicy>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  MlpChainPolicy::Params p{table, rowmap, nrows, bias_all, coeff, Rall, L, S, Hd, tcg::debug_flags()};
+  const size_t smem = chain::SMEM_BYTES + 1024;
+  cudaFuncSetAttribute(chain::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  chain::Params p{table, rowmap, nrows, bias_all, coeff, Rall, L, S, Hd};
   const int items = lnb::ceil_div(Rall, tcg::BM) * L;
   const int grid = items < tcg::sm_count() ? items : tcg::sm_count();
-  kern<<<grid, tcg::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
+  chain::mlp_chain_kernel<<<grid, chain::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
   lnb::count_launch();
   return lnb::finish_launch("ritz_filter_mlp");
 }

@@ -656,27 +656,46 @@ struct SpectralPolicy {
     }
     tcg::producers_sync();
     const int Rtot = tb->Rtot;
-    // one thread per (row, 4 outputs); row Rtot stands for the constant padded-node row
-    for (int e = tid; e < (Rtot + 1) * PQ; e += tcg::PRODUCER_THREADS) {
-      const int rr = e / PQ, oq = e - rr * PQ;
-      const float4* x4 = reinterpret_cast<const float4*>((rr < Rtot) ? Xs + (size_t)rr * XP : cx);
-      const float4* w4 = reinterpret_cast<const float4*>(Wr + (size_t)4 * oq * HP);
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int h4 = 0; h4 < H / 4; ++h4) {
-        const float4 x = x4[h4];
+    // warp <-> (block of 32 rows, third of the outputs): lane = row, so the row loads are
+    // conflict-free and every weight load is one broadcast wavefront
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int rb = warp & 3, og = warp >> 2;
+      const int per = (P1 + 2) / 3;
+      const int o_end = min(P1, (og + 1) * per);
+      const int row = rb * 32 + lane;
+      const float4* x4 = reinterpret_cast<const float4*>(Xs + (size_t)(row < Rtot ? row : 0) * XP);
+      for (int o0 = og * per; o0 < o_end; o0 += 6) {
+        const int cnt = min(6, o_end - o0);
+        const float4* w4 = reinterpret_cast<const float4*>(Wr + (size_t)o0 * HP);
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int h4 = 0; h4 < H / 4; ++h4) {
+          const float4 x = x4[h4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 w = w4[j * (HP / 4) + h4];
-          acc[j] = fmaf(x.x, w.x, acc[j]); acc[j] = fmaf(x.y, w.y, acc[j]);
-          acc[j] = fmaf(x.z, w.z, acc[j]); acc[j] = fmaf(x.w, w.w, acc[j]);
+          for (int j = 0; j < 6; ++j) {
+            if (j < cnt) {
+              const float4 wv = w4[j * (HP / 4) + h4];
+              acc[j] = fmaf(x.x, wv.x, acc[j]); acc[j] = fmaf(x.y, wv.y, acc[j]);
+              acc[j] = fmaf(x.z, wv.z, acc[j]); acc[j] = fmaf(x.w, wv.w, acc[j]);
+            }
+          }
+        }
+        if (row < Rtot) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j)
+            if (j < cnt) {
+              const int o = o0 + j;
+              Yr[row * P1 + o] = acc[j] + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+            }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = 4 * oq + j;
-        if (o < P1)
-          Yr[(rr < Rtot ? rr : RMAX) * P1 + o] = acc[j] + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+      if (warp == 0) {                               // the constant padded-node row
+        for (int o = lane; o < P1; o += 32) {
+          float acc = 0.f;
+          for (int h = 0; h < H; ++h) acc = fmaf(cx[h], Wr[o * HP + h], acc);
+          Yr[RMAX * P1 + o] = acc + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+        }
       }
     }
     tcg::producers_sync();
