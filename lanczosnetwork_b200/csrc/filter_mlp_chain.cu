@@ -9,14 +9,18 @@
 // into the A ring (tcgen05.st) as the k-blocks of stage s+1 -- output chunk cc of stage s IS
 // k-block cc of stage s+1 for the same thread (row <-> TMEM lane in both).
 //
-// Every CTA walks a contiguous range of items two at a time (A, B) with the steps interleaved
-// A0 B0 A1 B1 A2 B2 A3 B3: while the CUDA cores turn A.s into the operand of A.(s+1), the tensor
-// core runs B.s, so the MMA pipe only idles while an accumulator is drained to registers.
+// Every CTA walks a contiguous range of items (layer-major order) two at a time: A and B are
+// consecutive row tiles of the SAME layer with the steps interleaved A0 B0 A1 B1 A2 B2 A3 B3.
+// While the CUDA cores turn A.s into the operand of A.(s+1) the tensor core runs B.s, so the MMA
+// pipe only idles while an accumulator is drained to registers; and every W tile is fetched from
+// L2 once per pair (A.s and B.s multiply by the same weights) -- at full MMA rate a single item
+// would ask L2 for more than its ~42 B/clk/SM share.
 // Only rows (graph, k) with k < k_eff(graph) are evaluated (rowmap): zero-padded Ritz pairs
 // multiply zero Ritz vectors downstream (exact).
 //
 // Warps: 0-11 workers (group g = warp / 4 owns k-block G when G % 3 == g, G = CTA-global k-block
-// count; lane quarter = warp % 4), 12 TMA (W tiles, 3-stage shared-memory ring), 13 MMA issue.
+// count; lane quarter = warp % 4), 12 TMA (W tiles, 6-slot shared-memory ring: the 4 k-blocks of
+// a stage stay until B has used them while the next stage prefetches), 13 MMA issue.
 // TMEM: [0,128) D_main, [128,256) D_corr, [256,512) A ring of 4 slots x (32 hi + 32 lo).
 #include "tc_gemm.cuh"
 
@@ -25,7 +29,7 @@ namespace {
 namespace chain {
 
 constexpr int NSLOT = 4;                 // A ring slots in tensor memory
-constexpr int NSTB = 3;                  // W ring stages in shared memory
+constexpr int NSTB = 6;                  // W ring slots in shared memory (one stage = 4 + prefetch)
 constexpr int NGRP = 3;
 constexpr int WORKER_WARPS = 4 * NGRP;
 constexpr int TMA_WARP = WORKER_WARPS, MMA_WARP = WORKER_WARPS + 1;
@@ -44,15 +48,17 @@ struct Params {
 
 // The step sequence every role of the CTA walks in the same order.
 struct Walk {
-  int rows, i0, i1, n;                   // valid rows, item range [i0, i1), k-blocks per hidden stage
+  int rows, ntile, i0, i1, n;            // valid rows, row tiles, item range [i0, i1), k-blocks per hidden stage
   __device__ Walk(const Params& p, int cta, int ncta) {
     rows = p.nrows ? __ldg(p.nrows) : p.Rall;
-    const long long items = (long long)((rows + tcg::BM - 1) / tcg::BM) * p.L;
+    ntile = (rows + tcg::BM - 1) / tcg::BM;
+    const long long items = (long long)ntile * p.L;
     i0 = (int)(items * cta / ncta);
     i1 = (int)(items * (cta + 1) / ncta);
     n = p.Hd / tcg::BK;
   }
-  __device__ __forceinline__ int npairs() const { return (i1 - i0 + 1) >> 1; }
+  // item i = (layer i / ntile, tile i % ntile); items i, i + 1 pair up when they share the layer
+  __device__ __forceinline__ bool paired(int i) const { return i + 1 < i1 && (i + 1) / ntile == i / ntile; }
 };
 
 __device__ __forceinline__ int w_row0(const Params& p, int layer, int stage) {
@@ -61,6 +67,7 @@ __device__ __forceinline__ int w_row0(const Params& p, int layer, int stage) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                 const __grid_constant__ CUtensorMap map_hi32, const __grid_constant__ CUtensorMap map_lo32,
                  const Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t pad = (1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -82,6 +89,8 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   if (warp == TMA_WARP && lane == 0) {
     tc05::tma_prefetch_desc(&map_hi);
     tc05::tma_prefetch_desc(&map_lo);
+    tc05::tma_prefetch_desc(&map_hi32);
+    tc05::tma_prefetch_desc(&map_lo32);
   }
   if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -146,19 +155,20 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 
     uint32_t nstep = 0;
     int Gp = 0;                                               // k-block count at the pair start
-    for (int pr = 0; pr < w.npairs(); ++pr) {
-      const int item[2] = {w.i0 + 2 * pr, w.i0 + 2 * pr + 1};
-      const bool vb = item[1] < w.i1;
+    for (int it = w.i0; it < w.i1;) {
+      const int item[2] = {it, it + 1};
+      const bool vb = w.paired(it);
+      it += vb ? 2 : 1;
       // first k-block of step (X, s) in the interleaved order A0 B0 A1 B1 ... (or A0 A1 A2 A3)
       auto base = [&](int X, int s) {
         return vb ? Gp + (s == 0 ? X : 2 + 2 * n * (s - 1) + X * n) : Gp + (s == 0 ? 0 : 1 + n * (s - 1));
       };
-      int src[2] = {-1, -1}, layer[2] = {0, 0};
+      int src[2] = {-1, -1};
+      const int layer = item[0] / w.ntile;
 #pragma unroll
       for (int X = 0; X < 2; ++X) {
         if (X == 1 && !vb) break;
-        layer[X] = item[X] % p.L;
-        const int i = (item[X] / p.L) * tcg::BM + r;
+        const int i = (item[X] % w.ntile) * tcg::BM + r;
         if (i < w.rows) src[X] = p.rowmap ? __ldg(p.rowmap + i) : i;
       }
       // stage-0 operands: the S powers of this row's Ritz value
@@ -177,7 +187,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       const int nst = vb ? 8 : 4;
       for (int j = 0; j < nst; ++j, ++nstep) {
         const int X = vb ? (j & 1) : 0, s = vb ? (j >> 1) : j;
-        const float* bias = p.bias_all + w_row0(p, layer[X], s);
+        const float* bias = p.bias_all + w_row0(p, layer, s);
         tc05::mbar_wait(acc_full, nstep & 1u);
         tc05::fence_after_thread_sync();
         if (s < 3) {
@@ -213,7 +223,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           if (mine) { uint32_t u[32]; ld_main(0, u); add_corr(0, u, x); }
           release_acc();
           if (mine && src[X] >= 0) {
-            float* dst = p.coeff + ((int64_t)layer[X] * p.Rall + src[X]) * p.S;
+            float* dst = p.coeff + ((int64_t)layer * p.Rall + src[X]) * p.S;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
               if (c < p.S) dst[c] = x[c] + __ldg(bias + c);
@@ -224,23 +234,23 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
   } else if (warp == TMA_WARP) {
     // ================================ TMA producer (W tiles) ==============================
-    uint32_t G = 0;
-    for (int pr = 0; pr < w.npairs(); ++pr) {
-      const int item[2] = {w.i0 + 2 * pr, w.i0 + 2 * pr + 1};
-      const bool vb = item[1] < w.i1;
-      const int nst = vb ? 8 : 4;
-      for (int j = 0; j < nst; ++j) {
-        const int X = vb ? (j & 1) : 0, s = vb ? (j >> 1) : j;
-        const int row0 = w_row0(p, item[X] % p.L, s);
-        const int nkb = s == 0 ? 1 : n;
-        for (int kb = 0; kb < nkb; ++kb, ++G) {
-          const uint32_t st = G % NSTB;
-          tc05::mbar_wait(&b_empty[st], ((G / NSTB) & 1u) ^ 1u);
+    // one load per (stage, k-block) of an item or same-layer pair
+    uint32_t Wg = 0;
+    for (int it = w.i0; it < w.i1;) {
+      const int layer = it / w.ntile;
+      it += w.paired(it) ? 2 : 1;
+      for (int st_ = 0; st_ < 4; ++st_) {
+        const int row0 = w_row0(p, layer, st_);
+        const int nkb = st_ == 0 ? 1 : n;
+        const bool small = st_ == 3;                          // S <= 32 output rows: 32-row boxes
+        for (int kb = 0; kb < nkb; ++kb, ++Wg) {
+          const uint32_t st = Wg % NSTB;
+          tc05::mbar_wait(&b_empty[st], ((Wg / NSTB) & 1u) ^ 1u);
           if (tc05::elect_one()) {
             uint8_t* dst = Bst + st * tcg::STAGE_B_BYTES;
-            tc05::mbar_arrive_expect_tx(&b_full[st], tcg::STAGE_B_BYTES);
-            tc05::tma_load_2d(dst, &map_hi, &b_full[st], kb * tcg::BK, row0);
-            tc05::tma_load_2d(dst + tcg::TILE_B_BYTES, &map_lo, &b_full[st], kb * tcg::BK, row0);
+            tc05::mbar_arrive_expect_tx(&b_full[st], small ? 2 * 32 * 128 : tcg::STAGE_B_BYTES);
+            tc05::tma_load_2d(dst, small ? &map_hi32 : &map_hi, &b_full[st], kb * tcg::BK, row0);
+            tc05::tma_load_2d(dst + tcg::TILE_B_BYTES, small ? &map_lo32 : &map_lo, &b_full[st], kb * tcg::BK, row0);
           }
           __syncwarp();
         }
@@ -252,19 +262,22 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     constexpr uint32_t idesc128 = tc05::umma_idesc_tf32(tcg::BM, tcg::BN);
     constexpr uint32_t idesc32 = tc05::umma_idesc_tf32(tcg::BM, 32);
     const uint32_t d_main = tmem_base + COL_MAIN, d_corr = tmem_base + COL_CORR;
-    uint32_t G = 0, nstep = 0;
-    for (int pr = 0; pr < w.npairs(); ++pr) {
-      const bool vb = w.i0 + 2 * pr + 1 < w.i1;
+    uint32_t G = 0, Wp = 0, nstep = 0;
+    for (int it = w.i0; it < w.i1;) {
+      const bool vb = w.paired(it);
+      it += vb ? 2 : 1;
       const int nst = vb ? 8 : 4;
       for (int j = 0; j < nst; ++j, ++nstep) {
-        const int s = vb ? (j >> 1) : j;
+        const int X = vb ? (j & 1) : 0, s = vb ? (j >> 1) : j;
         const int nkb = s == 0 ? 1 : n;
         const int ksteps = s == 0 ? ksteps0 : tcg::BK / 8;
+        const bool last_use = !vb || X == 1;                  // B (or a single item) frees the W slot
         tc05::mbar_wait(acc_empty, (nstep & 1u) ^ 1u);       // previous accumulator drained
         tc05::fence_after_thread_sync();
         for (int kb = 0; kb < nkb; ++kb, ++G) {
-          const uint32_t st = G % NSTB, slot = G % NSLOT;
-          tc05::mbar_wait(&b_full[st], (G / NSTB) & 1u);
+          const uint32_t Wg = Wp + (s == 0 ? 0 : 1 + n * (s - 1)) + kb;
+          const uint32_t st = Wg % NSTB, slot = G % NSLOT;
+          tc05::mbar_wait(&b_full[st], (Wg / NSTB) & 1u);
           tc05::mbar_wait(&a_full[slot], (G / NSLOT) & 1u);
           tc05::fence_after_thread_sync();
           if (tc05::elect_one()) {
@@ -289,12 +302,13 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               }
             }
             tc05::umma_commit(&a_empty[slot]);
-            tc05::umma_commit(&b_empty[st]);
+            if (last_use) tc05::umma_commit(&b_empty[st]);
             if (kb == nkb - 1) tc05::umma_commit(acc_full);
           }
           __syncwarp();
         }
       }
+      Wp += 1 + 3 * n;
     }
   }
 
@@ -377,12 +391,17 @@ int lnb_ritz_filter_mlp(lnb_stream_t stream, const float* table, const int32_t* 
   if (rc != LNB_OK) return rc;
   rc = tcg::make_weight_map(&map_lo, W_lo, wrows, Hd, "ritz_filter_mlp");
   if (rc != LNB_OK) return rc;
+  CUtensorMap map_hi32, map_lo32;                       // 32-row boxes for the S-row last stage
+  rc = tcg::make_weight_map(&map_hi32, W_hi, wrows, Hd, "ritz_filter_mlp", 32);
+  if (rc != LNB_OK) return rc;
+  rc = tcg::make_weight_map(&map_lo32, W_lo, wrows, Hd, "ritz_filter_mlp", 32);
+  if (rc != LNB_OK) return rc;
   const size_t smem = chain::SMEM_BYTES + 1024;
   cudaFuncSetAttribute(chain::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   chain::Params p{table, rowmap, nrows, bias_all, coeff, Rall, L, S, Hd};
   const int items = lnb::ceil_div(Rall, tcg::BM) * L;
   const int grid = items < tcg::sm_count() ? items : tcg::sm_count();
-  chain::mlp_chain_kernel<<<grid, chain::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, p);
+  chain::mlp_chain_kernel<<<grid, chain::THREADS, smem, (cudaStream_t)stream>>>(map_hi, map_lo, map_hi32, map_lo32, p);
   lnb::count_launch();
   return lnb::finish_launch("ritz_filter_mlp");
 }

@@ -38,17 +38,28 @@ constexpr int FR = 8;           // filter coefficients held in registers per row
 __global__ void __launch_bounds__(256)
 graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, int N, int E1, int K,
                      float* __restrict__ ell_val, uint8_t* __restrict__ ell_idx,
-                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext) {
+                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext, int stage_smem) {
+  extern __shared__ __align__(16) float gp_smem[];     // [N*N*E1] this graph's operators (optional)
   __shared__ int s_max[EMAX];
   __shared__ int s_ext[2];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < EMAX) s_max[tid] = 0;
   if (tid < 2) s_ext[tid] = 0;
+  const int64_t per = (int64_t)N * N * E1;
+  const float* Lb = L + b * per;
+  if (stage_smem) {                                    // coalesced copy, then strided reads hit smem
+    if ((per & 3) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(Lb);
+      float4* dst = reinterpret_cast<float4*>(gp_smem);
+      for (int i = tid; i < (int)(per >> 2); i += 256) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < (int)per; i += 256) gp_smem[i] = __ldg(Lb + i);
+    }
+    Lb = gp_smem;
+  }
   __syncthreads();
-  const float* Lb = L + (int64_t)b * N * N * E1;
   const int pairs = N * E1;
-  // pair index p = n*E1 + e keeps the E1 channels of one row in adjacent threads -> their loads
-  // of L[b,n,i,:] coalesce.
+  // pair index p = n*E1 + e keeps the E1 channels of one row in adjacent threads
   int ne = 0;
   for (int p0 = 0; p0 < pairs; p0 += 256) {
     const int p = p0 + tid;
@@ -107,10 +118,12 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
 __global__ void __launch_bounds__(1024)
 tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __restrict__ tiles,
                    int32_t* __restrict__ scratch /* [3 * B] */, int32_t* __restrict__ rowmap,
-                   int32_t* __restrict__ nrows) {
+                   int32_t* __restrict__ nrows, int scratch_smem) {
+  extern __shared__ int32_t ta_smem[];   // [3 * B] when it fits: the serial hop loop reads it
   __shared__ int warp_n[32], warp_k[32], warp_r[32];
   __shared__ int run_n, run_k, run_r;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (scratch_smem) scratch = ta_smem;
   int32_t* PN = scratch;            // inclusive prefix of n_eff
   int32_t* PK = scratch + B;        // inclusive prefix of ceil4(k_eff)
   int32_t* NX = scratch + 2 * B;    // end (exclusive) of the tile starting at i
@@ -738,8 +751,18 @@ int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B
               "graph_prepare: bad dims B=%d N=%d E1=%d K=%d", B, N, E1, K);
   if (B == 0) return LNB_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  graph_prepare_kernel<<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
-  tile_assign_kernel<<<1, 1024, 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
+  const size_t lbytes = (size_t)N * N * E1 * sizeof(float);
+  const int stage = lbytes <= 64 * 1024;
+  if (stage && lbytes > 40 * 1024)
+    cudaFuncSetAttribute(graph_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbytes);
+  graph_prepare_kernel<<<B, 256, stage ? lbytes : 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max,
+                                                         gext, stage);
+  const size_t tbytes = (size_t)3 * B * sizeof(int32_t);
+  const int tsm = tbytes <= 160 * 1024;
+  if (tsm && tbytes > 40 * 1024)
+    cudaFuncSetAttribute(tile_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);
+  tile_assign_kernel<<<1, 1024, tsm ? tbytes : 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows,
+                                                      tsm);
   lnb::count_launch(2);
   return lnb::finish_launch("graph_prepare");
 }

@@ -335,12 +335,13 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // Row-major [rows, cols] fp32 weight matrix; box = 32 columns (128 B) x 128 rows; 128 B swizzle.
-inline int make_weight_map(CUtensorMap* map, const float* W, int rows, int cols, const char* who) {
+inline int make_weight_map(CUtensorMap* map, const float* W, int rows, int cols, const char* who,
+                           int box_rows = BN) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { lnb::set_err("%s: cuTensorMapEncodeTiled unavailable", who); return LNB_ERR_UNSUPPORTED; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), gdim, gstride,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
