@@ -13,6 +13,8 @@ namespace lnb {
 char* err_buf();
 void set_err(const char* fmt, ...);
 void count_launch(int n = 1);
+unsigned long long* prof_buffer();          // profiling aid (lnb_debug_set_prof), nullptr = off
+void set_prof_buffer(unsigned long long* p);
 
 inline int finish_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

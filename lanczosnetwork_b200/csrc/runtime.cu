@@ -17,6 +17,10 @@ void set_err(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
+static unsigned long long* g_prof_buf = nullptr;
+unsigned long long* prof_buffer() { return g_prof_buf; }
+void set_prof_buffer(unsigned long long* p) { g_prof_buf = p; }
+
 }  // namespace lnb
 
 extern "C" {

@@ -35,53 +35,57 @@ constexpr int FR = 8;           // filter coefficients held in registers per row
 //   gext[b] = {n_eff, k_eff}: the operators are zero outside their leading n_eff rows/columns,
 //   Q[b] is zero outside its leading n_eff rows / k_eff columns.
 // --------------------------------------------------------------------------------------------
+template <bool STAGE>   // STAGE: this graph's operators fit in shared memory
 __global__ void __launch_bounds__(256)
 graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, int N, int E1, int K,
                      float* __restrict__ ell_val, uint8_t* __restrict__ ell_idx,
-                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext, int stage_smem) {
+                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext) {
   extern __shared__ __align__(16) float gp_smem[];     // [N*N*E1] this graph's operators (optional)
   __shared__ int s_max[EMAX];
   __shared__ int s_ext[2];
+  __shared__ uint8_t cnt_s[256 * EMAX];                // non-zeros per (row, channel); N <= 255
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < EMAX) s_max[tid] = 0;
   if (tid < 2) s_ext[tid] = 0;
   const int64_t per = (int64_t)N * N * E1;
-  const float* Lb = L + b * per;
-  if (stage_smem) {                                    // coalesced copy, then strided reads hit smem
+  const float* Lg = L + b * per;
+  if (STAGE) {                                         // coalesced copy, then strided reads hit smem
     if ((per & 3) == 0) {
-      const float4* src = reinterpret_cast<const float4*>(Lb);
+      const float4* src = reinterpret_cast<const float4*>(Lg);
       float4* dst = reinterpret_cast<float4*>(gp_smem);
       for (int i = tid; i < (int)(per >> 2); i += 256) dst[i] = __ldg(src + i);
     } else {
-      for (int i = tid; i < (int)per; i += 256) gp_smem[i] = __ldg(Lb + i);
+      for (int i = tid; i < (int)per; i += 256) gp_smem[i] = __ldg(Lg + i);
     }
-    Lb = gp_smem;
   }
+  const float* Lb = STAGE ? gp_smem : Lg;
   __syncthreads();
   const int pairs = N * E1;
-  // pair index p = n*E1 + e keeps the E1 channels of one row in adjacent threads
-  int ne = 0;
-  for (int p0 = 0; p0 < pairs; p0 += 256) {
-    const int p = p0 + tid;
-    if (p < pairs) {
-      const int n = p / E1, e = p % E1;
-      float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
-      uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
-      int cnt = 0;
-      for (int i = 0; i < N; ++i) {
-        const float v = Lb[((int64_t)n * N + i) * E1 + e];
-        if (v != 0.f) {
-          val[(int64_t)cnt * N] = v;
-          idx[(int64_t)cnt * N] = (uint8_t)i;
-          ++cnt;
-          ne = max(ne, max(n, i) + 1);
-        }
+  // thread <-> (row n, channel e), p = n*E1 + e: one pass over the row, compacting as it goes
+  int ne = 0, ke = 0;
+  for (int p = tid; p < pairs; p += 256) {
+    const int n = p / E1, e = p - n * E1;
+    const float* row = Lb + (n * N) * E1 + e;
+    float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
+    uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
+    int cnt = 0, far = 0;
+#pragma unroll 2
+    for (int i = 0; i < N; ++i) {
+      const float v = row[i * E1];
+      if (v != 0.f) {
+        val[cnt * N] = v;
+        idx[cnt * N] = (uint8_t)i;
+        ++cnt;
+        far = i + 1;
       }
+    }
+    cnt_s[p] = (uint8_t)cnt;
+    if (cnt) {
       atomicMax(&s_max[e], cnt);
+      ne = max(ne, max(n + 1, far));
     }
   }
   const float* Qb = Q + (int64_t)b * N * K;
-  int ke = 0;
   for (int i = tid; i < N * K; i += 256) {
     if (Qb[i] != 0.f) {
       ne = max(ne, i / K + 1);
@@ -93,18 +97,13 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
   __syncthreads();
   // zero-fill the tail of every row up to the channel maximum of this graph, so consumers can
   // run all rows of a (graph, channel) to the same length without per-row guards
-  for (int p0 = 0; p0 < pairs; p0 += 256) {
-    const int p = p0 + tid;
-    if (p < pairs) {
-      const int n = p / E1, e = p % E1;
-      int cnt = 0;
-      for (int i = 0; i < N; ++i) cnt += (Lb[((int64_t)n * N + i) * E1 + e] != 0.f) ? 1 : 0;
-      float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
-      uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
-      for (int t = cnt; t < s_max[e]; ++t) {
-        val[(int64_t)t * N] = 0.f;
-        idx[(int64_t)t * N] = 0;
-      }
+  for (int pr = tid; pr < pairs; pr += 256) {
+    const int n = pr / E1, e = pr - n * E1;
+    float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
+    uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
+    for (int t = cnt_s[pr]; t < s_max[e]; ++t) {
+      val[(int64_t)t * N] = 0.f;
+      idx[(int64_t)t * N] = 0;
     }
   }
   if (tid < E1) ell_max[b * E1 + tid] = s_max[tid];
@@ -112,21 +111,24 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
 }
 
 // Next-fit assignment of consecutive graphs to tiles.  tiles[0] = T, tiles[1 + t] = first graph
-// of tile t, tiles[1 + T] = B.  One CTA.  Parallel part: inclusive prefix sums of the row /
-// Ritz-row counts and, for every graph i, the end of the tile that would start at i (a window
-// of <= 32 graphs); sequential part: one thread follows that jump table (T hops, not B steps).
+// of tile t, tiles[1 + T] = B.  One CTA, all of it parallel: inclusive prefix sums of the row /
+// Ritz-row counts; for every graph i the end NX[i] of the tile that would start at i (a window of
+// <= 32 graphs); the tile starts are the graphs reachable from 0 along NX, found by pointer
+// jumping (round k marks the starts 2^k .. 2^(k+1)-1 hops away and squares the jump table); a
+// prefix sum over the marks numbers the tiles.  The arrays live in shared memory (6 (B+1) ints);
+// batches too large for that use the global scratch and a serial walk.
 __global__ void __launch_bounds__(1024)
 tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __restrict__ tiles,
                    int32_t* __restrict__ scratch /* [3 * B] */, int32_t* __restrict__ rowmap,
-                   int32_t* __restrict__ nrows, int scratch_smem) {
-  extern __shared__ int32_t ta_smem[];   // [3 * B] when it fits: the serial hop loop reads it
+                   int32_t* __restrict__ nrows, int in_smem) {
+  extern __shared__ int32_t ta_smem[];
   __shared__ int warp_n[32], warp_k[32], warp_r[32];
   __shared__ int run_n, run_k, run_r;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (scratch_smem) scratch = ta_smem;
-  int32_t* PN = scratch;            // inclusive prefix of n_eff
-  int32_t* PK = scratch + B;        // inclusive prefix of ceil4(k_eff)
-  int32_t* NX = scratch + 2 * B;    // end (exclusive) of the tile starting at i
+  int32_t* PN = in_smem ? ta_smem : scratch;                     // inclusive prefix of n_eff
+  int32_t* PK = PN + B;                                          // inclusive prefix of ceil4(k_eff)
+  int32_t* NX = PK + B;                                          // [B + 1] end of the tile starting at i
+  int32_t* PR = NX + 3 * (B + 1);                                // (shared memory only) inclusive prefix of k_eff
   if (tid == 0) { run_n = 0; run_k = 0; run_r = 0; }
   __syncthreads();
   for (int b0 = 0; b0 < B; b0 += 1024) {
@@ -159,7 +161,9 @@ tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __re
     if (b < B) {
       PN[b] = run_n + warp_n[warp] + in;
       PK[b] = run_k + warp_k[warp] + ik;
-      if (rowmap) {                       // {b*K + k : k < k_eff(b)}, see lnb_ritz_rowmap
+      if (in_smem) {
+        PR[b] = run_r + warp_r[warp] + ir;
+      } else if (rowmap) {                // {b*K + k : k < k_eff(b)}, see lnb_ritz_rowmap
         const int base = run_r + warp_r[warp] + ir - kr;
         for (int i = 0; i < kr; ++i) rowmap[base + i] = b * K + i;
       }
@@ -170,6 +174,18 @@ tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __re
   }
   if (tid == 0 && nrows) nrows[0] = run_r;
   __threadfence_block();
+  if (in_smem && rowmap) {
+    // coalesced expansion of the row list: entry j belongs to the graph b with PR[b-1] <= j < PR[b]
+    const int total = run_r;
+    for (int j = tid; j < total; j += 1024) {
+      int lo = 0, hi = B - 1;                        // smallest b with PR[b] > j
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (PR[mid] > j) hi = mid; else lo = mid + 1;
+      }
+      rowmap[j] = lo * K + (j - (lo ? PR[lo - 1] : 0));
+    }
+  }
   for (int i = tid; i < B; i += 1024) {
     const int pn0 = i ? PN[i - 1] : 0, pk0 = i ? PK[i - 1] : 0;
     int j = i + 1;                                   // the first graph always fits (n_eff <= 128)
@@ -178,11 +194,61 @@ tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __re
     NX[i] = j;
   }
   __syncthreads();
+  if (!in_smem) {                                    // huge batch: serial walk over the jump table
+    if (tid == 0) {
+      int T = 0, i = 0;
+      while (i < B) { tiles[1 + T] = i; ++T; i = NX[i]; }
+      tiles[0] = T;
+      tiles[1 + T] = B;
+    }
+    return;
+  }
+  int32_t* Ja = NX;
+  int32_t* Jb = NX + (B + 1);
+  int32_t* MK = Jb + (B + 1);
+  for (int i = tid; i <= B; i += 1024) MK[i] = (i == 0) ? 1 : 0;
+  if (tid == 0) { Ja[B] = B; Jb[B] = B; }
+  __syncthreads();
+  for (int span = 1; span < B; span <<= 1) {
+    // starts fewer than `span` hops from graph 0 are marked; Ja = NX applied `span` times
+    for (int i = tid; i < B; i += 1024)
+      if (MK[i]) MK[Ja[i]] = 1;                      // late marks only add true starts (idempotent)
+    for (int i = tid; i < B; i += 1024) Jb[i] = Ja[Ja[i]];
+    __syncthreads();
+    int32_t* t = Ja; Ja = Jb; Jb = t;
+  }
+  // number the starts: exclusive prefix sum of the marks
+  if (tid == 0) run_n = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    const int m = (b < B) ? MK[b] : 0;
+    int in = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tn = __shfl_up_sync(0xffffffffu, in, o);
+      if (lane >= o) in += tn;
+    }
+    if (lane == 31) warp_n[warp] = in;
+    __syncthreads();
+    if (warp == 0) {
+      int wn = warp_n[lane], sn = wn;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tn = __shfl_up_sync(0xffffffffu, sn, o);
+        if (lane >= o) sn += tn;
+      }
+      warp_n[lane] = sn - wn;
+    }
+    __syncthreads();
+    if (m) tiles[1 + run_n + warp_n[warp] + in - 1] = b;
+    __syncthreads();
+    if (tid == 1023) run_n += warp_n[31] + in;
+    __syncthreads();
+  }
   if (tid == 0) {
-    int T = 0, i = 0;
-    while (i < B) { tiles[1 + T] = i; ++T; i = NX[i]; }
-    tiles[0] = T;
-    tiles[1 + T] = B;
+    tiles[0] = run_n;
+    tiles[1 + run_n] = B;
   }
 }
 
@@ -738,6 +804,7 @@ extern "C" {
 int lnb_debug_set_prof(unsigned long long* buf) {
   cudaError_t e = cudaMemcpyToSymbol(tcg::g_prof, &buf, sizeof(buf));
   if (e != cudaSuccess) { lnb::set_err("debug_set_prof: %s", cudaGetErrorString(e)); return (int)e; }
+  lnb::set_prof_buffer(buf);
   return LNB_OK;
 }
 
@@ -753,12 +820,15 @@ int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B
   cudaStream_t s = (cudaStream_t)stream;
   const size_t lbytes = (size_t)N * N * E1 * sizeof(float);
   const int stage = lbytes <= 64 * 1024;
-  if (stage && lbytes > 40 * 1024)
-    cudaFuncSetAttribute(graph_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbytes);
-  graph_prepare_kernel<<<B, 256, stage ? lbytes : 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max,
-                                                         gext, stage);
-  const size_t tbytes = (size_t)3 * B * sizeof(int32_t);
-  const int tsm = tbytes <= 160 * 1024;
+  if (stage) {
+    if (lbytes > 40 * 1024)
+      cudaFuncSetAttribute(graph_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbytes);
+    graph_prepare_kernel<true><<<B, 256, lbytes, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
+  } else {
+    graph_prepare_kernel<false><<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
+  }
+  const size_t tbytes = (size_t)6 * (B + 1) * sizeof(int32_t);
+  const int tsm = tbytes <= 200 * 1024;
   if (tsm && tbytes > 40 * 1024)
     cudaFuncSetAttribute(tile_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);
   tile_assign_kernel<<<1, 1024, tsm ? tbytes : 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows,
