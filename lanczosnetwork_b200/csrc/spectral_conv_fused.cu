@@ -117,10 +117,11 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
 // jumping (round k marks the starts 2^k .. 2^(k+1)-1 hops away and squares the jump table); a
 // prefix sum over the marks numbers the tiles.  The arrays live in shared memory (6 (B+1) ints);
 // batches too large for that use the global scratch and a serial walk.
+template <bool in_smem>
 __global__ void __launch_bounds__(1024)
 tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __restrict__ tiles,
                    int32_t* __restrict__ scratch /* [3 * B] */, int32_t* __restrict__ rowmap,
-                   int32_t* __restrict__ nrows, int in_smem) {
+                   int32_t* __restrict__ nrows) {
   extern __shared__ int32_t ta_smem[];
   __shared__ int warp_n[32], warp_k[32], warp_r[32];
   __shared__ int run_n, run_k, run_r;
@@ -175,15 +176,10 @@ tile_assign_kernel(const int32_t* __restrict__ gext, int B, int K, int32_t* __re
   if (tid == 0 && nrows) nrows[0] = run_r;
   __threadfence_block();
   if (in_smem && rowmap) {
-    // coalesced expansion of the row list: entry j belongs to the graph b with PR[b-1] <= j < PR[b]
-    const int total = run_r;
-    for (int j = tid; j < total; j += 1024) {
-      int lo = 0, hi = B - 1;                        // smallest b with PR[b] > j
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (PR[mid] > j) hi = mid; else lo = mid + 1;
-      }
-      rowmap[j] = lo * K + (j - (lo ? PR[lo - 1] : 0));
+    // coalesced expansion of the row list: a warp writes the k_eff consecutive entries of a graph
+    for (int b = warp; b < B; b += 32) {
+      const int base = b ? PR[b - 1] : 0, kr = PR[b] - base;
+      for (int i = lane; i < kr; i += 32) rowmap[base + i] = b * K + i;
     }
   }
   for (int i = tid; i < B; i += 1024) {
@@ -830,9 +826,11 @@ int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B
   const size_t tbytes = (size_t)6 * (B + 1) * sizeof(int32_t);
   const int tsm = tbytes <= 200 * 1024;
   if (tsm && tbytes > 40 * 1024)
-    cudaFuncSetAttribute(tile_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);
-  tile_assign_kernel<<<1, 1024, tsm ? tbytes : 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows,
-                                                      tsm);
+    cudaFuncSetAttribute(tile_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);
+  if (tsm)
+    tile_assign_kernel<true><<<1, 1024, tbytes, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
+  else
+    tile_assign_kernel<false><<<1, 1024, 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
   lnb::count_launch(2);
   return lnb::finish_launch("graph_prepare");
 }
