@@ -80,6 +80,15 @@ int lnb_batched_gemm(lnb_stream_t stream, const lnb_gemm_desc* desc /* host */);
 int lnb_split_tf32(lnb_stream_t stream, const float* x, int64_t n, float* hi, float* lo);
 int lnb_linear_tf32x3(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
                       const float* bias, int M, int N, int K, int relu, float* C);
+/* Split-K variant for few output tiles and a deep K (the 4096-wide learned filter MLP of
+ * model/ada_lanczos_net.py:54-63 at M = batch): every 128 x 128 output tile is computed by `splits`
+ * CTAs over disjoint K ranges, so 2 x 32 tiles fill 128 SMs instead of 64 and the weight stream uses
+ * the whole HBM bandwidth.  workspace: ceil(M/128)*ceil(N/128)*splits*128*128 floats; counters:
+ * ceil(M/128)*ceil(N/128) ints, zero on entry (the kernel leaves them zero). */
+int lnb_linear_tf32x3_splitk(lnb_stream_t stream, const float* A, const float* W_hi, const float* W_lo,
+                             const float* bias, int M, int N, int K, int relu, float* C, int splits,
+                             float* workspace, int* counters);
+
 /* Block-diagonal ("grouped") variant: C[:, g*N:(g+1)*N] = act(A[:, g*K:(g+1)*K] @ W_g^T + b_g)
  * with A [M, groups*K], W stacked [groups*N, K], bias [groups*N], C [M, groups*N].  Used to run
  * the per-layer Ritz-filter MLPs of all layers (model/lanczos_net.py:47-58,109-113) in one launch

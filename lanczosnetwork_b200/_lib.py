@@ -61,6 +61,9 @@ SIGNATURES = {
     'lnb_split_tf32': (c_int, [c_stream, c_f32p, c_i64, c_f32p, c_f32p]),
     'lnb_linear_tf32x3':
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p]),
+    'lnb_linear_tf32x3_splitk':
+        (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p, c_int,
+                 c_f32p, ctypes.c_void_p]),
     'lnb_linear_tf32x3_grouped':
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_graph_prepare': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p,

@@ -190,13 +190,43 @@ lanczos_cta_kernel(const float* __restrict__ A, const uint8_t* __restrict__ mask
   for (int i = 0; i < iters; ++i) {
     const float* qi = Qs + (int64_t)i * NP;
     const float* qp = i > 0 ? Qs + (int64_t)(i - 1) * NP : nullptr;
-    // z = A q_i : one warp per row, lanes stride the row (coalesced / conflict-free)
-    for (int r = warp; r < N; r += nwarps) {
-      const float* row = Aop + (int64_t)r * lda;
-      float s = 0.f;
-      for (int m = lane; m < N; m += 32) s = fmaf(row[m], qi[m], s);
-      s = lnb::warp_sum(s);
-      if (lane == 0) zs[r] = s;
+    if (!stage_A && (N & 3) == 0) {
+      // z = A q_i with the operator streamed from HBM / L2: a warp takes 4 rows at a time and
+      // reads them as 16-byte vectors, two column blocks in flight -> 4 KB of loads in flight per
+      // warp (the scalar row-at-a-time loop kept ~8 KB in flight per SM: latency bound at 18 % of HBM)
+      const float4* q4 = reinterpret_cast<const float4*>(qi);
+      const int nv = N >> 2;
+      for (int r0 = warp * 4; r0 < N; r0 += nwarps * 4) {
+        const float4* rows[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          rows[u] = reinterpret_cast<const float4*>(Ag + (int64_t)min(r0 + u, N - 1) * N);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int m = lane; m < nv; m += 32) {
+          const float4 q = q4[m];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 a = __ldcs(rows[u] + m);
+            s[u] = fmaf(a.x, q.x, s[u]); s[u] = fmaf(a.y, q.y, s[u]);
+            s[u] = fmaf(a.z, q.z, s[u]); s[u] = fmaf(a.w, q.w, s[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float t = lnb::warp_sum(s[u]);
+          if (lane == 0 && r0 + u < N) zs[r0 + u] = t;
+        }
+      }
+    } else {
+      // z = A q_i : one warp per row, lanes stride the row (coalesced / conflict-free)
+      for (int r = warp; r < N; r += nwarps) {
+        const float* row = Aop + (int64_t)r * lda;
+        float s = 0.f;
+        for (int m = lane; m < N; m += 32) s = fmaf(row[m], qi[m], s);
+        s = lnb::warp_sum(s);
+        if (lane == 0) zs[r] = s;
+      }
     }
     __syncthreads();
     part = 0.f;

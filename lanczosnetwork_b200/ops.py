@@ -95,11 +95,49 @@ def linear_tf32x3(x, w_hi, w_lo, bias=None, relu=False, out=None):
   N = w_hi.shape[0]
   if out is None:
     out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+  tiles = ((M + 127) // 128) * ((N + 127) // 128)
+  nkb = (K + 31) // 32
+  splits = 1
+  if tiles * 2 <= _sm_count(x.device) and nkb >= 32:
+    # few output tiles, deep K (the Ada filter MLP): split K so every SM streams weights
+    splits = min(_sm_count(x.device) // tiles, 8, nkb // 16)
+    while splits > 1 and ((nkb + splits - 1) // splits) * (splits - 1) >= nkb:
+      splits -= 1
   with torch.cuda.device(x.device):
-    _lib.check(_lib.load().lnb_linear_tf32x3(_stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo),
-                                             _ptr(bias), M, N, K, int(bool(relu)), _ptr(out)),
-               'lnb_linear_tf32x3')
+    if splits > 1:
+      ws, counters = _splitk_workspace(x.device, tiles * splits * 128 * 128, tiles)
+      _lib.check(_lib.load().lnb_linear_tf32x3_splitk(
+          _stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo), _ptr(bias), M, N, K, int(bool(relu)),
+          _ptr(out), splits, _ptr(ws), _ptr(counters)), 'lnb_linear_tf32x3_splitk')
+    else:
+      _lib.check(_lib.load().lnb_linear_tf32x3(_stream(x), _ptr(x), _ptr(w_hi), _ptr(w_lo),
+                                               _ptr(bias), M, N, K, int(bool(relu)), _ptr(out)),
+                 'lnb_linear_tf32x3')
   return out
+
+
+_SPLITK_WS = {}
+_SM_COUNT = {}
+
+
+def _sm_count(device):
+  idx = device.index if device.index is not None else torch.cuda.current_device()
+  if idx not in _SM_COUNT:
+    _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+  return _SM_COUNT[idx]
+
+
+def _splitk_workspace(device, nfloats, ntiles):
+  """Per-device split-K scratch: partial tiles + per-tile arrival counters (zero between launches;
+  launches on one stream are ordered, so one buffer per device and stream is enough)."""
+  key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+  ws, counters = _SPLITK_WS.get(key, (None, None))
+  if ws is None or ws.numel() < nfloats or counters.numel() < ntiles:
+    ws = torch.empty((max(nfloats, ws.numel() if ws is not None else 0),), device=device,
+                     dtype=torch.float32)
+    counters = torch.zeros((max(ntiles, 256),), device=device, dtype=torch.int32)
+    _SPLITK_WS[key] = (ws, counters)
+  return ws, counters
 
 
 def linear_tf32x3_grouped(x, w_hi, w_lo, bias, groups, relu=False):

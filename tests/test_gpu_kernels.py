@@ -123,7 +123,8 @@ def test_bgemm_bias_relu_edges(M, N, K):
 @pytest.mark.parametrize('M,N,K,relu', [(128, 128, 32, False), (300, 128, 1920, True),
                                         (26624, 128, 960, True), (1000, 2000, 512, False),
                                         (77, 8, 128, False), (2048, 128, 8, True),
-                                        (64, 4096, 2000, True), (5, 40, 100, False)])
+                                        (64, 4096, 2000, True), (5, 40, 100, False),
+                                        (256, 4096, 4096, True), (130, 520, 3204, False)])
 def test_linear_tf32x3_fp32_grade(M, N, K, relu):
   g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
   x = torch.randn(M, K, generator=g).to(dev())
@@ -134,6 +135,8 @@ def test_linear_tf32x3_fp32_grade(M, N, K, relu):
   assert torch.equal(w_hi.view(torch.int32) & 0x1FFF, torch.zeros_like(w_hi, dtype=torch.int32))
   assert (w - (w_hi + w_lo)).abs().max() <= 2.0 ** -21 * w.abs().max()
   out = ops().linear_tf32x3(x, w_hi, w_lo, b, relu)
+  # deep K with few output tiles runs split-K: a second call must find its counters at zero
+  assert torch.equal(out, ops().linear_tf32x3(x, w_hi, w_lo, b, relu))
   ref = x.double() @ w.double().t() + b.double()
   if relu:
     ref = torch.relu(ref)
