@@ -260,8 +260,11 @@ def main():
     else:
       max_err = None
 
-    for i in range(args.warmup):
+    # every resident batch is seen twice before timing: the second sighting of a set of device
+    # buffers is when the module captures its zero-copy graph for them
+    for i in range(max(args.warmup, 2 * NUM_BATCHES)):
       step_resident(i)
+    for i in range(args.warmup):
       step_e2e(i)
     sampler = ClockSampler(local)
     sampler.start()
@@ -342,7 +345,7 @@ def main():
                              'batch=%d per GPU, N=26 padded, 7 layers, fp32 (3xTF32 tensor cores)' % B,
                  'global_batch': B * world, 'parallelism': 'dp%d' % world,
                  'cache': 'inputs larger than L2: %d distinct resident batches rotated '
-                          '(%.0f MB) + >200 MB of per-layer message buffers' %
+                          '(%.0f MB > 126 MB L2), each copied into the CUDA graph\'s static input buffers' %
                           (NUM_BATCHES, NUM_BATCHES * h2d_bytes / 1e6)},
       'e2e': {'value': e2e_value, 'unit': 'molecules/s', 'h2d_bytes_per_step': h2d_bytes,
               'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},

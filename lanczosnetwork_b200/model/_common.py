@@ -141,6 +141,38 @@ class SpectralNetBase(nn.Module):
     entry = cache.get(key)
     sig = self._param_signature()
     cur = torch.cuda.current_stream(dev)
+    # Inputs already resident on this device: a graph bound to their addresses needs no copy at
+    # all.  Such a graph is captured the second time the same buffers show up (data loaders /
+    # serving loops that recycle a few device buffers); any live tensor found at a captured
+    # address with the captured shape and dtype is read correctly, so no reference is kept.
+    if all(t is None or (t.is_cuda and t.device == dev and t.is_contiguous()) for t in inputs):
+      pkey = key + tuple(None if t is None else t.data_ptr() for t in inputs)
+      zc = self.__dict__.setdefault('_graphs_resident', {})
+      hit = zc.get(pkey)
+      if hit is not None and hit['sig'] == sig:
+        hit['graph'].replay()
+        _lib.note_graph_replay(hit['kernels'])
+        return hit['out'].clone()
+      seen = self.__dict__.setdefault('_resident_seen', {})
+      if len(seen) > 256:
+        seen.clear()
+      seen[pkey] = seen.get(pkey, 0) + 1
+      if seen[pkey] >= 2 and entry is not None and entry['sig'] == sig:   # caches are warm
+        if len(zc) >= 16:
+          zc.pop(next(iter(zc)))
+        if '_resident_pool' not in self.__dict__:
+          self._resident_pool = torch.cuda.graph_pool_handle()
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        n0 = int(_lib.load().lnb_launch_count())
+        with torch.cuda.graph(graph, pool=self._resident_pool):
+          out = impl(*inputs)
+        hit = {'graph': graph, 'out': out, 'sig': sig,
+               'kernels': int(_lib.load().lnb_launch_count()) - n0}
+        zc[pkey] = hit
+        graph.replay()
+        _lib.note_graph_replay(hit['kernels'])
+        return out.clone()
     if entry is None or entry['sig'] != sig:
       slots = []
       for _ in range(2):
