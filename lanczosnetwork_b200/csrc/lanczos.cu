@@ -401,21 +401,24 @@ lanczos_resident_kernel(const float* __restrict__ A, const uint8_t* __restrict__
     // z_r = sum_c A[r][c] q[c]
     float z = 0.f;
     {
+      // four independent partial sums: one accumulator would be a 128-deep dependent FMA chain
+      float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
       const float4* q4 = reinterpret_cast<const float4*>(qs + p * CW);
 #pragma unroll
       for (int c = 0; c < CR / 4; ++c) {
         const float4 v = q4[c];
-        z = fmaf(a[4 * c + 0], v.x, z); z = fmaf(a[4 * c + 1], v.y, z);
-        z = fmaf(a[4 * c + 2], v.z, z); z = fmaf(a[4 * c + 3], v.w, z);
+        z0 = fmaf(a[4 * c + 0], v.x, z0); z1 = fmaf(a[4 * c + 1], v.y, z1);
+        z2 = fmaf(a[4 * c + 2], v.z, z2); z3 = fmaf(a[4 * c + 3], v.w, z3);
       }
       if (CS) {
         const float4* a4 = reinterpret_cast<const float4*>(As + (size_t)t * ASP);
 #pragma unroll 4
         for (int c = 0; c < CS / 4; ++c) {
           const float4 v = q4[CR / 4 + c], w = a4[c];
-          z = fmaf(w.x, v.x, z); z = fmaf(w.y, v.y, z); z = fmaf(w.z, v.z, z); z = fmaf(w.w, v.w, z);
+          z0 = fmaf(w.x, v.x, z0); z1 = fmaf(w.y, v.y, z1); z2 = fmaf(w.z, v.z, z2); z3 = fmaf(w.w, v.w, z3);
         }
       }
+      z = (z0 + z1) + (z2 + z3);
 #pragma unroll
       for (int o = 1; o < TPR; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
     }
@@ -434,7 +437,16 @@ lanczos_resident_kernel(const float* __restrict__ A, const uint8_t* __restrict__
           if (lane == 0) cs[j] = sdot / (qq[j] + kEps);
         }
         group_bar<TPG>(grp);
-        for (int j = 0; j < i; ++j) z -= cs[j] * Qs[(size_t)j * NP + r];
+        {
+          float d0 = 0.f, d1 = 0.f;                  // two chains instead of one of length i
+          int j = 0;
+          for (; j + 1 < i; j += 2) {
+            d0 = fmaf(cs[j], Qs[(size_t)j * NP + r], d0);
+            d1 = fmaf(cs[j + 1], Qs[(size_t)(j + 1) * NP + r], d1);
+          }
+          if (j < i) d0 = fmaf(cs[j], Qs[(size_t)j * NP + r], d0);
+          z -= d0 + d1;
+        }
       }
     }
     const float beta = sqrtf(group_sum<TPG>(own * z * z, red, flip, grp, wg, lane));

@@ -11,7 +11,7 @@
 namespace {
 
 struct RowLoadPolicy {
-  static constexpr int kStagesB = 3;
+  static constexpr int kStagesB = 6;      // 192 KB of W tiles in flight per SM: the weight stream of a deep, narrow GEMM is HBM latency x bandwidth bound
   // groups > 1: block-diagonal ("grouped") layer -- column block g of A [M, groups*K] times
   // W_g [N, K] (stacked [groups*N, K]) into column block g of C [M, groups*N].
   struct Params {

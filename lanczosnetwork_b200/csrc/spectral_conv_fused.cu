@@ -31,7 +31,8 @@ constexpr int FR = 8;           // filter coefficients held in registers per row
 // --------------------------------------------------------------------------------------------
 // Per-forward operator compression and extents.
 //   ell_val/ell_idx [B, E1, N(t), N(n)]: the t-th non-zero of row n of channel e (t-major so a
-//   warp of consecutive rows reads consecutive addresses); ell_max[b,e] = max non-zeros per row.
+//   warp of consecutive rows reads consecutive addresses; the diagonal entry first, then by
+//   column); ell_max[b,e] = max non-zeros per row.
 //   gext[b] = {n_eff, k_eff}: the operators are zero outside their leading n_eff rows/columns,
 //   Q[b] is zero outside its leading n_eff rows / k_eff columns.
 // --------------------------------------------------------------------------------------------
@@ -69,14 +70,23 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
     float* val = ell_val + ((int64_t)(b * E1 + e) * N) * N + n;
     uint8_t* idx = ell_idx + ((int64_t)(b * E1 + e) * N) * N + n;
     int cnt = 0, far = 0;
+    // the diagonal entry goes first: consecutive rows then gather consecutive rows of X for
+    // entry 0 (conflict-free in the fused kernel), the other entries follow in column order
+    const float dg = row[n * E1];
+    if (dg != 0.f) {
+      val[0] = dg;
+      idx[0] = (uint8_t)n;
+      cnt = 1;
+      far = n + 1;
+    }
 #pragma unroll 2
     for (int i = 0; i < N; ++i) {
       const float v = row[i * E1];
-      if (v != 0.f) {
+      if (v != 0.f && i != n) {
         val[cnt * N] = v;
         idx[cnt * N] = (uint8_t)i;
         ++cnt;
-        far = i + 1;
+        far = max(far, i + 1);
       }
     }
     cnt_s[p] = (uint8_t)cnt;

@@ -32,7 +32,7 @@ constexpr int COL_MAIN = 0, COL_CORR = 128, COL_A = 256;   // A stage s: COL_A +
 constexpr int PRODUCER_THREADS = 128 * NGROUPS;
 constexpr int TMA_WARP = 4 * NGROUPS, MMA_WARP = 4 * NGROUPS + 1;
 constexpr int THREADS = PRODUCER_THREADS + 64;
-constexpr int MAX_B_STAGES = 3;
+constexpr int MAX_B_STAGES = 6;
 // shared memory of the skeleton: W ring (Policy::kStagesB stages) + barriers / TMEM holder
 __host__ __device__ constexpr int core_smem(int stages_b) { return stages_b * STAGE_B_BYTES + 256; }
 
@@ -86,7 +86,7 @@ __device__ __forceinline__ void producers_sync() {   // named barrier 1: all pro
 
 // Policy contract (all __device__).  A "step" is one accumulator lifetime: its k-blocks are
 // produced / multiplied, then the epilogue hands the 128 x 128 result to the policy.
-//   static constexpr int kStagesB                        depth of the W (shared memory) ring: 2 or 3
+//   static constexpr int kStagesB                        depth of the W (shared memory) ring: 2 .. 6
 //   struct Params;                                       kernel parameter block (by value)
 //   static int  num_steps(const Params&, int cta, int ncta)       steps this CTA runs
 //   static void decode(const Params&, int cta, int ncta, int it, int& m_tile, int& sub)
