@@ -382,12 +382,20 @@ struct SpectralPolicy {
     const int Rtot = __shfl_sync(0xffffffffu, pn, 31), Ztot = __shfl_sync(0xffffffffu, pk, 31);
     const int nquads = __shfl_sync(0xffffffffu, pq, 31);
     // per-channel maximum row length over the tile's graphs, per-graph row lengths
-    for (int e = 0; e < E1; ++e) {
-      int m = (lane < ng) ? __ldg(p.ell_max + (gs + lane) * E1 + e) : 0;
-      if (lane < ng) tb->emax[lane][e] = (uint8_t)m;
+    // (all loads issued before the first reduction: one global round trip instead of E1)
+    int em[EMAX];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) tb->tmax_e[e] = m;
+    for (int e = 0; e < EMAX; ++e)
+      em[e] = (e < E1 && lane < ng) ? __ldg(p.ell_max + (gs + lane) * E1 + e) : 0;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      if (e < E1) {
+        int m = em[e];
+        if (lane < ng) tb->emax[lane][e] = (uint8_t)m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) tb->tmax_e[e] = m;
+      }
     }
     __syncwarp();
     if (lane == 0) {
@@ -434,9 +442,9 @@ struct SpectralPolicy {
       }
       float* xd = Xs + (size_t)row * XP;
       for (int q4 = lane; q4 < dv; q4 += 32) tc05::cp_async_16(xd + 4 * q4, xsrc + 4 * q4);
-      const float* qsrc = p.Q + src_row * K;
+      const float* qsrc = p.Q + src_row * K;            // K % 4 == 0: 16-byte pieces
       float* qd = Qs + (size_t)row * K;
-      for (int k = lane; k < K; k += 32) tc05::cp_async_4(qd + k, qsrc + k);
+      for (int k4 = lane; k4 < (K >> 2); k4 += 32) tc05::cp_async_16(qd + 4 * k4, qsrc + 4 * k4);
     }
     // ---- staged ELL lines: line l <-> (channel e, entry t); a warp per line, batched loads ---
     {
@@ -775,12 +783,13 @@ struct SpectralPolicy {
             }
         }
       }
-      if (warp == 0) {                               // the constant padded-node row
-        for (int o = lane; o < P1; o += 32) {
-          float acc = 0.f;
-          for (int h = 0; h < H; ++h) acc = fmaf(cx[h], Wr[o * HP + h], acc);
-          Yr[RMAX * P1 + o] = acc + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
-        }
+      // the constant padded-node row: one warp per output, lanes stride the H features
+      for (int o = warp; o < P1; o += tcg::PRODUCER_THREADS / 32) {
+        float acc = 0.f;
+        for (int h = lane; h < H; h += 32) acc = fmaf(cx[h], Wr[o * HP + h], acc);
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+        if (lane == 0) Yr[RMAX * P1 + o] = acc + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
       }
     }
     tcg::producers_sync();
@@ -868,8 +877,9 @@ static int launch_stack(lnb_stream_t stream, const lnb_spectral_stack& d, const 
                  KMAX, EMAX);
     return LNB_ERR_UNSUPPORTED;
   }
-  if (d.bias && (reinterpret_cast<uintptr_t>(d.bias) & 15)) {
-    lnb::set_err("%s: bias must be 16-byte aligned", who);
+  if ((d.bias && (reinterpret_cast<uintptr_t>(d.bias) & 15)) || (reinterpret_cast<uintptr_t>(d.Q) & 15) ||
+      (d.X && (reinterpret_cast<uintptr_t>(d.X) & 15)) || (d.emb_table && (reinterpret_cast<uintptr_t>(d.emb_table) & 15))) {
+    lnb::set_err("%s: X / emb_table / Q / bias must be 16-byte aligned", who);
     return LNB_ERR_ARG;
   }
   if (d.B == 0) return LNB_OK;
