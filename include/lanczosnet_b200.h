@@ -238,8 +238,8 @@ int lnb_tridiag_powers(lnb_stream_t stream, const float* T, int B, int K, const 
 int lnb_symmetrize_filters(lnb_stream_t stream, const float* Y, int B, int K, int S,
                            float* G /* [B,S,K,K] */);
 
-/* Profiling aid (not used by the product path): register a device buffer of 148*8 uint64 that
- * the fused convolution kernel fills with per-CTA clock64 totals per phase; NULL disables. */
+/* Profiling aid (not used by the product path): register a device buffer of (number of SMs) x 32 uint64 that
+ * the tcgen05 kernels fill with per-CTA clock64 totals per phase; NULL disables. */
 int lnb_debug_set_prof(unsigned long long* buf);
 
 #ifdef __cplusplus

@@ -333,6 +333,7 @@ struct SpectralPolicy {
   float* Ev;                // [LB][RMAX] staged ELL values
   uint8_t* Ei;              // [LB][RMAX] staged ELL columns as tile-local row indices
   float fr[FR];             // this (graph, k) row's filter coefficients f[k, 0..S)
+  tcg::PhaseTimer* ptm = nullptr;   // profiling aid: the current step's timer
 
   static __host__ __device__ constexpr size_t tables_bytes() { return (sizeof(Tables) + 15) & ~size_t(15); }
 
@@ -420,9 +421,11 @@ struct SpectralPolicy {
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = tcg::PRODUCER_THREADS / 32;
     const int dv = Din / 4;
+    ptm = &tm;
     if (layer == 0) {
     if (warp == 0) build_tables(m_tile);
     tcg::producers_sync();
+    tm.lap(16);
     const int gs = tb->gs, Rtot = tb->Rtot;
     // ---- phase A: asynchronous copies of the real rows of X and Q (one warp per row) --------
     int64_t my_id = 0;                           // lane j: embedding id of this warp's j-th row
@@ -446,6 +449,7 @@ struct SpectralPolicy {
       float* qd = Qs + (size_t)row * K;
       for (int k4 = lane; k4 < (K >> 2); k4 += 32) tc05::cp_async_16(qd + 4 * k4, qsrc + 4 * k4);
     }
+    tm.lap(17);
     // ---- staged ELL lines: line l <-> (channel e, entry t); a warp per line, batched loads ---
     {
       constexpr int ELL_BATCH = 4;
@@ -480,6 +484,7 @@ struct SpectralPolicy {
         }
       }
     }
+    tm.lap(18);
     }  // layer == 0: tile state staged once, reused by every layer
     const int gs = tb->gs, Ztot = tb->Ztot;
     // this thread's (graph, k) row: filter coefficients of this layer into registers
@@ -698,6 +703,7 @@ struct SpectralPolicy {
   __device__ void post_epilogue(int sub) {
     if ((sub & 1) == 0 || (sub >> 1) != p.L - 1) return;
     tcg::producers_sync();              // every chunk of every row is in shared memory
+    if (ptm) ptm->lap(19);
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int NW = tcg::PRODUCER_THREADS / 32;
     const int hv = H / 4, gs = tb->gs, Rtot = tb->Rtot;
@@ -747,7 +753,11 @@ struct SpectralPolicy {
       float t = bias_last ? __ldg(bias_last + h) : 0.f;
       cx[h] = (p.relu != 0) ? fmaxf(t, 0.f) : t;
     }
+    uint8_t* mk = reinterpret_cast<uint8_t*>(cx + H);   // [ng][N] node masks of the tile's graphs
+    for (int e = tid; e < tb->ng * N; e += tcg::PRODUCER_THREADS)
+      mk[e] = p.mask ? __ldg(p.mask + (int64_t)tb->gs * N + e) : (uint8_t)1;
     tcg::producers_sync();
+    if (ptm) ptm->lap(20);
     const int Rtot = tb->Rtot;
     // warp <-> (block of 32 rows, third of the outputs): lane = row, so the row loads are
     // conflict-free and every weight load is one broadcast wavefront
@@ -762,7 +772,7 @@ struct SpectralPolicy {
         const int cnt = min(6, o_end - o0);
         const float4* w4 = reinterpret_cast<const float4*>(Wr + (size_t)o0 * HP);
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 4
         for (int h4 = 0; h4 < H / 4; ++h4) {
           const float4 x = x4[h4];
 #pragma unroll
@@ -779,7 +789,8 @@ struct SpectralPolicy {
           for (int j = 0; j < 6; ++j)
             if (j < cnt) {
               const int o = o0 + j;
-              Yr[row * P1 + o] = acc[j] + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+              const float v = acc[j] + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+              Yr[row * P1 + o] = (o < P) ? v : 1.f / (1.f + expf(-v));     // column P: the gate
             }
         }
       }
@@ -789,21 +800,24 @@ struct SpectralPolicy {
         for (int h = lane; h < H; h += 32) acc = fmaf(cx[h], Wr[o * HP + h], acc);
 #pragma unroll
         for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-        if (lane == 0) Yr[RMAX * P1 + o] = acc + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+        if (lane == 0) {
+          const float v = acc + ((o < P) ? __ldg(p.b_out + o) : __ldg(p.b_att));
+          Yr[RMAX * P1 + o] = (o < P) ? v : 1.f / (1.f + expf(-v));
+        }
       }
     }
     tcg::producers_sync();
+    if (ptm) ptm->lap(21);
     for (int e = tid; e < tb->ng * P; e += tcg::PRODUCER_THREADS) {
       const int g = e / P, o = e - g * P;
       const int nb = tb->nbase[g], n_g = tb->gn[g];
-      const uint8_t* m = p.mask ? p.mask + (int64_t)(tb->gs + g) * N : nullptr;
+      const uint8_t* m = mk + g * N;
       float acc = 0.f;
       int cnt = 0;
       for (int n = 0; n < N; ++n) {
-        if (m && m[n] == 0) continue;
+        if (m[n] == 0) continue;
         const float* y = Yr + (n < n_g ? nb + n : RMAX) * P1;
-        const float gate = 1.f / (1.f + expf(-y[P]));
-        acc += gate * y[o];
+        acc += y[P] * y[o];
         ++cnt;
       }
       p.score[(int64_t)(tb->gs + g) * P + o] = acc / (float)cnt;
@@ -815,7 +829,7 @@ struct SpectralPolicy {
 
 extern "C" {
 
-// profiling aid: register (or clear with NULL) a device buffer of 148*8 uint64 phase timers
+// profiling aid: register (or clear with NULL) a device buffer of SMs x 32 uint64 phase timers
 int lnb_debug_set_prof(unsigned long long* buf) {
   cudaError_t e = cudaMemcpyToSymbol(tcg::g_prof, &buf, sizeof(buf));
   if (e != cudaSuccess) { lnb::set_err("debug_set_prof: %s", cudaGetErrorString(e)); return (int)e; }

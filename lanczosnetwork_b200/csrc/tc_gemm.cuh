@@ -62,7 +62,7 @@ __device__ __forceinline__ Core carve(uint8_t* base, int stages_b) {
 }
 
 // Optional phase timers (profiling aid): when a buffer is registered with lnb_debug_set_prof,
-// thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*16 + phase]
+// thread 0 of every CTA accumulates clock64() deltas per phase into prof[cta*32 + phase]
 // (slots 8 / 9: k-loop / accumulator wait of odd sub-steps, 10: post_epilogue):
 //   0 staging issue  1 staging wait  2 U = V^T X   (policy)   3 k-loop  4 pre_epilogue
 //   5 wait for the accumulator  6 tcgen05.ld  7 epilogue store
@@ -72,7 +72,7 @@ struct PhaseTimer {          // thread 0 of the CTA only; no-op unless a buffer 
   unsigned long long* buf;
   long long t0;
   __device__ __forceinline__ void start(int cta, int tid) {
-    buf = (tid == 0 && g_prof) ? g_prof + cta * 16 : nullptr;
+    buf = (tid == 0 && g_prof) ? g_prof + cta * 32 : nullptr;
     if (buf) t0 = clock64();
   }
   __device__ __forceinline__ void lap(int slot) {
@@ -282,9 +282,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
   if (tid == 0 && g_prof) {
     unsigned long long ns1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
-    atomicAdd(&g_prof[cta * 16 + 11], ns1 - prof_ns0);
-    atomicAdd(&g_prof[cta * 16 + 12], (unsigned long long)(clock64() - prof_c0));
-    g_prof[cta * 16 + 13] = prof_ns0;               // CTA start (ns), for launch skew
+    atomicAdd(&g_prof[cta * 32 + 11], ns1 - prof_ns0);
+    atomicAdd(&g_prof[cta * 32 + 12], (unsigned long long)(clock64() - prof_c0));
+    g_prof[cta * 32 + 13] = prof_ns0;               // CTA start (ns), for launch skew
   }
 }
 

@@ -168,9 +168,19 @@ def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates():
     mod.use_cuda_graph = False
     eager = mod(*args, mask=mask)
     mod.use_cuda_graph = True
-    first = mod(*args, mask=mask)          # capture
-    replay = mod(*args, mask=mask)         # replay
-    assert torch.equal(eager, first) and torch.equal(eager, replay)
+    first = mod(*args, mask=mask)          # capture (two static-buffer slots)
+    replay = mod(*args, mask=mask)         # second sighting of these device buffers: zero-copy graph
+    third = mod(*args, mask=mask)          # replay of the zero-copy graph
+    assert torch.equal(eager, first) and torch.equal(eager, replay) and torch.equal(eager, third)
+    assert len(mod._graphs_resident) == 1
+    # new content in the same buffers is picked up by the address-bound graph
+    saved = args[1].clone()
+    args[1].mul_(0.5)
+    changed = mod(*args, mask=mask)
+    mod.use_cuda_graph = False
+    assert torch.equal(changed, mod(*args, mask=mask)) and not torch.equal(changed, eager)
+    mod.use_cuda_graph = True
+    args[1].copy_(saved)
     # host (pinned) inputs go straight into the static buffers
     host = [_t(g[k]).pin_memory() for k in ('node_feat', 'L', 'D', 'V')]
     assert torch.equal(mod(*host, mask=_t(g['node_mask']).pin_memory()), eager)

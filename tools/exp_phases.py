@@ -26,7 +26,7 @@ def run(flag):
   for _ in range(2):
     ops.spectral_conv_fused(X, V, coeff, prep, w_hi, w_lo, bias, True)
   torch.cuda.synchronize()
-  prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+  prof = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
   _lib.check(_lib.load().lnb_debug_set_prof(ctypes.c_void_p(prof.data_ptr())), 'set_prof')
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   a.record()
@@ -34,7 +34,7 @@ def run(flag):
   b.record()
   torch.cuda.synchronize()
   _lib.load().lnb_debug_set_prof(None)
-  p = prof.cpu().reshape(148, 16).double()
+  p = prof.cpu().reshape(148, 32).double()
   names = ['stage issue', 'stage wait', 'U', 'k-loop s0', 'pre_epi', 'acc wait s0', 'tmem ld', 'store', 'k-loop s1', 'acc wait s1']
   print('LNB_DBG=%d kernel %.1f us; per-CTA clock64 totals (cycles), CTAs 0..3 and mean over CTAs with 2 tiles:' % (flag, a.elapsed_time(b) * 1e3))
   for i in range(10):

@@ -18,7 +18,7 @@ mod.use_cuda_graph = False
 B = int(sys.argv[1]) if len(sys.argv) > 1 else bench.BATCH
 b = bench.make_batches(1, B, 1000)[0]
 t = {k: torch.from_numpy(b[k]).to(dev) for k in ('node_feat', 'L', 'D', 'V', 'node_mask')}
-prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+prof = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
 lib = _lib.load()
 orig = ops.spectral_stack_forward
 times = []
@@ -44,12 +44,14 @@ with torch.no_grad():
   prof.zero_()
   mod(t['node_feat'], t['L'], t['D'], t['V'], mask=t['node_mask'])
   ops.spectral_stack_forward = orig
-p = prof.cpu().reshape(148, 16).double()
+p = prof.cpu().reshape(148, 32).double()
 names = ['stage issue', 'stage wait', 'U', 'k-loop s0', 'pre_epi', 'acc wait s0', 'tmem ld', 'store',
          'k-loop s1', 'acc wait s1', 'post_epi']
 print('stack kernel %.1f us (with timers); clock64 totals per CTA (cycles)' % times[-1])
 for i in range(11):
   print('  %-12s cta0 %8d cta1 %8d cta100 %8d  mean %8d  max %8d' % (names[i], p[0, i], p[1, i], p[100, i], p[:, i].mean(), p[:, i].max()))
+for i, nm in [(16, 'stage: tables'), (17, 'stage: X/Q issue'), (18, 'stage: ELL lines'), (19, 'readout: wait'), (20, 'readout: W stage'), (21, 'readout: dots')]:
+  print('  %-18s mean %8d  max %8d' % (nm, p[:, i].mean(), p[:, i].max()))
 print('  sum cta0 %d, mean %d, max %d' % (p[0, :11].sum(), p[:, :11].sum(1).mean(), p[:, :11].sum(1).max()))
 act = p[:, 12] > 0
 print('  active CTAs %d; whole-CTA ns: mean %.0f max %.0f; cycles mean %.0f max %.0f; => %.3f GHz; start skew %.0f ns; first start->last end %.0f ns' % (
