@@ -188,19 +188,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       tc05::mbar_wait(c.acc_full, (uint32_t)it & 1u);
       tc05::fence_after_thread_sync();
       tm.lap((sub & 1) ? 9 : 5);
-#pragma unroll 1
-      for (int cc = grp; cc < BN / EW; cc += NGROUPS) {   // 8 units over 3 groups: 3 / 3 / 2
-        const int col = cc * EW;
+      {
+        // 8 units over 3 groups (3 / 3 / 2); the loads of the next unit are in flight while the
+        // current one is stored (tcgen05.wait::ld waits for everything issued so far)
         uint32_t vm[EW], vc[EW];
-        tc05::tmem_ld_32x16(lane_addr + COL_MAIN + col, vm);
-        tc05::tmem_ld_32x16(lane_addr + COL_CORR + col, vc);
+        tc05::tmem_ld_32x16(lane_addr + COL_MAIN + grp * EW, vm);
+        tc05::tmem_ld_32x16(lane_addr + COL_CORR + grp * EW, vc);
         tc05::tmem_wait_ld();
-        tm.lap(6);
-        float x[EW];
+#pragma unroll 1
+        for (int cc = grp; cc < BN / EW; cc += NGROUPS) {
+          const int col = cc * EW;
+          float x[EW];
 #pragma unroll
-        for (int j = 0; j < EW; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
-        pol.store(sub, col, x);
-        tm.lap(7);
+          for (int j = 0; j < EW; ++j) x[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+          if (cc + NGROUPS < BN / EW) {
+            tc05::tmem_ld_32x16(lane_addr + COL_MAIN + col + NGROUPS * EW, vm);
+            tc05::tmem_ld_32x16(lane_addr + COL_CORR + col + NGROUPS * EW, vc);
+          }
+          tm.lap(6);
+          pol.store(sub, col, x);
+          tc05::tmem_wait_ld();
+          tm.lap(7);
+        }
       }
       tc05::fence_before_thread_sync();
       __syncwarp();
