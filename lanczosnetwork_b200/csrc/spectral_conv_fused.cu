@@ -50,20 +50,27 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
   if (tid < 2) s_ext[tid] = 0;
   const int64_t per = (int64_t)N * N * E1;
   const float* Lg = L + b * per;
-  if (STAGE) {                                         // coalesced copy, then strided reads hit smem
+  if (STAGE) {                                         // coalesced async copy; strided reads then hit smem
     if ((per & 3) == 0) {
-      const float4* src = reinterpret_cast<const float4*>(Lg);
-      float4* dst = reinterpret_cast<float4*>(gp_smem);
-      for (int i = tid; i < (int)(per >> 2); i += 256) dst[i] = __ldg(src + i);
+      for (int i = tid; i < (int)(per >> 2); i += 256) tc05::cp_async_16(gp_smem + 4 * i, Lg + 4 * i);
     } else {
-      for (int i = tid; i < (int)per; i += 256) gp_smem[i] = __ldg(Lg + i);
+      for (int i = tid; i < (int)per; i += 256) tc05::cp_async_4(gp_smem + i, Lg + i);
     }
   }
   const float* Lb = STAGE ? gp_smem : Lg;
+  // extents of Q while the operator copy is in flight
+  const float* Qb = Q + (int64_t)b * N * K;
+  int ne = 0, ke = 0;
+  for (int i = tid; i < N * K; i += 256) {
+    if (__ldg(Qb + i) != 0.f) {
+      ne = max(ne, i / K + 1);
+      ke = max(ke, i % K + 1);
+    }
+  }
+  if (STAGE) tc05::cp_async_wait_all();
   __syncthreads();
   const int pairs = N * E1;
   // thread <-> (row n, channel e), p = n*E1 + e: one pass over the row, compacting as it goes
-  int ne = 0, ke = 0;
   for (int p = tid; p < pairs; p += 256) {
     const int n = p / E1, e = p - n * E1;
     const float* row = Lb + (n * N) * E1 + e;
@@ -93,13 +100,6 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
     if (cnt) {
       atomicMax(&s_max[e], cnt);
       ne = max(ne, max(n + 1, far));
-    }
-  }
-  const float* Qb = Q + (int64_t)b * N * K;
-  for (int i = tid; i < N * K; i += 256) {
-    if (Qb[i] != 0.f) {
-      ne = max(ne, i / K + 1);
-      ke = max(ke, i % K + 1);
     }
   }
   if (ne) atomicMax(&s_ext[0], ne);
