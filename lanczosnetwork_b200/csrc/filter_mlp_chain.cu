@@ -388,9 +388,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb, ++G) {
           const uint32_t Wg = Wp + w.kb_before(s) + kb;
           const uint32_t st = Wg % NSTB, slot = G % NSLOT;
-          tc05::mbar_wait(&b_full[st], (Wg / NSTB) & 1u);
-          if (prof) { t1 = clock64(); pt[1] += t1 - t0; if (s < 3) pw[kb & 3] += t1 - t0; t0 = t1; }
-          tc05::mbar_wait(&a_full[slot], (G / NSLOT) & 1u);
+          tc05::mbar_wait2(&b_full[st], (Wg / NSTB) & 1u, &a_full[slot], (G / NSLOT) & 1u);
           tc05::fence_after_thread_sync();
           if (prof) { t1 = clock64(); pt[2] += t1 - t0; if (s < 3) pa[kb & 3] += t1 - t0; t0 = t1; }
           if (tc05::elect_one()) {

@@ -41,6 +41,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Wait for two barriers; the two polls are issued back to back so their latencies overlap.
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b,
+                                           uint32_t parity_b) {
+  bool oka = mbar_try_wait(bar_a, parity_a), okb = mbar_try_wait(bar_b, parity_b);
+  while (!(oka && okb)) {
+    if (!oka) oka = mbar_try_wait(bar_a, parity_a);
+    if (!okb) okb = mbar_try_wait(bar_b, parity_b);
+  }
+}
 
 // ---- TMA ----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

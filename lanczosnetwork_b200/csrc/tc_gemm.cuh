@@ -259,8 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi,
       tc05::fence_after_thread_sync();
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         const uint32_t sb = cnt % SB, sa = cnt % NGROUPS;
-        tc05::mbar_wait(&c.b_full[sb], (cnt / SB) & 1u);
-        tc05::mbar_wait(&c.a_full[sa], (cnt / NGROUPS) & 1u);
+        tc05::mbar_wait2(&c.b_full[sb], (cnt / SB) & 1u, &c.a_full[sa], (cnt / NGROUPS) & 1u);
         tc05::fence_after_thread_sync();
         if (tc05::elect_one()) {
           const uint32_t a_hi = tmem_base + COL_A + sa * 64, a_lo = a_hi + 32;
