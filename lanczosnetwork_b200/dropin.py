@@ -6,7 +6,7 @@ What it does:
   1. registers ``operators._ext`` / ``operators._ext.segment_reduction`` in ``sys.modules`` so
      ``from model import *`` of the reference works without building its THC-era extension
      (model/mpnn.py:6 -> operators/functions/unsorted_segment_sum.py:5);
-  2. rebinds ``LanczosNet`` / ``AdaLanczosNet`` / ``LanczosNetGeneral`` inside the runner
+  2. rebinds ``LanczosNet`` / ``AdaLanczosNet`` / ``LanczosNetGeneral`` / ``GCN`` inside the runner
      modules' globals, because the runners resolve the class with ``eval(name)`` in their own
      namespace (runner/qm8_runner.py:59,288; runner/graph_runner.py:57,285);
   3. runs the reference ``run_exp.main()`` unchanged.
@@ -18,7 +18,7 @@ import sys
 from . import model as _models
 from .operators import _ext as _ext_pkg
 
-DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral')
+DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral', 'GCN')
 
 
 def register_native_op():

@@ -135,6 +135,18 @@ def lanczos_net_forward(params, spec, node_feat, L, D, V, mask, dtype=torch.floa
   return (score, states) if return_states else score
 
 
+def gcn_forward(params, spec, node_feat, L, mask, dtype=torch.float32):
+  """GCN.forward without the loss (model/gcn.py:64-119): the LanczosNet layer with no
+  diffusion scales -- msg = [L_e X]_e (:84-88), Linear + ReLU (:90-91), gated readout (:95-110)."""
+  assert not spec['short'] and not spec['long']
+  params = _cast(params, dtype)
+  L = torch.as_tensor(L).to(dtype)
+  state = params['embedding.weight'][torch.as_tensor(node_feat).long()]   # gcn.py:81
+  for layer in range(spec['num_layer']):
+    state = conv_layer(params, spec, layer, state, L, None)
+  return readout(params, spec, state, None if mask is None else torch.as_tensor(mask))
+
+
 # ----------------------------------------------------------------------------
 # AdaLanczosNet pieces
 # ----------------------------------------------------------------------------

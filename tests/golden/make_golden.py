@@ -37,6 +37,7 @@ operators._ext = sys.modules['operators._ext']
 operators._ext.segment_reduction = sys.modules['operators._ext.segment_reduction']
 
 from model import LanczosNet, AdaLanczosNet, LanczosNetGeneral  # noqa: E402  (reference)
+from model import GCN  # noqa: E402  (reference)
 from utils import data_helper as ref_dh  # noqa: E402
 import dataset.qm8 as ref_qm8  # noqa: E402
 import dataset.graph_data as ref_gd  # noqa: E402
@@ -148,6 +149,23 @@ def golden_lanczosnet_qm8(B=8, data_seed=7, weight_seed=1234):
        L=batch['L'].numpy(), D=batch['D'].numpy(), V=batch['V'].numpy(),
        label=batch['label'].numpy(), score=score.numpy(), loss=np.array(float(loss)),
        Lf0=Lf0.numpy(), score_power=score2.numpy(), weight_seed=np.array(weight_seed))
+
+
+def golden_gcn_qm8(weight_seed=2468):
+  """Reference GCN (model/gcn.py) on the inputs of lanczosnet_qm8.npz (the QM8 collate feeds GCN the
+  same L = [L_simple_4 | L_multi], dataset/qm8.py:220-262); only the outputs are stored."""
+  g = np.load(os.path.join(HERE, 'lanczosnet_qm8.npz'))
+  cfg = configs.qm8_gcn()
+  model = GCN(cfg)
+  model.load_state_dict(deterministic_state_dict(model, weight_seed))
+  model.eval()
+  nf, L = torch.from_numpy(g['node_feat']), torch.from_numpy(g['L'])
+  mask = torch.from_numpy(g['node_mask'])
+  with torch.no_grad():
+    score, loss = model(nf, L, label=torch.from_numpy(g['label']), mask=mask)
+    score_nomask = model(nf, L)
+  save('gcn_qm8.npz', score=score.numpy(), loss=np.array(float(loss)),
+       score_nomask=score_nomask.numpy(), weight_seed=np.array(weight_seed))
 
 
 def golden_general_synth(num_graphs=16, weight_seed=4321):
@@ -264,6 +282,7 @@ def golden_ada_forward(weight_seed=999):
 if __name__ == '__main__':
   golden_data_helper()
   golden_lanczosnet_qm8()
+  golden_gcn_qm8()
   golden_general_synth()
   golden_lanczos_layer()
   golden_ada_forward()

@@ -6,7 +6,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs, data
-from lanczosnetwork_b200.model import AdaLanczosNet, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import AdaLanczosNet, GCN, LanczosNet, LanczosNetGeneral
 from oracle import lanczos_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -157,6 +157,31 @@ def test_lanczos_plus_ritz_pipeline_reproduces_low_rank_operator():
                    theta.cpu().numpy().astype(np.float64), V.cpu().numpy().astype(np.float64))
   ref = np.einsum('bnk,bk,bmk->bnm', Vo, th, Vo)
   np.testing.assert_allclose(ours, ref, atol=5e-5)
+
+
+def test_gcn_matches_reference_golden():
+  """model/gcn.py through the same one-launch stack kernel (no long scales)."""
+  g, gg = load_golden('lanczosnet_qm8.npz'), load_golden('gcn_qm8.npz')
+  mod, params = _build(GCN, configs.qm8_gcn(), int(gg['weight_seed']))
+  nf, L = _t(g['node_feat']).to(dev()), _t(g['L']).to(dev())
+  with torch.no_grad():
+    n0 = ops_launches()
+    score, loss = mod(nf, L, label=_t(g['label']).to(dev()), mask=_t(g['node_mask']).to(dev()))
+    nomask = mod(nf, L)
+  np.testing.assert_allclose(score.cpu().numpy(), gg['score'], rtol=FWD_RTOL, atol=FWD_ATOL)
+  np.testing.assert_allclose(nomask.cpu().numpy(), gg['score_nomask'], rtol=FWD_RTOL, atol=FWD_ATOL)
+  assert abs(float(loss) - float(gg['loss'])) <= 1e-4 * abs(float(gg['loss']))
+  spec = oracle_spec(mod, 'GCN')
+  s64 = orc.gcn_forward(params, spec, g['node_feat'], g['L'], g['node_mask'], dtype=torch.float64).numpy()
+  e_ref = np.abs(gg['score'] - s64).max()
+  e_ours = np.abs(score.cpu().numpy() - s64).max()
+  assert e_ours <= max(4 * e_ref, 5e-6), (e_ours, e_ref)
+  assert ops_launches() > n0
+
+
+def ops_launches():
+  from lanczosnetwork_b200 import ops
+  return ops.launch_count()
 
 
 def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates():

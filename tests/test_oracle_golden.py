@@ -6,7 +6,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs
-from lanczosnetwork_b200.model import AdaLanczosNet, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import AdaLanczosNet, GCN, LanczosNet, LanczosNetGeneral
 from oracle import graph_prep
 from oracle import lanczos_oracle as orc
 
@@ -61,6 +61,20 @@ def test_lanczosnet_forward_matches_reference():
   s64 = orc.lanczos_net_forward(params, spec, g['node_feat'], g['L'], g['D'], g['V'],
                                 g['node_mask'], dtype=torch.float64)
   assert np.abs(s64.numpy() - g['score']).max() < 2e-5
+
+
+def test_gcn_forward_matches_reference():
+  """the sibling GCN (model/gcn.py) on the inputs of the LanczosNet fixture."""
+  g, gg = load_golden('lanczosnet_qm8.npz'), load_golden('gcn_qm8.npz')
+  mod = GCN(configs.qm8_gcn())
+  params = deterministic_state_dict(mod, int(gg['weight_seed']))
+  spec = oracle_spec(mod, 'GCN')
+  score = orc.gcn_forward(params, spec, g['node_feat'], g['L'], g['node_mask'])
+  np.testing.assert_allclose(score.numpy(), gg['score'], rtol=1e-4, atol=2e-6)
+  nomask = orc.gcn_forward(params, spec, g['node_feat'], g['L'], None)
+  np.testing.assert_allclose(nomask.numpy(), gg['score_nomask'], rtol=1e-4, atol=2e-6)
+  s64 = orc.gcn_forward(params, spec, g['node_feat'], g['L'], g['node_mask'], dtype=torch.float64)
+  assert np.abs(s64.numpy() - gg['score']).max() < 2e-5
 
 
 def test_lanczosnet_power_filter_matches_reference():
