@@ -132,10 +132,12 @@ def test_dropin_rebinds_names_in_a_runner_namespace():
   from lanczosnetwork_b200 import dropin
   fake_runner = types.ModuleType('fake_runner')
   fake_runner.LanczosNet = object
-  fake_runner.GCN = 'untouched'
+  fake_runner.GCN = object
+  fake_runner.MPNN = 'untouched'          # models off the path keep the reference class
   dropin.patch_namespace(fake_runner)
-  from lanczosnetwork_b200.model import LanczosNet
-  assert fake_runner.LanczosNet is LanczosNet and fake_runner.GCN == 'untouched'
+  from lanczosnetwork_b200.model import GCN, LanczosNet
+  assert fake_runner.LanczosNet is LanczosNet and fake_runner.GCN is GCN
+  assert fake_runner.MPNN == 'untouched'
   dropin.register_native_op()
   import importlib
   sr = importlib.import_module('operators._ext.segment_reduction')
