@@ -110,7 +110,8 @@ int lnb_linear_tf32x3_grouped(lnb_stream_t stream, const float* A, const float* 
  *                sum n_eff <= 128, sum ceil4(k_eff) <= 128, <= 32 graphs), tiles[1+T] = B;
  *                entries [B+2, 4B+2) are scratch of the assignment kernel;
  *   rowmap [B*K], nrows [1] (both optional, NULL to skip): the compact Ritz row list of
- *                lnb_ritz_rowmap, produced by the same pass.
+ *                lnb_ritz_rowmap, produced by the same pass;
+ *   flags bit 0: store 1.0 for every non-zero (the `L[L != 0] = 1.0` of model/gcnfp.py:83).
  * Skipping exact zeros / padded rows is exact.  write_pad != 0 also writes the constant rows
  * act(bias) of padded nodes (needed when the full [B,N,H] tensor is read afterwards).
  * Requirements of the fused kernel: N <= 128, Din % 32 == 0, K % 4 == 0, K <= 32, H % 4 == 0,
@@ -119,7 +120,7 @@ int lnb_linear_tf32x3_grouped(lnb_stream_t stream, const float* A, const float* 
  * ------------------------------------------------------------------------------------- */
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
                       int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* gext,
-                      int32_t* tiles, int32_t* rowmap, int32_t* nrows);
+                      int32_t* tiles, int32_t* rowmap, int32_t* nrows, int flags);
 int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q, const float* coeff,
                             const float* ell_val, const uint8_t* ell_idx, const int32_t* ell_max,
                             const int32_t* gext, const int32_t* tiles, const float* W_hi,

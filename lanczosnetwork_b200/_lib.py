@@ -68,7 +68,7 @@ SIGNATURES = {
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_graph_prepare': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                  ctypes.c_void_p, ctypes.c_void_p]),
+                                  ctypes.c_void_p, ctypes.c_void_p, c_int]),
     'lnb_spectral_conv_fused':
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
                  ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int,

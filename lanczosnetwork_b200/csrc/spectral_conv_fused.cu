@@ -40,7 +40,7 @@ template <bool STAGE>   // STAGE: this graph's operators fit in shared memory
 __global__ void __launch_bounds__(256)
 graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, int N, int E1, int K,
                      float* __restrict__ ell_val, uint8_t* __restrict__ ell_idx,
-                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext) {
+                     int32_t* __restrict__ ell_max, int32_t* __restrict__ gext, int binarize) {
   extern __shared__ __align__(16) float gp_smem[];     // [N*N*E1] this graph's operators (optional)
   __shared__ int s_max[EMAX];
   __shared__ int s_ext[2];
@@ -81,7 +81,7 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
     // entry 0 (conflict-free in the fused kernel), the other entries follow in column order
     const float dg = row[n * E1];
     if (dg != 0.f) {
-      val[0] = dg;
+      val[0] = binarize ? 1.f : dg;
       idx[0] = (uint8_t)n;
       cnt = 1;
       far = n + 1;
@@ -90,7 +90,7 @@ graph_prepare_kernel(const float* __restrict__ L, const float* __restrict__ Q, i
     for (int i = 0; i < N; ++i) {
       const float v = row[i * E1];
       if (v != 0.f && i != n) {
-        val[cnt * N] = v;
+        val[cnt * N] = binarize ? 1.f : v;
         idx[cnt * N] = (uint8_t)i;
         ++cnt;
         far = max(far, i + 1);
@@ -840,7 +840,7 @@ int lnb_debug_set_prof(unsigned long long* buf) {
 int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B, int N, int E1,
                       int K, float* ell_val, uint8_t* ell_idx, int32_t* ell_max, int32_t* gext,
                       int32_t* tiles /* [4*B + 2]: B + 2 tile table followed by 3*B scratch */,
-                      int32_t* rowmap, int32_t* nrows) {
+                      int32_t* rowmap, int32_t* nrows, int flags) {
   LNB_REQUIRE(L && Q && ell_val && ell_idx && ell_max && gext && tiles, "graph_prepare: null pointer");
   LNB_REQUIRE((rowmap == nullptr) == (nrows == nullptr), "graph_prepare: rowmap and nrows go together");
   LNB_REQUIRE(B >= 0 && N >= 1 && N <= 255 && E1 >= 1 && E1 <= EMAX && K >= 1,
@@ -852,9 +852,11 @@ int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B
   if (stage) {
     if (lbytes > 40 * 1024)
       cudaFuncSetAttribute(graph_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbytes);
-    graph_prepare_kernel<true><<<B, 256, lbytes, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
+    graph_prepare_kernel<true><<<B, 256, lbytes, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext,
+                                                      flags & 1);
   } else {
-    graph_prepare_kernel<false><<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext);
+    graph_prepare_kernel<false><<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext,
+                                                  flags & 1);
   }
   const size_t tbytes = (size_t)6 * (B + 1) * sizeof(int32_t);
   const int tsm = tbytes <= 200 * 1024;

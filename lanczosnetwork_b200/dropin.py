@@ -18,7 +18,7 @@ import sys
 from . import model as _models
 from .operators import _ext as _ext_pkg
 
-DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral', 'GCN')
+DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral', 'GCN', 'GCNFP')
 
 
 def register_native_op():

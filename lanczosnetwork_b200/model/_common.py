@@ -245,7 +245,11 @@ class SpectralNetBase(nn.Module):
     while first < nl and not ok[first]:
       first += 1
     stack_ok = uniform and first < nl and all(ok[first:]) and nl - first <= 8
-    ctx = GraphContext(L, V)
+    binarize = getattr(self, '_binarize_operators', False)
+    if binarize and not (stack_ok and first == 0):
+      L = (L != 0).to(L.dtype)          # shapes off the fused path read the dense operators
+      binarize = False
+    ctx = GraphContext(L, V, binarize)
     coeffs = table = None
     if S > 0:
       mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None

@@ -9,7 +9,7 @@ import torch.nn as nn
 from ._common import SpectralNetBase, _opt
 from ..spectral_conv import WeightCache
 
-__all__ = ['GCN']
+__all__ = ['GCN', 'GCNFP']
 
 
 class GCN(SpectralNetBase):
@@ -52,3 +52,11 @@ class GCN(SpectralNetBase):
     # no Ritz vectors: an all-zero block makes lnb_graph_prepare take the extents from L alone
     V = torch.zeros((B, N, 4), device=L.device, dtype=torch.float32)
     return self._ritz_conv_stack(None, node_feat.long(), L, None, V, mask)
+
+
+class GCNFP(GCN):
+  """Drop-in for the reference ``model.GCNFP`` (model/gcnfp.py:8-125): GCN on the non-zero pattern
+  of the operators (``L[L != 0] = 1.0``, :83).  The 0/1 values are produced while the operators are
+  compressed (lnb_graph_prepare flag), so the dense tensor is never rewritten -- unlike the
+  reference, the caller's ``L`` is left untouched."""
+  _binarize_operators = True

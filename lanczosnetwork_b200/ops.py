@@ -165,7 +165,7 @@ class GraphPrep(tuple):
   nrows = None
 
 
-def graph_prepare(L, Q):
+def graph_prepare(L, Q, binarize=False):
   """Per-forward compression of the dense operators L [B,N,N,E1] (ELL rows), the real extents
   of every graph, the packed-tile assignment for the fused convolution kernel and the compact
   list of non-zero Ritz rows.  Returns GraphPrep(ell_val, ell_idx, ell_max, gext, tiles)."""
@@ -184,7 +184,8 @@ def graph_prepare(L, Q):
   with torch.cuda.device(dev):
     _lib.check(_lib.load().lnb_graph_prepare(_stream(L), _ptr(L), _ptr(Q), B, N, E1, K,
                                              _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max),
-                                             _ptr(gext), _ptr(tiles), _ptr(rowmap), _ptr(nrows)),
+                                             _ptr(gext), _ptr(tiles), _ptr(rowmap), _ptr(nrows),
+                                             1 if binarize else 0),
                'lnb_graph_prepare')
   prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
   prep.rowmap, prep.nrows = rowmap, nrows

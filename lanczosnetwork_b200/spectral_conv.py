@@ -162,14 +162,15 @@ class GraphContext(object):
   """Layer-invariant per-forward state: the operators, the Ritz / Lanczos vectors and (lazily)
   their compressed form for the fused kernel."""
 
-  def __init__(self, L, Qv):
+  def __init__(self, L, Qv, binarize=False):
     self.L = L
     self.Qv = Qv
+    self.binarize = binarize          # operators enter as their non-zero pattern (model/gcnfp.py:83)
     self._prep = None
 
   def prep(self):
     if self._prep is None:
-      self._prep = ops.graph_prepare(self.L, self.Qv)
+      self._prep = ops.graph_prepare(self.L, self.Qv, self.binarize)
     return self._prep
 
 

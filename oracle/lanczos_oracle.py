@@ -135,12 +135,15 @@ def lanczos_net_forward(params, spec, node_feat, L, D, V, mask, dtype=torch.floa
   return (score, states) if return_states else score
 
 
-def gcn_forward(params, spec, node_feat, L, mask, dtype=torch.float32):
+def gcn_forward(params, spec, node_feat, L, mask, dtype=torch.float32, binarize=False):
   """GCN.forward without the loss (model/gcn.py:64-119): the LanczosNet layer with no
-  diffusion scales -- msg = [L_e X]_e (:84-88), Linear + ReLU (:90-91), gated readout (:95-110)."""
+  diffusion scales -- msg = [L_e X]_e (:84-88), Linear + ReLU (:90-91), gated readout (:95-110).
+  binarize=True is GCNFP.forward (model/gcnfp.py:68-125): the same on L[L != 0] = 1.0 (:83)."""
   assert not spec['short'] and not spec['long']
   params = _cast(params, dtype)
   L = torch.as_tensor(L).to(dtype)
+  if binarize:
+    L = (L != 0).to(dtype)
   state = params['embedding.weight'][torch.as_tensor(node_feat).long()]   # gcn.py:81
   for layer in range(spec['num_layer']):
     state = conv_layer(params, spec, layer, state, L, None)

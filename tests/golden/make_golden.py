@@ -37,7 +37,7 @@ operators._ext = sys.modules['operators._ext']
 operators._ext.segment_reduction = sys.modules['operators._ext.segment_reduction']
 
 from model import LanczosNet, AdaLanczosNet, LanczosNetGeneral  # noqa: E402  (reference)
-from model import GCN  # noqa: E402  (reference)
+from model import GCN, GCNFP  # noqa: E402  (reference)
 from utils import data_helper as ref_dh  # noqa: E402
 import dataset.qm8 as ref_qm8  # noqa: E402
 import dataset.graph_data as ref_gd  # noqa: E402
@@ -164,8 +164,16 @@ def golden_gcn_qm8(weight_seed=2468):
   with torch.no_grad():
     score, loss = model(nf, L, label=torch.from_numpy(g['label']), mask=mask)
     score_nomask = model(nf, L)
+  # GCNFP (model/gcnfp.py): same parameters layout, operators binarised IN PLACE by the forward
+  cfg_fp = configs.qm8_gcn(name='GCNFP')
+  model_fp = GCNFP(cfg_fp)
+  model_fp.load_state_dict(deterministic_state_dict(model_fp, weight_seed + 1))
+  model_fp.eval()
+  with torch.no_grad():
+    score_fp = model_fp(nf, L.clone(), mask=mask)
   save('gcn_qm8.npz', score=score.numpy(), loss=np.array(float(loss)),
-       score_nomask=score_nomask.numpy(), weight_seed=np.array(weight_seed))
+       score_nomask=score_nomask.numpy(), score_fp=score_fp.numpy(),
+       weight_seed=np.array(weight_seed))
 
 
 def golden_general_synth(num_graphs=16, weight_seed=4321):

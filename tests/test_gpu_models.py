@@ -6,7 +6,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs, data
-from lanczosnetwork_b200.model import AdaLanczosNet, GCN, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import AdaLanczosNet, GCN, GCNFP, LanczosNet, LanczosNetGeneral
 from oracle import lanczos_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -179,6 +179,14 @@ def test_gcn_matches_reference_golden():
   # scale, inside FWD_ATOL; budget stated against the fp64 oracle
   assert e_ours <= max(4 * e_ref, 1.5e-5), (e_ours, e_ref)
   assert ops_launches() > n0
+  # GCNFP: operators binarised inside lnb_graph_prepare; the caller's L stays untouched
+  mod_fp, params_fp = _build(GCNFP, configs.qm8_gcn(name='GCNFP'), int(gg['weight_seed']) + 1)
+  L_before = L.clone()
+  with torch.no_grad():
+    fp = mod_fp(nf, L, mask=_t(g['node_mask']).to(dev()))
+  assert torch.equal(L, L_before)
+  scale = float(np.abs(gg['score_fp']).max())
+  np.testing.assert_allclose(fp.cpu().numpy(), gg['score_fp'], rtol=FWD_RTOL, atol=FWD_ATOL * max(1.0, scale))
 
 
 def ops_launches():

@@ -6,7 +6,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs
-from lanczosnetwork_b200.model import AdaLanczosNet, GCN, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import AdaLanczosNet, GCN, GCNFP, LanczosNet, LanczosNetGeneral
 from oracle import graph_prep
 from oracle import lanczos_oracle as orc
 
@@ -75,6 +75,12 @@ def test_gcn_forward_matches_reference():
   np.testing.assert_allclose(nomask.numpy(), gg['score_nomask'], rtol=1e-4, atol=2e-6)
   s64 = orc.gcn_forward(params, spec, g['node_feat'], g['L'], g['node_mask'], dtype=torch.float64)
   assert np.abs(s64.numpy() - gg['score']).max() < 2e-5
+  # GCNFP: the same layer on the non-zero pattern of the operators
+  mod_fp = GCNFP(configs.qm8_gcn(name='GCNFP'))
+  params_fp = deterministic_state_dict(mod_fp, int(gg['weight_seed']) + 1)
+  fp = orc.gcn_forward(params_fp, oracle_spec(mod_fp, 'GCNFP'), g['node_feat'], g['L'], g['node_mask'],
+                       binarize=True)
+  np.testing.assert_allclose(fp.numpy(), gg['score_fp'], rtol=1e-4, atol=1e-5)
 
 
 def test_lanczosnet_power_filter_matches_reference():
