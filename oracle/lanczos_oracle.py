@@ -150,6 +150,28 @@ def gcn_forward(params, spec, node_feat, L, mask, dtype=torch.float32, binarize=
   return readout(params, spec, state, None if mask is None else torch.as_tensor(mask))
 
 
+def dcnn_forward(params, diffusion_dist, num_edgetype, num_layer, node_feat, L, mask,
+                 dtype=torch.float32):
+  """DCNN.forward without the loss (model/dcnn.py:64-124): per layer the walk L_0^k X for k in
+  diffusion_dist (:88-92), the edge-type products (:94-96), concatenated EDGES FIRST (:98),
+  Linear + ReLU (:99); the gated readout shared with the other models (:103-118)."""
+  params = _cast(params, dtype)
+  L = torch.as_tensor(L).to(dtype)
+  state = params['embedding.weight'][torch.as_tensor(node_feat).long()]   # dcnn.py:83
+  B, N = state.shape[0], state.shape[1]
+  for layer in range(num_layer):
+    scales, walk = [], state
+    for step in range(1, max(diffusion_dist) + 1):
+      walk = torch.bmm(L[:, :, :, 0], walk)
+      if step in diffusion_dist:
+        scales.append(walk)
+    msgs = [torch.bmm(L[:, :, :, e], state) for e in range(num_edgetype + 1)]
+    cat = torch.cat(msgs + scales, dim=2).reshape(B * N, -1)
+    state = torch.relu(_linear(params, 'filter.%d' % layer, cat)).reshape(B, N, -1)
+  spec = {'num_layer': num_layer}
+  return readout(params, spec, state, None if mask is None else torch.as_tensor(mask))
+
+
 # ----------------------------------------------------------------------------
 # AdaLanczosNet pieces
 # ----------------------------------------------------------------------------

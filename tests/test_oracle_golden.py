@@ -6,7 +6,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs
-from lanczosnetwork_b200.model import AdaLanczosNet, GCN, GCNFP, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import AdaLanczosNet, DCNN, GCN, GCNFP, LanczosNet, LanczosNetGeneral
 from oracle import graph_prep
 from oracle import lanczos_oracle as orc
 
@@ -81,6 +81,13 @@ def test_gcn_forward_matches_reference():
   fp = orc.gcn_forward(params_fp, oracle_spec(mod_fp, 'GCNFP'), g['node_feat'], g['L'], g['node_mask'],
                        binarize=True)
   np.testing.assert_allclose(fp.numpy(), gg['score_fp'], rtol=1e-4, atol=1e-5)
+  # DCNN: edge types + powers of the simple-graph operator
+  cfg = configs.qm8_dcnn()
+  mod_dc = DCNN(cfg)
+  params_dc = deterministic_state_dict(mod_dc, int(gg['weight_seed']) + 2)
+  dc = orc.dcnn_forward(params_dc, cfg.model.diffusion_dist, cfg.dataset.num_bond_type,
+                        cfg.model.num_layer, g['node_feat'], g['L'], g['node_mask'])
+  np.testing.assert_allclose(dc.numpy(), gg['score_dcnn'], rtol=1e-4, atol=2e-6)
 
 
 def test_lanczosnet_power_filter_matches_reference():
