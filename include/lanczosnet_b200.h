@@ -53,10 +53,14 @@ int lnb_unsorted_segment_sum_backward(lnb_stream_t stream, const float* grad_out
                                       int num_segments, float* grad_data);
 
 /* ---------------------------------------------------------------------------------------
- * Generic strided batched fp32 GEMM   C[b,z] = act( (A[b,z] * kscale[b,z]) @ B[b,z] + bias )
- * (the torch.bmm / nn.Linear call sites of model/lanczos_net.py:112-121,167-181).
+ * Generic strided batched fp32 GEMM
+ *     C[b,z] = act( alpha * (A[b,z] * kscale[b,z]) @ B[b,z] + beta * D[b,z] + bias )
+ * (the torch.bmm / nn.Linear call sites of model/lanczos_net.py:112-121,167-181; the addend D is
+ * the Chebyshev recurrence 2 L s_{k-1} - s_{k-2} of model/cheby_net.py:91-93).
  * Strides are in elements.  kscale (optional) multiplies column k of A; bias (optional) has
- * N entries; relu != 0 applies max(.,0).  CUDA-core FFMA path for arbitrary shapes/strides.
+ * N entries; relu != 0 applies max(.,0); alpha == 0 is read as 1 (zero-initialised descriptors
+ * keep their old meaning); addend == NULL skips the beta term.  CUDA-core FFMA path for
+ * arbitrary shapes/strides.
  * ------------------------------------------------------------------------------------- */
 typedef struct lnb_gemm_desc {
   const float* A; int64_t a_sb, a_sz, a_sm, a_sk;
@@ -65,6 +69,8 @@ typedef struct lnb_gemm_desc {
   const float* kscale; int64_t s_sb, s_sz, s_sk;
   const float* bias; int64_t bias_sz;   /* bias[z*bias_sz + n] */
   int32_t batch, nz, M, N, K, relu;
+  float alpha, beta;
+  const float* addend; int64_t d_sb, d_sz, d_sm, d_sn;
 } lnb_gemm_desc;
 int lnb_batched_gemm(lnb_stream_t stream, const lnb_gemm_desc* desc /* host */);
 

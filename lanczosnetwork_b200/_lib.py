@@ -26,6 +26,8 @@ class GemmDesc(ctypes.Structure):
       ('bias', ctypes.c_void_p), ('bias_sz', c_i64),
       ('batch', ctypes.c_int32), ('nz', ctypes.c_int32), ('M', ctypes.c_int32),
       ('N', ctypes.c_int32), ('K', ctypes.c_int32), ('relu', ctypes.c_int32),
+      ('alpha', ctypes.c_float), ('beta', ctypes.c_float),
+      ('addend', ctypes.c_void_p), ('d_sb', c_i64), ('d_sz', c_i64), ('d_sm', c_i64), ('d_sn', c_i64),
   ]
 
 

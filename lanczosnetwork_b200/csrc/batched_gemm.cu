@@ -1,5 +1,5 @@
 // Generic strided batched fp32 GEMM on CUDA cores (FFMA), arbitrary shapes and strides.
-//   C[b,z] = act( (A[b,z] * kscale[b,z]) @ B[b,z] + bias )
+//   C[b,z] = act( alpha * (A[b,z] * kscale[b,z]) @ B[b,z] + beta * D[b,z] + bias )
 // This is the general-shape path behind the torch.bmm call sites of the reference
 // (model/lanczos_net.py:117,121,167,174,178; ada_lanczos_net.py:270,281,284,331,338,342):
 // channel-innermost operator slices L[:, :, :, e] are consumed in place through their element
@@ -23,6 +23,8 @@ batched_gemm_kernel(lnb_gemm_desc d, int a_k_contig, int b_n_contig) {
   const float* __restrict__ Bm = d.B + b * d.b_sb + z * d.b_sz;
   const float* __restrict__ ks = d.kscale ? d.kscale + b * d.s_sb + z * d.s_sz : nullptr;
   float* __restrict__ C = d.C + b * d.c_sb + z * d.c_sz;
+  const float* __restrict__ Dadd = d.addend ? d.addend + b * d.d_sb + z * d.d_sz : nullptr;
+  const float alpha = d.alpha == 0.f ? 1.f : d.alpha;
 
   const int t = threadIdx.x;
   const int ty = t / 16, tx = t % 16;  // 16x16 threads, 4x4 outputs each
@@ -78,7 +80,8 @@ batched_gemm_kernel(lnb_gemm_desc d, int a_k_contig, int b_n_contig) {
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= d.N) continue;
-      float v = acc[i][j];
+      float v = alpha * acc[i][j];
+      if (Dadd) v = fmaf(d.beta, Dadd[(int64_t)m * d.d_sm + (int64_t)n * d.d_sn], v);
       if (d.bias) v += d.bias[(int64_t)z * d.bias_sz + n];
       if (d.relu) v = fmaxf(v, 0.f);
       C[(int64_t)m * d.c_sm + (int64_t)n * d.c_sn] = v;

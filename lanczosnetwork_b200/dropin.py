@@ -18,7 +18,7 @@ import sys
 from . import model as _models
 from .operators import _ext as _ext_pkg
 
-DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral', 'GCN', 'GCNFP', 'DCNN')
+DROPIN_CLASSES = ('LanczosNet', 'AdaLanczosNet', 'LanczosNetGeneral', 'GCN', 'GCNFP', 'DCNN', 'ChebyNet')
 
 
 def register_native_op():

@@ -5,3 +5,4 @@ from .ada_lanczos_net import *      # noqa: F401,F403
 from .lanczos_net_general import *  # noqa: F401,F403
 from .gcn import *                  # noqa: F401,F403  (sibling models on the same kernels)
 from .dcnn import *                 # noqa: F401,F403
+from .cheby_net import *            # noqa: F401,F403

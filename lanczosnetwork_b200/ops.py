@@ -53,9 +53,10 @@ def launch_count():
 
 # --------------------------------------------------------------------------------------------
 def bgemm(A, a_str, Bm, b_str, C, c_str, batch, nz, M, N, K, kscale=None, s_str=(0, 0, 0),
-          bias=None, bias_sz=0, relu=False, a_off=0, b_off=0, c_off=0):
-  """C[b,z] = act((A[b,z] * kscale[b,z]) @ B[b,z] + bias); strides in elements, *_off element
-  offsets into the (fp32, CUDA) storage of A / B / C."""
+          bias=None, bias_sz=0, relu=False, a_off=0, b_off=0, c_off=0, alpha=1.0, addend=None,
+          add_str=(0, 0, 0, 0), add_off=0, beta=0.0):
+  """C[b,z] = act(alpha * (A[b,z] * kscale[b,z]) @ B[b,z] + beta * addend[b,z] + bias); strides in
+  elements, *_off element offsets into the (fp32, CUDA) storage of A / B / C / addend."""
   _need_cuda(A, Bm, C, kscale, bias)
   lib = _lib.load()
   d = GemmDesc()
@@ -70,6 +71,9 @@ def bgemm(A, a_str, Bm, b_str, C, c_str, batch, nz, M, N, K, kscale=None, s_str=
   d.bias = bias.data_ptr() if bias is not None else None
   d.bias_sz = int(bias_sz)
   d.batch, d.nz, d.M, d.N, d.K, d.relu = int(batch), int(nz), int(M), int(N), int(K), int(bool(relu))
+  d.alpha, d.beta = float(alpha), float(beta)
+  d.addend = addend.data_ptr() + 4 * add_off if addend is not None else None
+  d.d_sb, d.d_sz, d.d_sm, d.d_sn = [int(v) for v in add_str]
   with torch.cuda.device(C.device):
     _lib.check(lib.lnb_batched_gemm(_stream(C), ctypes.byref(d)), 'lnb_batched_gemm')
   return C

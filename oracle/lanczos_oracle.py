@@ -172,6 +172,29 @@ def dcnn_forward(params, diffusion_dist, num_edgetype, num_layer, node_feat, L, 
   return readout(params, spec, state, None if mask is None else torch.as_tensor(mask))
 
 
+def cheby_net_forward(params, polynomial_order, num_edgetype, num_layer, node_feat, L, mask,
+                      dtype=torch.float32):
+  """ChebyNet.forward without the loss (model/cheby_net.py:64-124): per layer the Chebyshev chain
+  on channel 0 -- state_scale[-1] = X, [0] = L_0 X, [k] = 2 L_0 [k-1] - [k-2] (:88-93; index -1 is
+  the LAST slot, which is how k = 1 reaches X) --, the bond-type products for e >= 1 (:95-97),
+  cat(edges + state_scale) (:99), Linear + ReLU (:100); the shared gated readout (:104-119)."""
+  params = _cast(params, dtype)
+  L = torch.as_tensor(L).to(dtype)
+  state = params['embedding.weight'][torch.as_tensor(node_feat).long()]   # cheby_net.py:83
+  B, N = state.shape[0], state.shape[1]
+  for layer in range(num_layer):
+    scale = [None] * (polynomial_order + 1)
+    scale[-1] = state
+    scale[0] = torch.bmm(L[:, :, :, 0], state)
+    for kk in range(1, polynomial_order):
+      scale[kk] = 2.0 * torch.bmm(L[:, :, :, 0], scale[kk - 1]) - scale[kk - 2]
+    msgs = [torch.bmm(L[:, :, :, e], state) for e in range(1, num_edgetype + 1)]
+    cat = torch.cat(msgs + scale, dim=2).reshape(B * N, -1)
+    state = torch.relu(_linear(params, 'filter.%d' % layer, cat)).reshape(B, N, -1)
+  return readout(params, {'num_layer': num_layer}, state,
+                 None if mask is None else torch.as_tensor(mask))
+
+
 # ----------------------------------------------------------------------------
 # AdaLanczosNet pieces
 # ----------------------------------------------------------------------------

@@ -37,7 +37,7 @@ operators._ext = sys.modules['operators._ext']
 operators._ext.segment_reduction = sys.modules['operators._ext.segment_reduction']
 
 from model import LanczosNet, AdaLanczosNet, LanczosNetGeneral  # noqa: E402  (reference)
-from model import GCN, GCNFP, DCNN  # noqa: E402  (reference)
+from model import GCN, GCNFP, DCNN, ChebyNet  # noqa: E402  (reference)
 from utils import data_helper as ref_dh  # noqa: E402
 import dataset.qm8 as ref_qm8  # noqa: E402
 import dataset.graph_data as ref_gd  # noqa: E402
@@ -177,9 +177,15 @@ def golden_gcn_qm8(weight_seed=2468):
   model_dc.eval()
   with torch.no_grad():
     score_dc = model_dc(nf, L, mask=mask)
+  # ChebyNet (model/cheby_net.py): Chebyshev chain on channel 0 + bond-type channels
+  model_ch = ChebyNet(configs.qm8_cheby_net())
+  model_ch.load_state_dict(deterministic_state_dict(model_ch, weight_seed + 3))
+  model_ch.eval()
+  with torch.no_grad():
+    score_ch = model_ch(nf, L, mask=mask)
   save('gcn_qm8.npz', score=score.numpy(), loss=np.array(float(loss)),
        score_nomask=score_nomask.numpy(), score_fp=score_fp.numpy(), score_dcnn=score_dc.numpy(),
-       weight_seed=np.array(weight_seed))
+       score_cheby=score_ch.numpy(), weight_seed=np.array(weight_seed))
 
 
 def golden_general_synth(num_graphs=16, weight_seed=4321):

@@ -6,7 +6,8 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs, data
-from lanczosnetwork_b200.model import AdaLanczosNet, DCNN, GCN, GCNFP, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import (AdaLanczosNet, ChebyNet, DCNN, GCN, GCNFP, LanczosNet,
+                                       LanczosNetGeneral)
 from oracle import lanczos_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -206,6 +207,27 @@ def test_dcnn_matches_reference_golden():
                          cfg.model.num_layer, g['node_feat'], g['L'], g['node_mask'],
                          dtype=torch.float64).numpy()
   e_ref = np.abs(gg['score_dcnn'] - s64).max()
+  e_ours = np.abs(eager.cpu().numpy() - s64).max()
+  assert e_ours <= max(4 * e_ref, 1.5e-5), (e_ours, e_ref)
+
+
+def test_cheby_net_matches_reference_golden():
+  """model/cheby_net.py; the recurrence runs as alpha / beta-addend batched GEMMs."""
+  g, gg = load_golden('lanczosnet_qm8.npz'), load_golden('gcn_qm8.npz')
+  cfg = configs.qm8_cheby_net()
+  mod, params = _build(ChebyNet, cfg, int(gg['weight_seed']) + 3)
+  nf, L, mask = _t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), _t(g['node_mask']).to(dev())
+  with torch.no_grad():
+    mod.use_cuda_graph = False
+    eager = mod(nf, L, mask=mask)
+    mod.use_cuda_graph = True
+    replay = [mod(nf, L, mask=mask) for _ in range(3)]
+  np.testing.assert_allclose(eager.cpu().numpy(), gg['score_cheby'], rtol=FWD_RTOL, atol=FWD_ATOL)
+  assert all(torch.equal(eager, r) for r in replay)
+  s64 = orc.cheby_net_forward(params, cfg.model.polynomial_order, cfg.dataset.num_bond_type,
+                              cfg.model.num_layer, g['node_feat'], g['L'], g['node_mask'],
+                              dtype=torch.float64).numpy()
+  e_ref = np.abs(gg['score_cheby'] - s64).max()
   e_ours = np.abs(eager.cpu().numpy() - s64).max()
   assert e_ours <= max(4 * e_ref, 1.5e-5), (e_ours, e_ref)
 

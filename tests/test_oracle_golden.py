@@ -6,7 +6,8 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs
-from lanczosnetwork_b200.model import AdaLanczosNet, DCNN, GCN, GCNFP, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import (AdaLanczosNet, ChebyNet, DCNN, GCN, GCNFP, LanczosNet,
+                                       LanczosNetGeneral)
 from oracle import graph_prep
 from oracle import lanczos_oracle as orc
 
@@ -88,6 +89,13 @@ def test_gcn_forward_matches_reference():
   dc = orc.dcnn_forward(params_dc, cfg.model.diffusion_dist, cfg.dataset.num_bond_type,
                         cfg.model.num_layer, g['node_feat'], g['L'], g['node_mask'])
   np.testing.assert_allclose(dc.numpy(), gg['score_dcnn'], rtol=1e-4, atol=2e-6)
+  # ChebyNet: Chebyshev chain on channel 0 + bond-type channels
+  cfg = configs.qm8_cheby_net()
+  mod_ch = ChebyNet(cfg)
+  params_ch = deterministic_state_dict(mod_ch, int(gg['weight_seed']) + 3)
+  ch = orc.cheby_net_forward(params_ch, cfg.model.polynomial_order, cfg.dataset.num_bond_type,
+                             cfg.model.num_layer, g['node_feat'], g['L'], g['node_mask'])
+  np.testing.assert_allclose(ch.numpy(), gg['score_cheby'], rtol=1e-4, atol=2e-6)
 
 
 def test_lanczosnet_power_filter_matches_reference():

@@ -1,4 +1,4 @@
-"""Throughput of the sibling-model drop-ins (GCN, GCNFP, DCNN) on the bench's QM8-shaped batches."""
+"""Throughput of the sibling-model drop-ins (GCN, GCNFP, DCNN, ChebyNet) on the bench's QM8-shaped batches."""
 import os
 import sys
 
@@ -10,13 +10,14 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import bench  # noqa: E402
 from helpers import deterministic_state_dict  # noqa: E402
 from lanczosnetwork_b200 import configs  # noqa: E402
-from lanczosnetwork_b200.model import DCNN, GCN, GCNFP  # noqa: E402
+from lanczosnetwork_b200.model import ChebyNet, DCNN, GCN, GCNFP  # noqa: E402
 
 dev = torch.device('cuda:0')
 B = bench.BATCH
 batches = bench.make_batches(4, B, 1000)
 res = [{k: torch.from_numpy(b[k]).to(dev) for k in ('node_feat', 'L', 'node_mask')} for b in batches]
-for cls, cfg in ((GCN, configs.qm8_gcn()), (GCNFP, configs.qm8_gcn(name='GCNFP')), (DCNN, configs.qm8_dcnn())):
+for cls, cfg in ((GCN, configs.qm8_gcn()), (GCNFP, configs.qm8_gcn(name='GCNFP')), (DCNN, configs.qm8_dcnn()),
+                 (ChebyNet, configs.qm8_cheby_net())):
   mod = cls(cfg)
   mod.load_state_dict(deterministic_state_dict(mod, 7))
   mod = mod.to(dev).eval()
