@@ -91,7 +91,7 @@ def test_c_abi_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(lib, name), name
   assert _lib.load().lnb_abi_version() == 1
-  assert ctypes.sizeof(_lib.GemmDesc) == 21 * 8 + 6 * 4
+  assert ctypes.sizeof(_lib.GemmDesc) == 26 * 8 + 6 * 4 + 2 * 4   # + alpha, beta, addend + 4 strides
 
 
 def test_modules_mirror_reference_surface():
