@@ -203,6 +203,21 @@ int lnb_readout(lnb_stream_t stream, const float* state, const float* W_out, con
                 int P, float* score /* [B,P] */);
 
 /* ---------------------------------------------------------------------------------------
+ * Operator chain on channel 0 of L [B,N,N,E1], per graph, starting from X [B,N,D]:
+ *   chebyshev == 0: w_s = L_0 w_{s-1} (w_0 = X), s = 1..steps   (model/dcnn.py:88-92, the short
+ *                   diffusion walk of model/lanczos_net.py:164-169);
+ *   chebyshev != 0: s_0 = L_0 X, s_k = 2 L_0 s_{k-1} - s_{k-2} with s_{-1} = X, k < steps
+ *                   (model/cheby_net.py:88-93).
+ * Result number i (0-based) is written to out[b, n, (out_col0 + block_of_step[i]) * D + d] when
+ * block_of_step[i] >= 0 (host array of `steps` ints); out strides in elements.  One launch for
+ * the whole chain: operator and walk stay in shared memory / registers.  N <= 32, steps <= 64
+ * (LNB_ERR_UNSUPPORTED otherwise: callers use lnb_batched_gemm per step).
+ * ------------------------------------------------------------------------------------- */
+int lnb_operator_chain(lnb_stream_t stream, const float* L, const float* X, int B, int N, int E1,
+                       int D, int steps, int chebyshev, const int* block_of_step /* host */,
+                       float* out, int64_t out_batch_stride, int64_t out_row_stride, int out_col0);
+
+/* ---------------------------------------------------------------------------------------
  * Gaussian-kernel graph Laplacian (model/ada_lanczos_net.py:101-137, adjacency from :310-311):
  *   adj = (L[b,i,j,0] != 0);  dist2 = |x_i - x_j|^2;  sigma2 = mean over all N^2 pairs;
  *   A = exp(-dist2/sigma2) * adj;  d = (rowsum + [rowsum==0])^-1/2;  out = d_i A_ij d_j

@@ -84,6 +84,8 @@ SIGNATURES = {
     'lnb_ritz_power_table': (c_int, [c_stream, c_f32p, c_i64, ctypes.POINTER(c_int), c_int, c_f32p]),
     'lnb_readout': (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p,
                             c_int, c_int, c_int, c_int, c_f32p]),
+    'lnb_operator_chain': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   ctypes.POINTER(c_int), c_f32p, c_i64, c_i64, c_int]),
     'lnb_gaussian_laplacian': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_lanczos_tridiag': (c_int, [c_stream, c_f32p, ctypes.c_void_p, c_f32p, c_int, c_int, c_int,
                                     c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),

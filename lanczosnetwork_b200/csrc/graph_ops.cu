@@ -161,6 +161,72 @@ gaussian_laplacian_kernel(const float* __restrict__ x, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// Operator chain on channel 0 of the operators, one CTA per graph, thread <-> feature column:
+//   power mode     w_s = L_0 w_{s-1}, w_0 = X               (model/dcnn.py:88-92, lanczos_net.py:164-169)
+//   Chebyshev mode s_0 = L_0 X, s_k = 2 L_0 s_{k-1} - s_{k-2}, s_{-1} = X   (model/cheby_net.py:88-93)
+// The N x N operator (transposed, so 4 rows of one column are one LDS.128) and the current walk
+// live in shared memory; a thread keeps its column of the new walk in N <= 32 registers, so one
+// step costs N^2 FMA + N^2/4 broadcast loads per thread.  Selected steps are written straight into
+// their column block of the message matrix (block index = sel[step], < 0: not stored).
+constexpr int CHAIN_NMAX = 32, CHAIN_STEPS_MAX = 64;
+struct ChainSel { int8_t blk[CHAIN_STEPS_MAX]; };
+
+__global__ void __launch_bounds__(128)
+operator_chain_kernel(const float* __restrict__ L, const float* __restrict__ X, int N, int E1, int D,
+                      int steps, int cheby, ChainSel sel, float* __restrict__ out, int64_t out_sb,
+                      int64_t out_sn, int out_col0) {
+  __shared__ __align__(16) float Lt[CHAIN_NMAX][CHAIN_NMAX];   // Lt[i][n] = L_0[n][i]
+  extern __shared__ __align__(16) float walk[];                // [2][N][Dc] ping-pong, Dc = blockDim.x
+  const int g = blockIdx.x, d0 = blockIdx.y * blockDim.x, t = threadIdx.x;
+  const int Dc = blockDim.x;
+  const bool live = d0 + t < D;
+  const float* Lg = L + (int64_t)g * N * N * E1;
+  for (int e = t; e < CHAIN_NMAX * CHAIN_NMAX; e += Dc) {
+    const int i = e / CHAIN_NMAX, n = e % CHAIN_NMAX;
+    Lt[i][n] = (i < N && n < N) ? __ldg(Lg + ((int64_t)n * N + i) * E1) : 0.f;
+  }
+  float* w0 = walk;
+  float* w1 = walk + (size_t)N * Dc;
+  const float* Xg = X + (int64_t)g * N * D + d0;
+  for (int n = 0; n < N; ++n) w0[n * Dc + t] = live ? __ldg(Xg + (int64_t)n * D + t) : 0.f;
+  __syncthreads();
+  float* og = out + (int64_t)g * out_sb + d0 + t;
+  float prev2[CHAIN_NMAX];                                     // Chebyshev: s_{k-2} of this column
+#pragma unroll
+  for (int n = 0; n < CHAIN_NMAX; ++n) prev2[n] = (cheby && n < N) ? w0[n * Dc + t] : 0.f;
+  for (int s = 0; s < steps; ++s) {
+    float acc[CHAIN_NMAX];
+#pragma unroll
+    for (int n = 0; n < CHAIN_NMAX; ++n) acc[n] = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const float o = w0[i * Dc + t];
+      const float4* l4 = reinterpret_cast<const float4*>(&Lt[i][0]);
+#pragma unroll
+      for (int q = 0; q < CHAIN_NMAX / 4; ++q) {
+        const float4 l = l4[q];
+        acc[4 * q + 0] = fmaf(l.x, o, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(l.y, o, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(l.z, o, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(l.w, o, acc[4 * q + 3]);
+      }
+    }
+    const int blk = sel.blk[s];
+#pragma unroll
+    for (int n = 0; n < CHAIN_NMAX; ++n) {
+      if (n < N) {
+        float v = acc[n];
+        if (cheby && s > 0) {                                  // s_k = 2 L s_{k-1} - s_{k-2}
+          v = 2.0f * v - prev2[n];
+          prev2[n] = w0[n * Dc + t];
+        }
+        w1[n * Dc + t] = v;
+        if (blk >= 0 && live) og[(int64_t)n * out_sn + (int64_t)(out_col0 + blk) * D] = v;
+      }
+    }
+    __syncthreads();
+    float* tmp = w0; w0 = w1; w1 = tmp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -247,6 +313,28 @@ int lnb_gaussian_laplacian(lnb_stream_t stream, const float* x, const float* L, 
   gaussian_laplacian_kernel<<<B, GL_THREADS, shm, (cudaStream_t)stream>>>(x, L, N, Dx, E1, out);
   lnb::count_launch();
   return lnb::finish_launch("gaussian_laplacian");
+}
+
+int lnb_operator_chain(lnb_stream_t stream, const float* L, const float* X, int B, int N, int E1,
+                       int D, int steps, int chebyshev, const int* block_of_step, float* out,
+                       int64_t out_batch_stride, int64_t out_row_stride, int out_col0) {
+  LNB_REQUIRE(L && X && out && block_of_step, "operator_chain: null pointer");
+  LNB_REQUIRE(B >= 0 && N >= 1 && E1 >= 1 && D >= 1 && steps >= 1, "operator_chain: bad dims");
+  if (N > CHAIN_NMAX || steps > CHAIN_STEPS_MAX) {
+    lnb::set_err("operator_chain: N=%d steps=%d exceed the register-resident kernel (N <= %d, steps <= %d)",
+                 N, steps, CHAIN_NMAX, CHAIN_STEPS_MAX);
+    return LNB_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return LNB_OK;
+  ChainSel sel;
+  for (int s = 0; s < CHAIN_STEPS_MAX; ++s) sel.blk[s] = s < steps ? (int8_t)block_of_step[s] : (int8_t)-1;
+  const int threads = 128;
+  dim3 grid((unsigned)B, (unsigned)lnb::ceil_div(D, threads));
+  const size_t shm = (size_t)2 * N * threads * sizeof(float);
+  operator_chain_kernel<<<grid, threads, shm, (cudaStream_t)stream>>>(
+      L, X, N, E1, D, steps, chebyshev ? 1 : 0, sel, out, out_batch_stride, out_row_stride, out_col0);
+  lnb::count_launch();
+  return lnb::finish_launch("operator_chain");
 }
 
 int lnb_split_tf32(lnb_stream_t stream, const float* x, int64_t n, float* hi, float* lo) {

@@ -72,8 +72,11 @@ class ChebyNet(SpectralNetBase):
       ops.bgemm(L, (N * N * E1, 1, N * E1, E1), state, x_str, msg, (N * CD, D, CD, 1),
                 B, E, N, D, N, a_off=1)
       # s_0 = L_0 X (:90), then s_k = 2 L_0 s_{k-1} - s_{k-2} with s_{-1} = X (:91-93)
-      ops.bgemm(L, l0, state, x_str, msg, blk, B, 1, N, D, N, c_off=E * D)
-      for k in range(1, order):
+      if ops.operator_chain_supported(N, order):             # the whole chain in one launch
+        ops.operator_chain(L, state, order, list(range(order)), msg, E, chebyshev=True)
+      else:
+        ops.bgemm(L, l0, state, x_str, msg, blk, B, 1, N, D, N, c_off=E * D)
+      for k in range(1, order if not ops.operator_chain_supported(N, order) else 0):
         prev2 = (state, x_str, 0) if k == 1 else (msg, blk, (E + k - 2) * D)
         ops.bgemm(L, l0, msg, blk, msg, blk, B, 1, N, D, N, b_off=(E + k - 1) * D,
                   c_off=(E + k) * D, alpha=2.0, addend=prev2[0], add_str=(prev2[1][0], 0, prev2[1][2], 1),

@@ -4,15 +4,17 @@ the powers ``L_0^k X`` for k in diffusion_dist (a chain of max(diffusion_dist) s
 concatenated edges-first, Linear + ReLU; then the shared gated readout.  Same constructor,
 parameter names and ``forward(node_feat, L, label=None, mask=None)``.
 
-The power chain needs every row of the previous walk, so this model runs through the general-shape
-ops (FFMA batched GEMMs for the chain, the 3xTF32 tcgen05 dense layer for the Linear) rather than
-the one-launch stack; the whole forward is still one CUDA-graph replay."""
+The power chain needs every row of the previous walk, so this model does not fit the one-launch
+stack: per layer one ``lnb_operator_chain`` launch runs all max(diffusion_dist) steps with the
+operator and the walk on chip (N <= 32; larger graphs fall back to one batched GEMM per step), one
+batched GEMM does the edge types, and the Linear runs on the 3xTF32 tcgen05 dense layer; the whole
+forward is one CUDA-graph replay."""
 import torch
 import torch.nn as nn
 
 from ._common import SpectralNetBase, _opt
 from ..data import check_dist
-from ..spectral_conv import WeightCache, graph_conv_layer_unfused
+from ..spectral_conv import WeightCache, dense, graph_conv_layer_unfused
 from .. import ops
 
 __all__ = ['DCNN']
@@ -71,7 +73,22 @@ class DCNN(SpectralNetBase):
 
   def _forward_impl(self, node_feat, L, mask):
     L = L.float().contiguous()
+    B, N, _, E1 = L.shape
     state = ops.embedding_rows(node_feat.long(), self.embedding.weight)
+    if ops.operator_chain_supported(N, self.max_dist):
+      # reference column order: [edge types | diffusion scales] (dcnn.py:98), no weight permutation
+      sel = [self.diffusion_dist.index(s) if s in self.diffusion_dist else -1
+             for s in range(1, self.max_dist + 1)]
+      for t in range(self.num_layer):
+        D = state.shape[2]
+        CD = (E1 + self.num_scale) * D
+        msg = torch.empty((B, N, CD), device=state.device, dtype=torch.float32)
+        ops.bgemm(L, (N * N * E1, 1, N * E1, E1), state, (N * D, 0, D, 1), msg, (N * CD, D, CD, 1),
+                  B, E1, N, D, N)
+        ops.operator_chain(L, state, self.max_dist, sel, msg, E1)
+        state = dense(msg.reshape(B * N, CD), self.filter[t].weight, self.filter[t].bias, True,
+                      self._wcache, 'filter.%d' % t).reshape(B, N, -1)
+      return self._readout(state, mask)
     for t in range(self.num_layer):
       state = graph_conv_layer_unfused(state, L, None, None, False, self.short_diffusion_dist, 0,
                                        self._layer_weight(t), self.filter[t].bias, self._wcache,

@@ -14,7 +14,7 @@ from ._lib import GemmDesc, SpectralStack
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
     'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
-    'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
+    'operator_chain', 'operator_chain_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
 
@@ -354,6 +354,27 @@ def readout(state, W_out, b_out, w_att, b_att, mask=None):
     _lib.check(_lib.load().lnb_readout(_stream(state), _ptr(state), _ptr(_f32c(W_out)),
                                        _ptr(_f32c(b_out)), _ptr(_f32c(w_att)), _ptr(_f32c(b_att)),
                                        _ptr(mask), B, N, H, P, _ptr(out)), 'lnb_readout')
+  return out
+
+
+def operator_chain_supported(N, steps):
+  return N <= 32 and steps <= 64
+
+
+def operator_chain(L, X, steps, block_of_step, out, out_col0, chebyshev=False):
+  """Power / Chebyshev chain of channel 0 of L [B,N,N,E1] applied to X [B,N,D]; result i goes to
+  column block out_col0 + block_of_step[i] of out [B,N,C*D] (block < 0: not stored)."""
+  _need_cuda(L, X, out)
+  L, X = _f32c(L), _f32c(X)
+  B, N, D = X.shape
+  E1 = L.shape[3]
+  assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[:2] == (B, N)
+  sel = (ctypes.c_int * steps)(*[int(v) for v in block_of_step])
+  with torch.cuda.device(X.device):
+    _lib.check(_lib.load().lnb_operator_chain(_stream(X), _ptr(L), _ptr(X), B, N, E1, D, int(steps),
+                                              1 if chebyshev else 0, sel, _ptr(out),
+                                              out.stride(0), out.stride(1), int(out_col0)),
+               'lnb_operator_chain')
   return out
 
 

@@ -493,3 +493,33 @@ def test_spectral_stack_equals_layer_by_layer():
                                            readout=(W_out, b_out, w_att, b_att), mask=None)
   torch.testing.assert_close(score2, ops().readout(state, W_out, b_out, w_att, b_att, None),
                              rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('cheby', [False, True])
+def test_operator_chain_matches_step_by_step(cheby):
+  """lnb_operator_chain (power chain of model/dcnn.py:88-92, Chebyshev chain of
+  model/cheby_net.py:88-93) against the step-by-step fp64 recurrence."""
+  B, N, D, E1, steps = 9, 26, 160, 3, 12
+  g = torch.Generator().manual_seed(77 + int(cheby))
+  L = torch.randn(B, N, N, E1, generator=g) * (torch.rand(B, N, N, E1, generator=g) < 0.2) / 3
+  X = torch.randn(B, N, D, generator=g)
+  sel = [-1 if s % 3 == 1 else s for s in range(steps)]       # some steps are not stored
+  out = torch.full((B, N, (2 + steps) * D), 7.0).to(dev())
+  ops().operator_chain(L.to(dev()), X.to(dev()), steps, sel, out, 2, chebyshev=cheby)
+  L0 = L[..., 0].double()
+  prev2, cur, ref = X.double(), X.double(), []
+  for s in range(steps):
+    nxt = torch.bmm(L0, cur)
+    if cheby and s > 0:
+      nxt = 2.0 * nxt - prev2
+    prev2, cur = cur, nxt
+    ref.append(nxt)
+  got = out.cpu().double()
+  assert torch.all(got[:, :, :2 * D] == 7.0)                   # blocks in front untouched
+  for s in range(steps):
+    blk = got[:, :, (2 + s) * D:(3 + s) * D]
+    if sel[s] < 0:
+      assert torch.all(blk == 7.0)
+    else:
+      scale = ref[s].abs().max().item()
+      assert (blk - ref[s]).abs().max().item() <= 2e-6 * max(1.0, scale) * (s + 1), s

@@ -232,6 +232,25 @@ def test_cheby_net_matches_reference_golden():
   assert e_ours <= max(4 * e_ref, 1.5e-5), (e_ours, e_ref)
 
 
+def test_sibling_models_large_graphs_use_the_per_step_path():
+  """N > 32: the operator chain of DCNN / ChebyNet falls back to one batched GEMM per step."""
+  rng = np.random.RandomState(3)
+  B, N = 3, 40
+  L = (rng.randn(B, N, N, 7) * (rng.rand(B, N, N, 7) < 0.1) / 4).astype(np.float32)
+  nf = rng.randint(0, 70, size=(B, N))
+  mask = (np.arange(N)[None, :] < np.array([40, 33, 17])[:, None]).astype(np.uint8)
+  for cls, cfg, fwd in (
+      (DCNN, configs.qm8_dcnn(num_layer=2, hidden_dim=[32, 32], diffusion_dist=[2, 5]),
+       lambda p, c: orc.dcnn_forward(p, c.model.diffusion_dist, 6, 2, nf, L, mask)),
+      (ChebyNet, configs.qm8_cheby_net(num_layer=2, hidden_dim=[32, 32], polynomial_order=4),
+       lambda p, c: orc.cheby_net_forward(p, 4, 6, 2, nf, L, mask))):
+    mod, params = _build(cls, cfg, 99)
+    with torch.no_grad():
+      out = mod(_t(nf).to(dev()), _t(L).to(dev()), mask=_t(mask).to(dev()))
+    ref = fwd(params, cfg).numpy()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=FWD_RTOL, atol=FWD_ATOL * max(1.0, np.abs(ref).max()))
+
+
 def ops_launches():
   from lanczosnetwork_b200 import ops
   return ops.launch_count()
