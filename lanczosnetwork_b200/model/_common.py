@@ -237,8 +237,7 @@ class SpectralNetBase(nn.Module):
     din0 = self.embedding.weight.shape[1] if node_ids is not None else state.shape[2]
     dims = [din0] + list(self.hidden_dim)
     ok = [ops.fused_conv_supported(N, dims[t], K, dims[t + 1], len(self.short_diffusion_dist),
-                                   False, S, E1) and (t == 0 or dims[t] == dims[t + 1] or True)
-          for t in range(nl)]
+                                   False, S, E1) for t in range(nl)]
     H = dims[1]
     uniform = all(d == H for d in dims[1:])
     first = 0

@@ -1,7 +1,6 @@
 """Drop-in for the reference ``model.LanczosNet`` (model/lanczos_net.py:13-199): same
 constructor, parameter names and ``forward(node_feat, L, D, V, label=None, mask=None)``;
 the forward runs in hand-written sm_100a CUDA (no CPU path)."""
-import torch
 import torch.nn as nn
 
 from ._common import SpectralNetBase

@@ -1,7 +1,6 @@
 """Drop-in for the reference ``model.LanczosNetGeneral`` (model/lanczos_net_general.py:13-201):
 LanczosNet with float node features instead of an atom embedding (:156) and the edge-type
 count taken from ``config.dataset.num_edge_type`` (:24)."""
-import torch
 
 from ._common import SpectralNetBase
 

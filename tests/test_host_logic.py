@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ROOT, deterministic_state_dict, load_golden
+from helpers import ROOT, load_golden
 from lanczosnetwork_b200 import configs, data
 from oracle import graph_prep
 

@@ -3,7 +3,6 @@ numbers are copied into profiles/).  Run on the B200 box:  python tools/bench_co
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch

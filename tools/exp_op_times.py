@@ -40,7 +40,6 @@ with torch.no_grad():
     mod(t['node_feat'], t['L'], t['D'], t['V'], mask=t['node_mask'])
   for n in names:
     setattr(ops, n, wrap(n))
-  import lanczosnetwork_b200.spectral_conv as sc
   for _ in range(10):
     mod(t['node_feat'], t['L'], t['D'], t['V'], mask=t['node_mask'])
   torch.cuda.synchronize()

@@ -2,9 +2,7 @@
 Times lnb_linear_tf32x3 and lnb_spectral_conv_fused with LNB_DBG debug bits set."""
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
