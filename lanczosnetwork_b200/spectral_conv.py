@@ -212,7 +212,13 @@ def graph_conv_layer_unfused(state, L, Qv, coeff, dense_filter, short_dist, num_
   x_str = (N * Din, 0, Din, 1)
   col = 0
   # ---- short diffusion chain: walk <- L0 walk (lanczos_net.py:164-169) --------------------
-  if n_short:
+  if n_short and ops.operator_chain_supported(N, max(short_dist)):
+    # the whole walk in one launch (operator and walk on chip), selected steps -> column blocks
+    steps = sorted(short_dist)
+    sel = [steps.index(s) if s in steps else -1 for s in range(1, max(short_dist) + 1)]
+    ops.operator_chain(L, state, max(short_dist), sel, msg, 0)
+    col = n_short
+  elif n_short:
     l0_str = (N * N * E1, 0, N * E1, E1)
     src, src_str, src_off = state, x_str, 0
     tmp = None
