@@ -10,8 +10,14 @@ numpy-seeded weights, fp32 (the big Linear runs as 3xTF32 on tcgen05 = fp32-grad
 A step = one forward over one batch.  ``value`` = molecules/s with inputs resident in HBM;
 ``e2e`` = the same through the module's public forward() with pinned HOST inputs (H2D of
 node_feat/L/D/V/mask and D2H of the scores inside the timed region).  Multi-GPU: one process
-per GPU (torchrun), batch shards with no data-path collective, one NCCL all-gather of the
-[B,16] predictions per step; weak scaling.
+per GPU (torchrun), batch shards with no data-path collective; the per-step predictions stay on
+the device and ONE NCCL all-gather of all [steps*B,16] predictions closes the timed region
+(a single gather of per-graph predictions); weak scaling.
+
+The default line also carries a ``workloads`` block (rank 0, N=1 only): the other BASELINE.json
+configs measured in the same run -- the batched Lanczos + Ritz kernels at QM8 size (config #2's
+provider), the K=40 sweep N in {64,256,1024} (config #5) against the HBM roofline, and the
+AdaLanczosNet forward (config #3).
 """
 import argparse
 import json
@@ -162,7 +168,11 @@ def run_reference_arm(args):
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': 'QM8 LanczosNet forward (config/qm8_lanczos_net.yaml), K=20, '
                              'N=26; CPU oracle port of model/lanczos_net.py on %d-molecule '
-                             'batches' % sample},
+                             'batches' % sample,
+                 'reference_batch': sample, 'same_config': False,
+                 'note': 'bounded sample: the CPU arm steps over %d-molecule batches (the B200 arm '
+                         'over 1024); molecules/s is per molecule, so the ratio is not inflated by '
+                         'the smaller batch (the port is not faster at 1024)' % sample},
       'cpu_baseline': {'value': value, 'unit': 'molecules/s', 'cores': cores, 'kind': 'port',
                        'sample': '%d steps x %d molecules, torch CPU fp32, best of {4,8,16,32,all} '
                                  'threads = %d (host has %d cores)'
@@ -174,6 +184,136 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(local):
+  """Bind this rank's host threads to the CPUs of its GPU's NUMA node before the pinned staging
+  buffers are allocated (first touch places them on that node): eight ranks pushing H2D through
+  one socket's memory was the e2e scaling limiter of round 1."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(local)
+    bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+    bus = bus.decode() if isinstance(bus, bytes) else bus
+    path = '/sys/bus/pci/devices/%s/local_cpulist' % bus.lower()[-12:]
+    with open(path) as fh:
+      spec = fh.read().strip()
+    cpus = set()
+    for part in spec.split(','):
+      lo, _, hi = part.partition('-')
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    cpus &= os.sched_getaffinity(0)
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      return spec
+  except Exception:
+    pass
+  return None
+
+
+def gnp_operator(rng, N, p):
+  """L4 = D^-1/2 (A + I) D^-1/2 of a G(N, p) graph (SURVEY 8d config #5), fp32."""
+  from lanczosnetwork_b200 import data
+  upper = np.triu(rng.rand(N, N) < p, k=1)
+  adj = (upper | upper.T).astype(np.float64)
+  return data.get_laplacian(adj).astype(np.float32)
+
+
+def lanczos_alg_bytes(N, K, with_ritz):
+  """SURVEY 8(d) compulsory bytes per graph of the Lanczos(+QL+Ritz) kernel:
+  4N^2 (A) + 4N (q1) + N (mask) + 4NK (Q) + 4(2K-1) (alpha, beta)  [+ 4NK + 4K when V, theta are written]."""
+  b = 4 * N * N + 4 * N + N + 4 * N * K + 4 * (2 * K - 1)
+  if with_ritz:
+    b += 4 * N * K + 4 * K
+  return b
+
+
+def time_events(fn, iters, warm):
+  for _ in range(warm):
+    fn()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(iters):
+    fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / iters
+
+
+def run_workloads(dev, peaks):
+  """The non-headline BASELINE.json configs, measured in the same run (rank 0, N=1).  Every entry:
+  CUDA-event ms over >= 3 launches after warm-up, graphs (molecules) per second, ALGORITHMIC
+  GB/s (SURVEY 8d bytes, never re-reads) and its fraction of the measured HBM copy bandwidth;
+  ``traffic`` = ncu dram bytes per launch from the committed capture named in ``traffic_source``."""
+  from helpers import deterministic_state_dict
+  from lanczosnetwork_b200 import configs, data, ops
+  from lanczosnetwork_b200.model import AdaLanczosNet
+  hbm = peaks['hbm_gbs']
+  tpath = os.path.join(ROOT, 'profiles', 'workloads_traffic.json')
+  traffic = {}
+  if os.path.exists(tpath):
+    with open(tpath) as fh:
+      traffic = json.load(fh)
+  out = {}
+
+  def entry(name, ms, graphs, alg_bytes_per_graph, extra=None):
+    gbs = graphs * alg_bytes_per_graph / (ms * 1e-3) / 1e9
+    rec = {'ms': ms, 'graphs': graphs, 'graphs_per_s': graphs / (ms * 1e-3),
+           'alg_bytes_per_graph': alg_bytes_per_graph, 'alg_GBs': gbs, 'frac_hbm': gbs / hbm,
+           'peak_GBs': hbm, 'peak_source': peaks['source'],
+           'traffic': traffic.get(name, {}).get('dram_bytes_per_launch'),
+           'traffic_source': traffic.get(name, {}).get('source')}
+    rec.update(extra or {})
+    out[name] = rec
+
+  # --- config #2's provider at QM8 size: adjacency -> Lanczos -> QL -> Ritz pairs, B=1024, N=26, K=20
+  batch = data.synthetic_qm8_batch(1024, seed=1)
+  A = torch.from_numpy(batch['L'][..., 0].copy()).to(dev)
+  mask = torch.from_numpy(batch['node_mask']).to(dev)
+  q1 = torch.randn(1024, 26, generator=torch.Generator().manual_seed(1)).to(dev)
+  t = time_events(lambda: ops.lanczos_ritz(A, mask, q1, 20), 20, 5)
+  entry('lanczos_qm8', t, 1024, lanczos_alg_bytes(26, 20, True),
+        {'config': 'QM8-shaped B=1024 N=26 K=20: Lanczos + QL + Ritz vectors, one launch',
+         'bound': 'latency / fp32 at this size (SURVEY 8d: AI ~ 38 flop/B)'})
+
+  # --- config #5: K=40 sweep, 10 000 graphs, L4 of G(N, min(0.5, 8/N)), n_b = N
+  for N in (64, 256, 1024):
+    K, G = 40, 10000
+    rng = np.random.RandomState(1234 + N)
+    base = np.stack([gnp_operator(rng, N, min(0.5, 8.0 / N)) for _ in range(8)])
+    Ad = torch.from_numpy(base).to(dev).repeat((G + 7) // 8, 1, 1)[:G].contiguous()
+    q1 = torch.randn(G, N, generator=torch.Generator().manual_seed(1234)).to(dev)
+    t = time_events(lambda: ops.lanczos_ritz(Ad, None, q1, K), 3, 1)
+    entry('lanczos_sweep_N%d' % N, t, G, lanczos_alg_bytes(N, K, True),
+          {'config': 'G(N,p) p=min(0.5,8/N), N=%d, K=%d, %d graphs (8 distinct operators tiled to '
+                     'distinct addresses; %.1f GB of operators > L2)' % (N, K, G, G * 4.0 * N * N / 1e9),
+           'gflops': G * (2.0 * K * N * N + 6.0 * N * K * K + 8.0 * N * K) / (t * 1e-3) / 1e9})
+    del Ad, q1
+    torch.cuda.empty_cache()
+
+  # --- config #3: QM8 AdaLanczosNet forward, K=20, B=256 (351 M parameters)
+  cfg = configs.qm8_ada_lanczos_net()
+  ada = AdaLanczosNet(cfg)
+  ada.load_state_dict(deterministic_state_dict(ada, 2024))
+  ada = ada.to(dev).eval()
+  b = data.synthetic_qm8_batch(256, seed=3)
+  nf = torch.from_numpy(b['node_feat']).to(dev)
+  L = torch.from_numpy(b['L']).to(dev)
+  mk = torch.from_numpy(b['node_mask']).to(dev)
+  with torch.no_grad():
+    t = time_events(lambda: ada(nf, L, mask=mk), 5, 3)
+  wbytes = sum(p.numel() for p in ada.parameters()) * 4
+  out['ada_qm8'] = {'ms': t, 'molecules': 256, 'molecules_per_s': 256 / (t * 1e-3),
+                    'config': 'QM8 AdaLanczosNet forward (config/qm8_ada_lanczos_net.yaml), K=20, B=256',
+                    'weight_bytes': wbytes, 'weight_stream_GBs': wbytes / (t * 1e-3) / 1e9,
+                    'frac_hbm_weights': wbytes / (t * 1e-3) / 1e9 / hbm,
+                    'bound': 'weight stream of the 4096-wide learned-filter MLP at small batch'}
+  del ada
+  torch.cuda.empty_cache()
+  return out
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -182,6 +322,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--batch', type=int, default=BATCH)
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-workloads', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -198,6 +339,7 @@ def main():
     raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torchrun)' % (args.gpus, world))
   dev = torch.device('cuda', local)
   torch.cuda.set_device(dev)
+  numa = pin_to_gpu_numa_node(local)
 
   mod, params = build_model()
   spec = oracle_spec(mod, 'LanczosNet')
@@ -209,25 +351,27 @@ def main():
   resident = [{k: v.to(dev) for k, v in p.items()} for p in pinned]
   h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
   P = 16
-  gathered = torch.empty((B * world, P), device=dev) if world > 1 else None
-  out_host = torch.empty((B * world if world > 1 else B, P)).pin_memory()
+  out_host = torch.empty((B, P)).pin_memory()
+  kept = []                  # this rank's per-step predictions, resident until the single gather
+
+  def gather_once():
+    """ONE collective for the whole timed region: [steps*B, P] per rank -> [world*steps*B, P]."""
+    if world == 1 or not kept:
+      return None
+    local_pred = torch.cat(kept, dim=0)
+    full = torch.empty((world * local_pred.shape[0], P), device=dev)
+    dist.all_gather_into_tensor(full, local_pred)
+    return full
 
   def step_resident(i):
     b = resident[i % NUM_BATCHES]
-    score = mod(b['node_feat'], b['L'], b['D'], b['V'], mask=b['node_mask'])
-    if world > 1:
-      dist.all_gather_into_tensor(gathered, score)
-      return gathered
-    return score
+    kept.append(mod(b['node_feat'], b['L'], b['D'], b['V'], mask=b['node_mask']))
 
   def step_e2e(i):
     p = pinned[i % NUM_BATCHES]
     score = mod(p['node_feat'], p['L'], p['D'], p['V'], mask=p['node_mask'])   # H2D inside
-    if world > 1:
-      dist.all_gather_into_tensor(gathered, score)
-      score = gathered
-    out_host.copy_(score, non_blocking=True)                                   # D2H
-    return score
+    out_host.copy_(score, non_blocking=True)                                   # D2H of the step's result
+    kept.append(score)
 
   def barrier():
     if world > 1:
@@ -235,16 +379,19 @@ def main():
     torch.cuda.synchronize(dev)
 
   def timed(fn, steps):
+    del kept[:]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
       fn(i)
+    gather_once()
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    del kept[:]
     return float(ms.item())
 
   with torch.no_grad():
@@ -266,6 +413,8 @@ def main():
       step_resident(i)
     for i in range(args.warmup):
       step_e2e(i)
+    gather_once()
+    del kept[:]
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.launch_count()
@@ -276,7 +425,7 @@ def main():
 
     # dominant kernel: the whole 7-layer spectral-conv stack + readout as ONE persistent tcgen05
     # kernel (K-depth 960 + 6 x 1920 per row), timed per launch with CUDA events on the
-    # launching stream.
+    # launching stream, in isolation (eager launches behind a short GPU spin).
     events = []
     orig = ops.spectral_stack_forward
 
@@ -295,6 +444,7 @@ def main():
     mod.use_cuda_graph = False            # eager launches so the events bracket single kernels
     for i in range(min(args.steps, 5)):
       step_resident(i)
+    del kept[:]
     torch.cuda.synchronize(dev)
     mod.use_cuda_graph = True
     ops.spectral_stack_forward = orig
@@ -307,12 +457,18 @@ def main():
     flops = 2.0 * M * N * K                       # algorithmic (padded B*N rows) flops per launch
     avg_ms = float(np.mean(durs))
     achieved = flops / (avg_ms * 1e-3) / 1e12
-    peak_tf32 = peaks['bf16_tflops_sustained'] / 2.0
-    traffic = None
+    # the probe times the kernel alone (5 eager launches): the BURST peak applies; the same flops over
+    # the whole replayed step are reported against the sustained peak as frac_in_step
+    peak_tf32 = peaks['bf16_tflops'] / 2.0
+    peak_tf32_sustained = peaks['bf16_tflops_sustained'] / 2.0
+    step_tflops = flops / (ms_total / args.steps * 1e-3) / 1e12
+    traffic = traffic_src = None
     tpath = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
     if os.path.exists(tpath):
       with open(tpath) as fh:
-        traffic = json.load(fh).get('dram_bytes_per_launch')
+        tj = json.load(fh)
+      traffic = tj.get('dram_bytes_per_launch')
+      traffic_src = tj.get('source')
     # what the tensor pipe really executes: packed 128-row tiles x 3 TF32 MMAs per product
     prep = ops.graph_prepare(resident[0]['L'], resident[0]['V'])
     n_tiles = int(prep[4][0].item())
@@ -321,16 +477,20 @@ def main():
     roof = {
         'bound': 'tensor', 'kernel': 'tc_gemm_kernel<SpectralPolicy> (lnb_spectral_stack_forward, 7 layers + readout)',
         'achieved': achieved, 'peak': peak_tf32, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf32,
-        'traffic': traffic, 'avg_ms_per_launch': avg_ms, 'launch_shape': [M, N, K],
+        'traffic': traffic, 'traffic_source': traffic_src,
+        'avg_ms_per_launch': avg_ms, 'launch_shape': [M, N, K],
+        'frac_in_step': step_tflops / peak_tf32_sustained, 'peak_sustained': peak_tf32_sustained,
         'executed_tensor_tflops': executed, 'frac_executed': executed / peak_tf32,
         'useful_tflops': 2.0 * real_rows * N * K / (avg_ms * 1e-3) / 1e12,
         'packed_tiles': n_tiles, 'real_rows': real_rows,
         'note': 'achieved = ALGORITHMIC fp32-equivalent GEMM flops 2*(B*N)*H*sum_l(C*D_l) of the padded '
-                'reference formulation / CUDA-event time per launch. The kernel drops padded rows '
-                '(packed tiles) and issues 3 TF32 MMAs per product (3xTF32): executed_tensor_tflops '
-                '= 3*2*(tiles*128)*H*(C*D)/t is what the tensor pipe does; useful_tflops counts real '
-                'nodes only. peak = %s bf16_tflops_sustained / 2 (TF32 rate is half the bf16 rate)'
-                % peaks['source'],
+                'reference formulation / CUDA-event time per launch, kernel timed alone -> peak = %s '
+                'bf16_tflops (burst) / 2 (TF32 rate is half the bf16 rate); frac_in_step = the same '
+                'flops / the whole replayed step against the sustained peak. The kernel drops padded '
+                'rows (packed tiles) and issues 3 TF32 MMAs per product (3xTF32): '
+                'executed_tensor_tflops = 3*2*(tiles*128)*H*(C*D)/t is what the tensor pipe does; '
+                'useful_tflops counts real nodes only. traffic = ncu dram bytes of the committed '
+                'capture named in traffic_source, not measured in this run' % peaks['source'],
     }
 
   total = B * world * args.steps
@@ -345,8 +505,13 @@ def main():
                              'batch=%d per GPU, N=26 padded, 7 layers, fp32 (3xTF32 tensor cores)' % B,
                  'global_batch': B * world, 'parallelism': 'dp%d' % world,
                  'cache': 'inputs larger than L2: %d distinct resident batches rotated '
-                          '(%.0f MB > 126 MB L2), each copied into the CUDA graph\'s static input buffers' %
-                          (NUM_BATCHES, NUM_BATCHES * h2d_bytes / 1e6)},
+                          '(%.0f MB > 126 MB L2); value: read in place by zero-copy CUDA graphs bound '
+                          'to the resident buffers; e2e: H2D from pinned host memory into the static '
+                          'input buffers of two alternating graph slots' %
+                          (NUM_BATCHES, NUM_BATCHES * h2d_bytes / 1e6),
+                 'collective': 'one all_gather_into_tensor of [steps*B,16] per rank at the end of the '
+                               'timed region' if world > 1 else 'none',
+                 'numa_cpulist': numa},
       'e2e': {'value': e2e_value, 'unit': 'molecules/s', 'h2d_bytes_per_step': h2d_bytes,
               'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': int(launches),
@@ -354,6 +519,9 @@ def main():
       'roofline': roof,
       'oracle_check_max_abs_err': max_err,
   }
+  if rank == 0 and world == 1 and not args.no_workloads:
+    with torch.no_grad():
+      line['workloads'] = run_workloads(dev, peaks)
   if rank == 0:
     if not args.no_cpu_baseline and world == 1:
       sample = 256

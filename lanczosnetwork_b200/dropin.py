@@ -38,8 +38,17 @@ def patch_namespace(module):
   return module
 
 
-def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.graph_runner')):
-  """Returns the list of patched modules.  ``reference_root`` is put on sys.path if given."""
+def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.graph_runner'),
+            compat=False):
+  """Returns the list of patched modules.  ``reference_root`` is put on sys.path if given.
+  ``compat=True`` first installs the shims of ``lanczosnetwork_b200.compat`` (missing easydict /
+  tensorboardX, PyYAML >= 6, numpy >= 2) so the 2019 checkout imports under a current stack.
+  Raises ImportError when NO runner module could be imported and patched: the runners resolve
+  the model class by name in their own namespace, so a silent miss would run the reference's
+  classes while claiming the drop-in."""
+  if compat:
+    from . import compat as _compat
+    _compat.install()
   if reference_root is not None:
     reference_root = os.path.abspath(reference_root)
     if reference_root not in sys.path:
@@ -48,12 +57,18 @@ def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.gr
   patched = []
   ref_model = importlib.import_module('model')
   patched.append(patch_namespace(ref_model))
+  errors = []
   for name in runner_modules:
     try:
       mod = importlib.import_module(name)
-    except ImportError:      # e.g. tensorboardX absent: that runner cannot be used anyway
+    except ImportError as exc:      # e.g. tensorboardX absent: that runner cannot be used anyway
+      errors.append('%s: %s' % (name, exc))
       continue
     patched.append(patch_namespace(mod))
+  if runner_modules and len(patched) == 1:
+    raise ImportError('dropin.install: no runner module could be imported, nothing would call the '
+                      'B200 classes (%s); pass compat=True for the shims of '
+                      'lanczosnetwork_b200.compat' % '; '.join(errors))
   return patched
 
 
@@ -62,7 +77,7 @@ def main(argv=None):
   if not argv:
     raise SystemExit(__doc__)
   root = argv.pop(0)
-  install(root)
+  install(root, compat=True)
   os.chdir(root)
   sys.argv = ['run_exp.py'] + argv
   run_exp = importlib.import_module('run_exp')

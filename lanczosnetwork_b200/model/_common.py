@@ -277,7 +277,8 @@ class SpectralNetBase(nn.Module):
     for t in range(first if stack_ok else nl):           # unfused / single-layer prefix
       state = graph_conv_layer(state, ctx, layer_coeff(t), False, self.short_diffusion_dist, S,
                                self.filter[t].weight, self.filter[t].bias, self._wcache,
-                               'filter.%d' % t, last=(t == nl - 1))
+                               'filter.%d' % t, last=(t == nl - 1),
+                               next_fused=(t + 1 < nl and ok[t + 1]))
     if not stack_ok:
       return self._readout(state, mask)
     layers = list(range(first, nl))

@@ -77,8 +77,10 @@ class DCNN(SpectralNetBase):
     state = ops.embedding_rows(node_feat.long(), self.embedding.weight)
     if ops.operator_chain_supported(N, self.max_dist):
       # reference column order: [edge types | diffusion scales] (dcnn.py:98), no weight permutation
-      sel = [self.diffusion_dist.index(s) if s in self.diffusion_dist else -1
-             for s in range(1, self.max_dist + 1)]
+      # scales are emitted in ascending step order like the reference loop (dcnn.py:88-92) and the
+      # general-shape path, whatever the order of the config list
+      steps = sorted(set(self.diffusion_dist))
+      sel = [steps.index(s) if s in steps else -1 for s in range(1, self.max_dist + 1)]
       for t in range(self.num_layer):
         D = state.shape[2]
         CD = (E1 + self.num_scale) * D

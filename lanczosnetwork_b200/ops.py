@@ -14,7 +14,7 @@ from ._lib import GemmDesc, SpectralStack
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
     'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
-    'operator_chain', 'operator_chain_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'tridiag_ritz', 'tridiag_powers',
+    'operator_chain', 'operator_chain_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'lanczos_ritz', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
 
@@ -423,6 +423,16 @@ def tridiag_ritz(alpha, beta, Q):
     _lib.check(_lib.load().lnb_tridiag_ritz(_stream(Q), _ptr(alpha), _ptr(beta), _ptr(Q), B, N, K,
                                             _ptr(theta), _ptr(V), _ptr(status)), 'lnb_tridiag_ritz')
   return theta, V, status
+
+
+def lanczos_ritz(A, mask, q1, K):
+  """adjacency operator -> Ritz pairs (the north-star pipeline Lanczos + QL + Ritz vectors).
+  Returns dict(theta [B,K] by descending |theta|, V [B,N,K] = Q S, status [B], plus the
+  tridiagonalisation outputs T, Q, alpha, beta, idx of lanczos_tridiag)."""
+  lz = lanczos_tridiag(A, mask, q1, K)
+  theta, V, status = tridiag_ritz(lz['alpha'], lz['beta'], lz['Q'])
+  lz.update(theta=theta, V=V, status=status)
+  return lz
 
 
 def tridiag_powers(T, powers):

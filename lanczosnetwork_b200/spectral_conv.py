@@ -175,9 +175,13 @@ class GraphContext(object):
 
 
 def graph_conv_layer(state, ctx, coeff, dense_filter, short_dist, num_long, weight, bias, cache,
-                     name, last=True):
+                     name, last=True, next_fused=False):
   """One spectral convolution layer: the fused tcgen05 kernel when the shape allows it
-  (LanczosNet-style diagonal filters), otherwise the unfused ops below."""
+  (LanczosNet-style diagonal filters), otherwise the unfused ops below.
+
+  The fused kernel may skip the constant rows of padded nodes only when the consumer of its
+  output is another fused layer (which never reads them): an unfused layer multiplies every
+  row, so 0 * uninitialised memory (NaN / Inf bit patterns) would leak into real rows."""
   L, Qv = ctx.L, ctx.Qv
   B, N, Din = state.shape
   if (num_long > 0 and Qv is not None and
@@ -185,7 +189,7 @@ def graph_conv_layer(state, ctx, coeff, dense_filter, short_dist, num_long, weig
                                num_long, L.shape[3])):
     w_hi, w_lo = cache.split(name, weight)
     return ops.spectral_conv_fused(state, Qv, coeff, ctx.prep(), w_hi, w_lo, bias, True,
-                                   write_pad=last)
+                                   write_pad=last or not next_fused)
   return graph_conv_layer_unfused(state, L, Qv, coeff, dense_filter, short_dist, num_long, weight,
                                   bias, cache, name)
 

@@ -53,6 +53,46 @@ def test_segment_sum_reference_flavours_agree_where_consistent():
   np.testing.assert_allclose(out.cpu().numpy(), a, atol=1e-6)
 
 
+def test_segment_sum_matches_compiled_reference_kernel():
+  """The reference's OWN CUDA kernels (operators/src/cuda/segment_reduction.cu:39-95), compiled from
+  where they lie by oracle/build_ref.py into oracle/_ref/, as a second checker on the domain where
+  the reference is self-consistent (num_segments == dim1, its hard-coded output batch stride
+  dim1*dim2, segment_reduction.cu:48); also pins the oracle's ``ref_cuda`` flavour."""
+  import ctypes
+  import os
+  from helpers import ROOT
+  path = os.path.join(ROOT, 'oracle', '_ref', 'libsegment_reduction_ref.so')
+  assert os.path.exists(path), 'oracle/_ref is built by __graft_entry__.build() and travels with the snapshot'
+  ref = ctypes.CDLL(path)
+  fwd = ref.unsorted_segment_sum_forward_gpu_kernel_launcher
+  bwd = ref.unsorted_segment_sum_backward_gpu_kernel_launcher
+  for f in (fwd, bwd):
+    f.restype = None
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
+                  ctypes.c_void_p]
+  rng = np.random.RandomState(11)
+  for B, C, X in ((3, 6, 4), (5, 33, 16), (1, 1, 1), (2, 70, 7)):
+    # integer-valued data: fp32 atomic sums are exact in any order -> bit-exact comparison
+    data = rng.randint(-8, 9, size=(B, C, X)).astype(np.float32)
+    seg = rng.randint(0, C, size=(B, C)).astype(np.int64)
+    d_data, d_seg = torch.from_numpy(data).to(dev()), torch.from_numpy(seg).to(dev())
+    shape = (ctypes.c_int * 3)(B, C, X)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out_ref = torch.zeros(B, C, X, device=dev())
+    fwd(stream, d_data.data_ptr(), d_seg.data_ptr(), shape, out_ref.data_ptr())
+    ours = ops().segment_sum_forward(d_data, d_seg, C)
+    torch.cuda.synchronize()
+    assert torch.equal(ours, out_ref)
+    assert np.array_equal(out_ref.cpu().numpy(), segment_oracle.segment_sum_forward(data, seg, C, 'ref_cuda'))
+    assert np.array_equal(out_ref.cpu().numpy(), segment_oracle.segment_sum_forward(data, seg, C, 'intended'))
+    gout = torch.from_numpy(rng.randn(B, C, X).astype(np.float32)).to(dev())
+    g_ref = torch.empty(B, C, X, device=dev())
+    bwd(stream, gout.data_ptr(), d_seg.data_ptr(), shape, g_ref.data_ptr())
+    g_ours = ops().segment_sum_backward(gout, d_seg, (B, C, X))
+    torch.cuda.synchronize()
+    assert torch.equal(g_ours, g_ref)
+
+
 def test_segment_sum_autograd_and_module():
   from lanczosnetwork_b200.operators.modules import UnsortedSegmentSum
   rng = np.random.RandomState(3)
