@@ -248,6 +248,25 @@ int lnb_tridiag_ritz(lnb_stream_t stream, const float* alpha, const float* beta,
                      int32_t* status /* [B] */);
 
 /* ---------------------------------------------------------------------------------------
+ * The north-star pipeline in ONE launch: operator -> K-step Lanczos (rules of
+ * model/ada_lanczos_net.py:139-247, as lnb_lanczos_tridiag) -> implicit-shift QL on (alpha, beta)
+ * -> Ritz vectors V = Q S ordered by descending |theta| (utils/data_helper.py:217-223) -- the pair
+ * (theta, V) is what utils/data_helper.py:169-226 + dataset/qm8.py:265-291 hand to
+ * LanczosNet.forward as (D, V).  One group of 32..512 threads per graph; the dense padded operator
+ * A [B,N,N] is read from HBM exactly once (its non-zeros are packed into shared memory, exact zeros
+ * contribute nothing to A q); the Krylov basis, (alpha, beta) and the QL rotations never leave the
+ * SM.  T, Q may be NULL (not written).  theta / ritz_vec / status may be NULL together: then only
+ * the tridiagonalisation is produced (AdaLanczosNet).  status[b]: bit 0 = QL sweeps exhausted,
+ * bit 1 = the graph's non-zeros did not fit on chip and its rows were streamed per iteration.
+ * Limits: N <= 1024, K <= 64 and a basis of K*(N+1) floats within shared memory
+ * (LNB_ERR_UNSUPPORTED otherwise: use lnb_lanczos_tridiag + lnb_tridiag_ritz).
+ * ------------------------------------------------------------------------------------- */
+int lnb_lanczos_ritz(lnb_stream_t stream, const float* A, const uint8_t* mask, const float* q1,
+                     int B, int N, int K, float* T, float* Q, float* alpha, float* beta,
+                     int32_t* idx, float* theta /* [B,K] */, float* ritz_vec /* [B,N,K] */,
+                     int32_t* status /* [B] */);
+
+/* ---------------------------------------------------------------------------------------
  * Powers of the tridiagonal for the learned filter (model/ada_lanczos_net.py:262-274):
  *   out[b, r, s, c] = (T_b ** powers[s])[r, c]    (the MLP input layout r*S*K + s*K + c)
  * powers: host pointer to S strictly increasing positive ints.

@@ -425,14 +425,35 @@ def tridiag_ritz(alpha, beta, Q):
   return theta, V, status
 
 
-def lanczos_ritz(A, mask, q1, K):
-  """adjacency operator -> Ritz pairs (the north-star pipeline Lanczos + QL + Ritz vectors).
-  Returns dict(theta [B,K] by descending |theta|, V [B,N,K] = Q S, status [B], plus the
-  tridiagonalisation outputs T, Q, alpha, beta, idx of lanczos_tridiag)."""
-  lz = lanczos_tridiag(A, mask, q1, K)
-  theta, V, status = tridiag_ritz(lz['alpha'], lz['beta'], lz['Q'])
-  lz.update(theta=theta, V=V, status=status)
-  return lz
+def lanczos_ritz(A, mask, q1, K, want_ritz=True, want_T=True, want_Q=True):
+  """adjacency operator -> Ritz pairs in ONE launch (Lanczos + QL + Ritz vectors fused).
+  Returns dict(alpha, beta [B,K], idx [B] int32, T [B,K,K], Q [B,N,K] when asked for, and with
+  want_ritz theta [B,K] by descending |theta|, V [B,N,K] = Q S, status [B] (bit 0: QL not
+  converged, bit 1: operator streamed because its non-zeros did not fit on chip))."""
+  _need_cuda(A, mask, q1)
+  A = _f32c(A)
+  B, N = A.shape[0], A.shape[1]
+  q1 = _f32c(q1).reshape(B, N)
+  if mask is not None:
+    mask = (mask != 0).to(torch.uint8).contiguous()
+  dev = A.device
+  out = {'alpha': torch.empty((B, K), device=dev, dtype=torch.float32),
+         'beta': torch.empty((B, K), device=dev, dtype=torch.float32),
+         'idx': torch.empty((B,), device=dev, dtype=torch.int32)}
+  if want_T:
+    out['T'] = torch.empty((B, K, K), device=dev, dtype=torch.float32)
+  if want_Q:
+    out['Q'] = torch.empty((B, N, K), device=dev, dtype=torch.float32)
+  if want_ritz:
+    out['theta'] = torch.empty((B, K), device=dev, dtype=torch.float32)
+    out['V'] = torch.empty((B, N, K), device=dev, dtype=torch.float32)
+    out['status'] = torch.empty((B,), device=dev, dtype=torch.int32)
+  with torch.cuda.device(dev):
+    _lib.check(_lib.load().lnb_lanczos_ritz(
+        _stream(A), _ptr(A), _ptr(mask), _ptr(q1), B, N, K, _ptr(out.get('T')), _ptr(out.get('Q')),
+        _ptr(out['alpha']), _ptr(out['beta']), _ptr(out['idx']), _ptr(out.get('theta')),
+        _ptr(out.get('V')), _ptr(out.get('status'))), 'lnb_lanczos_ritz')
+  return out
 
 
 def tridiag_powers(T, powers):

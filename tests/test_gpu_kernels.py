@@ -306,6 +306,142 @@ def test_tridiag_ritz_against_lapack(case):
   np.testing.assert_allclose(np.einsum('bnk,bk,bmk->bnm', V, theta, V), qtq, atol=2e-5)
 
 
+def _check_ritz(theta, V, alpha, beta, Q, T):
+  """(theta, V) of a fused launch against LAPACK on the launch's own tridiagonal."""
+  K = alpha.shape[1]
+  th_o, S_o, V_o = orc.tridiag_ritz(alpha, beta[:, :K - 1], Q)
+  theta, V = theta.astype(np.float64), V.astype(np.float64)
+  assert np.all(np.diff(np.abs(theta), axis=1) <= 1e-7)
+  np.testing.assert_allclose(np.sort(theta, axis=1), np.sort(th_o, axis=1), atol=3e-6)
+  for fn in (lambda t: t, lambda t: t * t, lambda t: np.sqrt(np.abs(t))):
+    ours = np.einsum('bnk,bk,bmk->bnm', V, fn(theta), V)
+    ref = np.einsum('bnk,bk,bmk->bnm', V_o, fn(th_o), V_o)
+    np.testing.assert_allclose(ours, ref, atol=2e-5)
+  qtq = np.einsum('bnk,bkj,bmj->bnm', Q.astype(np.float64), T.astype(np.float64), Q.astype(np.float64))
+  np.testing.assert_allclose(np.einsum('bnk,bk,bmk->bnm', V, theta, V), qtq, atol=2e-5)
+
+
+@pytest.mark.parametrize('case', ['qm8', 'small', 'nomask', 'cta64', 'cta100'])
+def test_fused_lanczos_ritz_matches_reference_outputs(case):
+  """lnb_lanczos_ritz (one launch: compress -> Lanczos -> QL -> V = Q S) against the EXECUTED
+  reference's T, Q on the five regimes of the golden file, same yardsticks as the two-kernel path;
+  its Ritz pairs against LAPACK on its own tridiagonal; and against the two-kernel path."""
+  g = load_golden('ada_lanczos_layer.npz')
+  A = torch.from_numpy(g[case + '_A'])
+  mask = None if case == 'nomask' else torch.from_numpy(g[case + '_mask'])
+  q1 = torch.from_numpy(g[case + '_q1'])
+  K = int(g[case + '_K'])
+  dm = None if mask is None else mask.to(dev())
+  out = ops().lanczos_ritz(A.to(dev()), dm, q1.to(dev()), K)
+  T_ref, Q_ref = g[case + '_T'], g[case + '_Q']
+  T, Q = out['T'].cpu().numpy(), out['Q'].cpu().numpy()
+  o64 = orc.lanczos_tridiagonalise(A.double(), mask, q1.double(), K)
+  assert np.array_equal(out['idx'].cpu().numpy(), o64['idx'].numpy())
+  assert np.array_equal(T != 0, T_ref != 0)
+  assert np.array_equal(Q != 0, Q_ref != 0)
+  eT_ref = np.abs(T_ref - o64['T'].numpy()).max()
+  eQ_ref = np.abs(Q_ref - o64['Q'].numpy()).max()
+  assert np.abs(T - o64['T'].numpy()).max() <= max(4 * eT_ref, 2e-5)
+  assert np.abs(Q - o64['Q'].numpy()).max() <= max(4 * eQ_ref, 2e-4)
+  alpha, beta = out['alpha'].cpu().numpy(), out['beta'].cpu().numpy()
+  np.testing.assert_array_equal(alpha, np.diagonal(T, axis1=1, axis2=2))
+  np.testing.assert_array_equal(beta[:, :K - 1], np.diagonal(T, offset=1, axis1=1, axis2=2))
+  assert int((out['status'] & 1).sum()) == 0
+  assert int((out['status'] & 2).sum()) == 0          # these operators are sparse: packed on chip
+  _check_ritz(out['theta'].cpu().numpy(), out['V'].cpu().numpy(), alpha, beta, Q, T)
+  # the tridiagonalisation-only call (AdaLanczosNet) returns the same T, Q bit for bit
+  only = ops().lanczos_ritz(A.to(dev()), dm, q1.to(dev()), K, want_ritz=False)
+  assert torch.equal(only['T'], out['T']) and torch.equal(only['Q'], out['Q'])
+  assert 'theta' not in only
+
+
+@pytest.mark.parametrize('N,K,B', [(26, 20, 64), (64, 40, 9), (200, 40, 5), (256, 40, 4),
+                                   (500, 24, 3), (1024, 40, 3)])
+def test_fused_lanczos_ritz_sweep_sizes_vs_fp64(N, K, B):
+  """Every thread-group configuration of the fused kernel (32 ... 512 threads per graph) on
+  G(n, min(0.5, 8/n)) operators with ragged sizes: idx exact, T / Q within 4x the fp32 oracle's own
+  distance from the fp64 oracle, Ritz pairs against LAPACK."""
+  import bench
+  rng = np.random.RandomState(N + K)
+  A = np.zeros((B, N, N), np.float32)
+  mask = np.zeros((B, N), np.uint8)
+  for b in range(B):
+    n = N if b == 0 else int(rng.randint(N // 2, N + 1))
+    A[b, :n, :n] = bench.gnp_operator(rng, n, min(0.5, 8.0 / n))
+    mask[b, :n] = 1
+  q1 = rng.randn(B, N).astype(np.float32)
+  out = ops().lanczos_ritz(torch.from_numpy(A).to(dev()), torch.from_numpy(mask).to(dev()),
+                           torch.from_numpy(q1).to(dev()), K)
+  o64 = orc.lanczos_tridiagonalise(torch.from_numpy(A).double(), torch.from_numpy(mask),
+                                   torch.from_numpy(q1).double(), K)
+  o32 = orc.lanczos_tridiagonalise(torch.from_numpy(A), torch.from_numpy(mask),
+                                   torch.from_numpy(q1), K)
+  assert np.array_equal(out['idx'].cpu().numpy(), o64['idx'].numpy())
+  eT = np.abs(o32['T'].numpy() - o64['T'].numpy()).max()
+  eQ = np.abs(o32['Q'].numpy() - o64['Q'].numpy()).max()
+  T, Q = out['T'].cpu().numpy(), out['Q'].cpu().numpy()
+  assert np.abs(T - o64['T'].numpy()).max() <= max(4 * eT, 2e-5)
+  assert np.abs(Q - o64['Q'].numpy()).max() <= max(4 * eQ, 2e-4)
+  assert int(out['status'].sum()) == 0
+  _check_ritz(out['theta'].cpu().numpy(), out['V'].cpu().numpy(), out['alpha'].cpu().numpy(),
+              out['beta'].cpu().numpy(), Q, T)
+
+
+def test_fused_lanczos_ritz_dense_operator_streams_and_agrees():
+  """A dense operator does not fit the on-chip pool: the kernel streams its rows per iteration
+  (status bit 1) and must agree with the packed path's arithmetic on the same matrix -- here
+  checked against the fp64 oracle like every other case -- and with the two-kernel path."""
+  rng = np.random.RandomState(5)
+  for N, K, B in ((26, 20, 7), (96, 24, 3), (300, 16, 2)):
+    M = rng.randn(B, N, N).astype(np.float32) / np.sqrt(N)
+    A = ((M + M.transpose(0, 2, 1)) * 0.5).astype(np.float32)
+    q1 = rng.randn(B, N).astype(np.float32)
+    dA, dq = torch.from_numpy(A).to(dev()), torch.from_numpy(q1).to(dev())
+    out = ops().lanczos_ritz(dA, None, dq, K)
+    if N * N > 65535 or N > 26:
+      assert int((out['status'] & 2).min()) == 2
+    o64 = orc.lanczos_tridiagonalise(torch.from_numpy(A).double(), None, torch.from_numpy(q1).double(), K)
+    o32 = orc.lanczos_tridiagonalise(torch.from_numpy(A), None, torch.from_numpy(q1), K)
+    assert np.array_equal(out['idx'].cpu().numpy(), o64['idx'].numpy())
+    eT = np.abs(o32['T'].numpy() - o64['T'].numpy()).max()
+    T, Q = out['T'].cpu().numpy(), out['Q'].cpu().numpy()
+    assert np.abs(T - o64['T'].numpy()).max() <= max(4 * eT, 2e-5)
+    assert int((out['status'] & 1).sum()) == 0
+    _check_ritz(out['theta'].cpu().numpy(), out['V'].cpu().numpy(), out['alpha'].cpu().numpy(),
+                out['beta'].cpu().numpy(), Q, T)
+
+
+def test_fused_lanczos_ritz_edges():
+  """Empty batch, N = 1, N < K (zero padding), all-masked graph next to a full one, unsupported
+  sizes refused loudly."""
+  o = ops()
+  z = o.lanczos_ritz(torch.zeros(0, 5, 5, device=dev()), None, torch.zeros(0, 5, device=dev()), 4)
+  assert z['theta'].shape == (0, 4) and z['V'].shape == (0, 5, 4)
+  one = o.lanczos_ritz(torch.full((2, 1, 1), 0.5, device=dev()), None, torch.ones(2, 1, device=dev()), 3)
+  assert one['idx'].tolist() == [0, 0] or one['idx'].tolist() == [1, 1]
+  ref = orc.lanczos_tridiagonalise(torch.full((2, 1, 1), 0.5), None, torch.ones(2, 1), 3)
+  assert one['idx'].cpu().tolist() == ref['idx'].tolist()
+  np.testing.assert_allclose(one['T'].cpu().numpy(), ref['T'].numpy(), atol=1e-6)
+  rng = np.random.RandomState(8)
+  N, K = 6, 10
+  import bench
+  A = np.stack([bench.gnp_operator(rng, N, 0.5) for _ in range(3)])
+  mask = np.ones((3, N), np.uint8); mask[1, 4:] = 0
+  A[1, 4:, :] = 0; A[1, :, 4:] = 0
+  q1 = rng.randn(3, N).astype(np.float32)
+  out = o.lanczos_ritz(torch.from_numpy(A).to(dev()), torch.from_numpy(mask).to(dev()),
+                       torch.from_numpy(q1).to(dev()), K)
+  r64 = orc.lanczos_tridiagonalise(torch.from_numpy(A).double(), torch.from_numpy(mask),
+                                   torch.from_numpy(q1).double(), K)
+  assert np.array_equal(out['idx'].cpu().numpy(), r64['idx'].numpy())
+  np.testing.assert_allclose(out['T'].cpu().numpy(), r64['T'].numpy(), atol=2e-5)
+  assert out['T'].shape == (3, K, K) and float(out['T'][:, N:, :].abs().sum()) == 0.0
+  with pytest.raises(RuntimeError):
+    o.lanczos_ritz(torch.zeros(1, 1100, 1100, device=dev()), None, torch.ones(1, 1100, device=dev()), 8)
+  with pytest.raises(RuntimeError):
+    o.lanczos_ritz(torch.zeros(1, 8, 8), None, torch.ones(1, 8), 4)          # CPU tensors: loud
+
+
 def test_tridiag_powers_and_symmetrize():
   g = load_golden('ada_lanczos_layer.npz')
   T = torch.from_numpy(g['qm8_T'])
