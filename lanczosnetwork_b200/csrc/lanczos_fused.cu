@@ -36,6 +36,7 @@ struct FusedParams {
   int cap;            // CSR pool capacity per graph (entries)
   int pool_words;     // 4-byte words reserved for the pool / the QL scratch that aliases it
   int per_graph;      // 4-byte words of shared memory per graph
+  unsigned long long* prof;   // profiling aid (lnb_debug_set_prof): per-phase clock64 totals, [8] = graphs
 };
 
 template <int TPG>
@@ -91,6 +92,13 @@ lanczos_ritz_kernel(const FusedParams P) {
   uint16_t* pcol = reinterpret_cast<uint16_t*>(pval + P.cap);
   float* Qs = pval + P.pool_words;              // K x NS      Krylov basis, row i = q_i
   int flip = 0;
+  long long tph = P.prof ? clock64() : 0;
+#define LNB_PHASE(k)                                                          \
+  if (P.prof && t == 0) {                                                     \
+    const long long now_ = clock64();                                         \
+    atomicAdd(&P.prof[k], (unsigned long long)(now_ - tph));                  \
+    tph = now_;                                                               \
+  }
 
   // ---- 0. init ----------------------------------------------------------------------------------
   if (t < 4) ctl[t] = 0;
@@ -130,6 +138,7 @@ lanczos_ritz_kernel(const FusedParams P) {
       ctl[1] = 1;
     }
   }
+  LNB_PHASE(0)
   // ---- start vector (ada_lanczos_net.py:159-167) --------------------------------------------------
   float q[NPT], qp[NPT], z[NPT];
   float cnt_real = 0.f, part = 0.f;
@@ -156,6 +165,7 @@ lanczos_ritz_kernel(const FusedParams P) {
   gbar<TPG>(grp);
   const bool dense = ctl[1] != 0;               // pool overflow: stream the dense rows instead
 
+  LNB_PHASE(1)
   // ---- 2. Lanczos ----------------------------------------------------------------------------------
   float beta_prev = 0.f, valid = 1.f;
   int count = 0;
@@ -290,6 +300,7 @@ lanczos_ritz_kernel(const FusedParams P) {
     gbar<TPG>(grp);
   }
 
+  LNB_PHASE(2)
   // ---- 3. masking rules + tridiagonal outputs (ada_lanczos_net.py:207-245) ------------------------
   const int idx = count < nreal ? count : nreal;
   // basis: columns k >= idx (or >= iters) and rows n >= idx are zero
@@ -333,7 +344,11 @@ lanczos_ritz_kernel(const FusedParams P) {
       Qg[e] = Qs[(size_t)k * NS + n];
     }
   }
-  if (!P.theta) return;
+  LNB_PHASE(3)
+  if (!P.theta) {
+    if (P.prof && t == 0) atomicAdd(&P.prof[8], 1ull);
+    return;
+  }
 
   // ---- 4. QL with implicit shifts on (al, be); rotations on the rows of a K x K identity ------------
   // scratch aliases the pool (the operator is dead): Zt[i][k] (column i of Z over rows k), then
@@ -349,64 +364,74 @@ lanczos_ritz_kernel(const FusedParams P) {
   gbar<TPG>(grp);
   int fail = 0;
   if (wg == 0) {
+    // All lanes carry the scalar recurrence redundantly (it is warp-uniform); lane 0 stores d / e.
+    // The dependent chain of one rotation is kept to ~8 instructions: rsqrt + one Newton step
+    // instead of sqrt and two divisions, d / e of the next rotation prefetched, the search for the
+    // small sub-diagonal done by the whole warp at once.
     float* d = al;
     float* e = be;                               // e[K-1] = 0 by construction
+    const bool act0 = lane < K, act1 = lane + 32 < K;
     for (int l = 0; l < K; ++l) {
       int sweeps = 0;
       while (true) {
-        int m = l;
-        for (; m < K - 1; ++m) {
-          const float dd = fabsf(d[m]) + fabsf(d[m + 1]);
-          if (fabsf(e[m]) <= FLT_EPSILON * dd) break;
+        int m = K - 1;
+        for (int m0 = l; m0 < K - 1; m0 += 32) {
+          const int mm = m0 + lane;
+          bool small = true;                     // lanes past K-2 terminate the search at K-1
+          if (mm < K - 1) small = fabsf(e[mm]) <= FLT_EPSILON * (fabsf(d[mm]) + fabsf(d[mm + 1]));
+          const unsigned hit = __ballot_sync(kFull, small);
+          if (hit) { m = m0 + __ffs(hit) - 1; break; }
         }
+        if (m > K - 1) m = K - 1;
         if (m == l) break;
         if (++sweeps > 60) { fail = 1; break; }
-        float gq = (d[l + 1] - d[l]) / (2.f * e[l]);
+        const float dl = d[l], el = e[l];
+        float gq = (d[l + 1] - dl) / (2.f * el);
         float r = sqrtf(gq * gq + 1.f);
-        gq = d[m] - d[l] + e[l] / (gq + copysignf(r, gq));
+        gq = d[m] - dl + el / (gq + copysignf(r, gq));
         float s = 1.f, c = 1.f, p = 0.f;
         int i = m - 1;
         bool underflow = false;
-        // rows k = lane (+32): the value of column i+1 travels in a register between rotations
-        const bool act0 = lane < K, act1 = lane + 32 < K;
+        float d_ip1 = d[m], d_i = d[m - 1], e_i = e[m - 1];
+        // rows k = lane (+32) of Z: the value of column i+1 travels in a register between rotations
         float hi0 = act0 ? Zt[(size_t)m * KR + lane] : 0.f;
         float hi1 = act1 ? Zt[(size_t)m * KR + lane + 32] : 0.f;
         for (; i >= l; --i) {
-          const float f = s * e[i];
-          const float b = c * e[i];
-          r = sqrtf(f * f + gq * gq);
-          __syncwarp();
-          if (lane == 0) e[i + 1] = r;
-          if (r == 0.f) {
-            if (lane == 0) { d[i + 1] -= p; e[m] = 0.f; }
+          const float d_n = (i > l) ? d[i - 1] : 0.f;       // prefetch for rotation i-1
+          const float e_n = (i > l) ? e[i - 1] : 0.f;
+          const float f = s * e_i;
+          const float b = c * e_i;
+          const float r2 = fmaf(f, f, gq * gq);
+          if (r2 == 0.f) {
+            if (lane == 0) { e[i + 1] = 0.f; d[i + 1] = d_ip1 - p; e[m] = 0.f; }
             underflow = true;
             break;
           }
-          s = f / r;
-          c = gq / r;
-          gq = d[i + 1] - p;
-          r = (d[i] - gq) * s + 2.f * c * b;
-          p = s * r;
-          __syncwarp();
-          if (lane == 0) d[i + 1] = gq + p;
-          gq = c * r - b;
+          float rinv = rsqrtf(r2);
+          rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);
+          s = f * rinv;
+          c = gq * rinv;
+          const float g2 = d_ip1 - p;
+          const float rr = fmaf(2.f * c, b, (d_i - g2) * s);
+          p = s * rr;
+          gq = fmaf(c, rr, -b);
+          if (lane == 0) { e[i + 1] = r2 * rinv; d[i + 1] = g2 + p; }
           {
             const float lo0 = act0 ? Zt[(size_t)i * KR + lane] : 0.f;
-            if (act0) Zt[(size_t)(i + 1) * KR + lane] = s * lo0 + c * hi0;
-            hi0 = c * lo0 - s * hi0;
+            if (act0) Zt[(size_t)(i + 1) * KR + lane] = fmaf(s, lo0, c * hi0);
+            hi0 = fmaf(c, lo0, -s * hi0);
             if (K > 32) {
               const float lo1 = act1 ? Zt[(size_t)i * KR + lane + 32] : 0.f;
-              if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = s * lo1 + c * hi1;
-              hi1 = c * lo1 - s * hi1;
+              if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = fmaf(s, lo1, c * hi1);
+              hi1 = fmaf(c, lo1, -s * hi1);
             }
           }
+          d_ip1 = d_i; d_i = d_n; e_i = e_n;
         }
         // column i+1 (= l after a complete sweep) still lives in the register
         if (act0) Zt[(size_t)(i + 1) * KR + lane] = hi0;
         if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = hi1;
-        __syncwarp();
-        if (underflow) continue;
-        if (lane == 0) { d[l] -= p; e[l] = gq; e[m] = 0.f; }
+        if (!underflow && lane == 0) { d[l] = d_ip1 - p; e[l] = gq; e[m] = 0.f; }
         __syncwarp();
       }
       if (fail) break;
@@ -426,6 +451,7 @@ lanczos_ritz_kernel(const FusedParams P) {
     if (lane == 0) P.status[g] = fail | (dense ? 2 : 0);
   }
   gbar<TPG>(grp);
+  LNB_PHASE(4)
   for (int e = t; e < K * K; e += TPG) {
     const int k = e / K, j = e - k * K;
     Zr[(size_t)k * K4 + rank[j]] = Zt[(size_t)j * KR + k];
@@ -461,6 +487,7 @@ lanczos_ritz_kernel(const FusedParams P) {
       if (j < K) Qs[(size_t)j * NS + n] = acc[j];
   }
   gbar<TPG>(grp);
+  LNB_PHASE(5)
   {
     float* Vg = P.V + (size_t)g * N * K;
     for (int e = t; e < N * K; e += TPG) {
@@ -468,6 +495,9 @@ lanczos_ritz_kernel(const FusedParams P) {
       Vg[e] = Qs[(size_t)k * NS + n];
     }
   }
+  LNB_PHASE(6)
+  if (P.prof && t == 0) atomicAdd(&P.prof[8], 1ull);
+#undef LNB_PHASE
 }
 
 struct FusedPlan {
@@ -570,6 +600,7 @@ int lnb_lanczos_ritz(lnb_stream_t stream, const float* A, const uint8_t* mask, c
   pl.p.A = A; pl.p.mask = mask; pl.p.q1 = q1; pl.p.B = B; pl.p.N = N; pl.p.K = K;
   pl.p.T = T; pl.p.Q = Q; pl.p.alpha = alpha; pl.p.beta = beta; pl.p.idx = idx;
   pl.p.theta = theta; pl.p.V = ritz_vec; pl.p.status = status;
+  pl.p.prof = lnb::prof_buffer();
   cudaStream_t s = (cudaStream_t)stream;
   int rc = LNB_OK;
   switch (sel) {

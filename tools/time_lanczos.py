@@ -14,7 +14,8 @@ from lanczosnetwork_b200 import data, ops  # noqa: E402
 
 dev = torch.device('cuda:0')
 peaks = bench.load_peaks()
-which = sys.argv[1:] or ['qm8', '64', '256', '1024']
+which = [a for a in sys.argv[1:] if a != 'phases-only'] or ['qm8', '64', '256', '1024']
+PHASES_ONLY = 'phases-only' in sys.argv
 
 
 def report(name, t, G, N, K, st):
@@ -31,10 +32,10 @@ if 'qm8' in which:
   mask = torch.from_numpy(b['node_mask']).to(dev)
   q1 = torch.randn(1024, 26, generator=torch.Generator().manual_seed(1)).to(dev)
   o = ops.lanczos_ritz(A, mask, q1, 20)
-  for kw in ({}, {'want_ritz': False}, {'want_T': False, 'want_Q': False}):
+  for kw in ([] if PHASES_ONLY else [{}, {'want_ritz': False}, {'want_T': False, 'want_Q': False}]):
     t = bench.time_events(lambda: ops.lanczos_ritz(A, mask, q1, 20, **kw), 20, 5)
     report('qm8 %s' % kw, t, 1024, 26, 20, o['status'])
-  t = bench.time_events(lambda: ops.lanczos_tridiag(A, mask, q1, 20), 20, 5)
+  t = 0.0 if PHASES_ONLY else bench.time_events(lambda: ops.lanczos_tridiag(A, mask, q1, 20), 20, 5)
   print('old lanczos_tridiag qm8 ms', t)
 for N, G in ((64, 10000), (256, 10000), (1024, 10000)):
   if str(N) not in which:
@@ -44,8 +45,39 @@ for N, G in ((64, 10000), (256, 10000), (1024, 10000)):
   Ad = torch.from_numpy(base).to(dev).repeat((G + 7) // 8, 1, 1)[:G].contiguous()
   q1 = torch.randn(G, N, generator=torch.Generator().manual_seed(1234)).to(dev)
   o = ops.lanczos_ritz(Ad, None, q1, 40)
-  for kw in ({}, {'want_ritz': False}, {'want_T': False, 'want_Q': False}):
+  for kw in ([] if PHASES_ONLY else [{}, {'want_ritz': False}, {'want_T': False, 'want_Q': False}]):
     t = bench.time_events(lambda: ops.lanczos_ritz(Ad, None, q1, 40, **kw), 3, 1)
     report('N=%d %s' % (N, kw), t, G, N, 40, o['status'])
   del Ad
   torch.cuda.empty_cache()
+
+# per-phase clock64 totals (cycles per graph, thread 0 of each group)
+import ctypes
+from lanczosnetwork_b200 import _lib
+lib = _lib.load()
+names = ['compress', 'start', 'lanczos', 'post+TQ', 'QL', 'V=QZ', 'write V']
+
+
+def phases(tag, fn):
+  prof = torch.zeros(64, dtype=torch.int64, device=dev)
+  _lib.check(lib.lnb_debug_set_prof(ctypes.c_void_p(prof.data_ptr())), 'set_prof')
+  fn()
+  torch.cuda.synchronize()
+  lib.lnb_debug_set_prof(None)
+  p = prof.cpu().double()
+  n = max(p[8].item(), 1)
+  print(tag, ' '.join('%s=%d' % (nm, p[i].item() / n) for i, nm in enumerate(names)), 'graphs=%d' % n, flush=True)
+
+
+if 'qm8' in which:
+  q1 = torch.randn(1024, 26, generator=torch.Generator().manual_seed(1)).to(dev)
+  phases('phases qm8', lambda: ops.lanczos_ritz(A, mask, q1, 20))
+for N, G in ((64, 10000), (256, 10000), (1024, 2000)):
+  if str(N) not in which:
+    continue
+  rng = np.random.RandomState(1234 + N)
+  base = np.stack([bench.gnp_operator(rng, N, min(0.5, 8.0 / N)) for _ in range(8)])
+  Ad = torch.from_numpy(base).to(dev).repeat((G + 7) // 8, 1, 1)[:G].contiguous()
+  q1 = torch.randn(G, N, generator=torch.Generator().manual_seed(1234)).to(dev)
+  phases('phases N=%d' % N, lambda: ops.lanczos_ritz(Ad, None, q1, 40))
+  del Ad
