@@ -258,11 +258,17 @@ int lnb_tridiag_ritz(lnb_stream_t stream, const float* alpha, const float* beta,
  * SM.  T, Q may be NULL (not written).  theta / ritz_vec / status may be NULL together: then only
  * the tridiagonalisation is produced (AdaLanczosNet).  status[b]: bit 0 = QL sweeps exhausted,
  * bit 1 = the graph's non-zeros did not fit on chip and its rows were streamed per iteration.
+ * flags: 0 = the reference's masking rules (idx = min(#valid betas, #real nodes) directions and node
+ * rows kept; the alpha of the breakdown step dropped, ada_lanczos_net.py:207-237);
+ * LNB_LANCZOS_PROPER = the textbook Krylov factorisation (m = #valid + 1 vectors, T_m with m alphas
+ * and m-1 betas, no row masking; idx[b] = m) whose Ritz values are eigenvalues of A -- the mode of
+ * the online (D, V) provider.
  * Limits: N <= 1024, K <= 64 and a basis of K*(N+1) floats within shared memory
  * (LNB_ERR_UNSUPPORTED otherwise: use lnb_lanczos_tridiag + lnb_tridiag_ritz).
  * ------------------------------------------------------------------------------------- */
+#define LNB_LANCZOS_PROPER 1
 int lnb_lanczos_ritz(lnb_stream_t stream, const float* A, const uint8_t* mask, const float* q1,
-                     int B, int N, int K, float* T, float* Q, float* alpha, float* beta,
+                     int B, int N, int K, int flags, float* T, float* Q, float* alpha, float* beta,
                      int32_t* idx, float* theta /* [B,K] */, float* ritz_vec /* [B,N,K] */,
                      int32_t* status /* [B] */);
 

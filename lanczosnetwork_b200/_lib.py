@@ -91,7 +91,7 @@ SIGNATURES = {
                                     c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
     'lnb_tridiag_ritz': (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_f32p,
                                  c_f32p, ctypes.c_void_p]),
-    'lnb_lanczos_ritz': (c_int, [c_stream, c_f32p, ctypes.c_void_p, c_f32p, c_int, c_int, c_int,
+    'lnb_lanczos_ritz': (c_int, [c_stream, c_f32p, ctypes.c_void_p, c_f32p, c_int, c_int, c_int, c_int,
                                  c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_f32p, c_f32p,
                                  ctypes.c_void_p]),
     'lnb_tridiag_powers': (c_int, [c_stream, c_f32p, c_int, c_int, ctypes.POINTER(c_int), c_int,

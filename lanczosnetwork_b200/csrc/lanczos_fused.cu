@@ -30,12 +30,13 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct FusedParams {
   const float* A; const uint8_t* mask; const float* q1;
-  int B, N, K;
+  int B, N, K, flags;
   float* T; float* Q; float* alpha; float* beta; int32_t* idx;
   float* theta; float* V; int32_t* status;
   int cap;            // CSR pool capacity per graph (entries)
   int pool_words;     // 4-byte words reserved for the pool / the QL scratch that aliases it
   int per_graph;      // 4-byte words of shared memory per graph
+  int zw;             // words of the zs / partial-projection region
   unsigned long long* prof;   // profiling aid (lnb_debug_set_prof): per-phase clock64 totals, [8] = graphs
 };
 
@@ -62,6 +63,29 @@ __device__ __forceinline__ float2 gsum2(float a, float b, float* red, int& flip,
   return make_float2(sa, sb);
 }
 
+// Sum NV (8 or 32) per-lane values across the warp with NV-1 (+ log2(32/NV)) shuffles: at every stage
+// the lanes whose bit `o` is set keep the upper half of the remaining values.  On return v[0] of lane
+// L is the warp total of value L * NV / 32.
+template <int NV>
+__device__ __forceinline__ void multi_reduce(float (&v)[NV], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int o = 16 >> s;
+    const int n = NV >> (s + 1);                // values kept after this stage
+    if (n >= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int k = 0; k < n; ++k) {
+        const float send = up ? v[k] : v[k + n];
+        const float keep = up ? v[k + n] : v[k];
+        v[k] = keep + __shfl_xor_sync(kFull, send, o);
+      }
+    } else {
+      v[0] += __shfl_xor_sync(kFull, v[0], o);
+    }
+  }
+}
+
 template <int TPG, int NPT, int KB>
 __global__ void __launch_bounds__((TPG > 128 ? TPG : 128))
 lanczos_ritz_kernel(const FusedParams P) {
@@ -83,12 +107,13 @@ lanczos_ritz_kernel(const FusedParams P) {
   float* cs = base;                             // K4          projection coefficients (float4 reads)
   float* al = cs + K4;                          // K4
   float* be = al + K4;                          // K4
-  float* qq = be + K4;                          // K4 + 4
-  float* red = qq + K4 + 4;                     // 64
+  float* iq = be + K4;                          // K4 + 4   1 / (q_j . q_j + EPS)
+  float* red = iq + K4 + 4;                     // 64
   int* ctl = reinterpret_cast<int*>(red + 64);  // 4  : cursor, overflow
   uint32_t* rinfo = reinterpret_cast<uint32_t*>(ctl + 4);    // NP : start | len << 16
-  float* zs = reinterpret_cast<float*>(rinfo + NP);          // NP   z of the projection pass
-  float* pval = zs + NP;                        // pool: cap values, then cap 16-bit columns (16-byte aligned)
+  float* zs = reinterpret_cast<float*>(rinfo + NP);          // ZW   z of the streamed matvec; aliased by
+  float* part = zs;                                          //      the per-warp partial projections [NWG][K4]
+  float* pval = zs + P.zw;                      // pool: cap values, then cap 16-bit columns (16-byte aligned)
   uint16_t* pcol = reinterpret_cast<uint16_t*>(pval + P.cap);
   float* Qs = pval + P.pool_words;              // K x NS      Krylov basis, row i = q_i
   int flip = 0;
@@ -107,41 +132,61 @@ lanczos_ritz_kernel(const FusedParams P) {
 
   // ---- 1. compress: dense rows (HBM, read once) -> CSR pool --------------------------------------
   const float* Ag = P.A + (size_t)g * N * N;
-  for (int r = wg; r < N; r += NWG) {
-    const float* row = Ag + (size_t)r * N;
-    float v[NCH];
+  {
+    // RB rows per warp in flight (RB * NCH independent coalesced loads) before any is consumed
+    constexpr int RB = NCH >= 16 ? 2 : (NCH >= 8 ? 4 : 8);
+    int cursor = 0;                              // single-warp groups allocate from a register
+    for (int r0 = wg; r0 < N; r0 += NWG * RB) {
+      float v[RB][NCH];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c = lane + 32 * k;
-      v[k] = (c < N) ? __ldcs(row + c) : 0.f;
-    }
-    int cnt = 0;
+      for (int b = 0; b < RB; ++b) {
+        const int r = r0 + b * NWG;
+        const float* row = Ag + (size_t)r * N;
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) cnt += __popc(__ballot_sync(kFull, v[k] != 0.f));
-    int start = 0;
-    if (lane == 0) start = atomicAdd(&ctl[0], cnt);
-    start = __shfl_sync(kFull, start, 0);
-    if (start + cnt <= P.cap) {
-      int off = start;
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        const unsigned m = __ballot_sync(kFull, v[k] != 0.f);
-        if (v[k] != 0.f) {
-          const int p = off + __popc(m & ((1u << lane) - 1u));
-          pval[p] = v[k];
-          pcol[p] = (uint16_t)(lane + 32 * k);
+        for (int k = 0; k < NCH; ++k) {
+          const int c = lane + 32 * k;
+          v[b][k] = (r < N && c < N) ? __ldcs(row + c) : 0.f;
         }
-        off += __popc(m);
       }
-      if (lane == 0) rinfo[r] = (uint32_t)start | ((uint32_t)cnt << 16);
-    } else if (lane == 0) {
-      ctl[1] = 1;
+#pragma unroll
+      for (int b = 0; b < RB; ++b) {
+        const int r = r0 + b * NWG;
+        if (r >= N) break;                       // warp-uniform
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) cnt += __popc(__ballot_sync(kFull, v[b][k] != 0.f));
+        int start;
+        if constexpr (TPG == 32) {
+          start = cursor;
+          cursor += cnt;
+        } else {
+          start = 0;
+          if (lane == 0) start = atomicAdd(&ctl[0], cnt);
+          start = __shfl_sync(kFull, start, 0);
+        }
+        if (start + cnt <= P.cap) {
+          int off = start;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const unsigned m = __ballot_sync(kFull, v[b][k] != 0.f);
+            if (v[b][k] != 0.f) {
+              const int p = off + __popc(m & ((1u << lane) - 1u));
+              pval[p] = v[b][k];
+              pcol[p] = (uint16_t)(lane + 32 * k);
+            }
+            off += __popc(m);
+          }
+          if (lane == 0) rinfo[r] = (uint32_t)start | ((uint32_t)cnt << 16);
+        } else if (lane == 0) {
+          ctl[1] = 1;
+        }
+      }
     }
   }
   LNB_PHASE(0)
   // ---- start vector (ada_lanczos_net.py:159-167) --------------------------------------------------
   float q[NPT], qp[NPT], z[NPT];
-  float cnt_real = 0.f, part = 0.f;
+  float cnt_real = 0.f, psum = 0.f;
 #pragma unroll
   for (int kk = 0; kk < NPT; ++kk) {
     const int n = t + kk * TPG;
@@ -151,9 +196,9 @@ lanczos_ritz_kernel(const FusedParams P) {
       v = P.q1[(size_t)g * N + n] * mk;
     }
     q[kk] = v; qp[kk] = 0.f;
-    part += v * v; cnt_real += mk;
+    psum += v * v; cnt_real += mk;
   }
-  float2 r0 = gsum2<TPG>(part, cnt_real, red, flip, grp, wg, lane);   // also orders the pool writes
+  float2 r0 = gsum2<TPG>(psum, cnt_real, red, flip, grp, wg, lane);   // also orders the pool writes
   const float nrm = sqrtf(r0.x);
   const int nreal = (int)(r0.y + 0.5f);
 #pragma unroll
@@ -202,56 +247,61 @@ lanczos_ritz_kernel(const FusedParams P) {
     for (int kk = 0; kk < NPT; ++kk) { pa = fmaf(q[kk], z[kk], pa); pq = fmaf(q[kk], q[kk], pq); }
     const float2 aq = gsum2<TPG>(pa, pq, red, flip, grp, wg, lane);
     const float alpha = aq.x;
-    if (t == 0) qq[i] = aq.y;                   // q_i . q_i: first read by the projections of step i+1
+    if (t == 0) iq[i] = 1.f / (aq.y + kEps);    // first read by the projections of step i+1
 #pragma unroll
     for (int kk = 0; kk < NPT; ++kk) z[kk] = z[kk] - alpha * q[kk] - beta_prev * qp[kk];
     if (i > 0) {
       for (int pass = 0; pass < 2; ++pass) {
+        // Projections c_j = (z . q_j) / (q_j . q_j + EPS), all j < i at once: every thread forms the
+        // partial products over its own nodes, a butterfly of select-and-add shuffle stages leaves
+        // lane L of each warp with the warp total of coefficient jb + L (31 shuffles for 32 values
+        // instead of 5 per value, and no serial chain over j).
+#pragma unroll 1
+        for (int jb = 0; jb < i; jb += 32) {
+          if (i - jb > 8) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = 0.f;
+              if (jb + j < i) {
+#pragma unroll
+                for (int kk = 0; kk < NPT; ++kk) a = fmaf(z[kk], Qs[(size_t)(jb + j) * NS + t + kk * TPG], a);
+              }
+              v[j] = a;
+            }
+            multi_reduce<32>(v, lane);
+            if (jb + lane < i) {
+              if constexpr (TPG == 32) cs[jb + lane] = v[0] * iq[jb + lane];
+              else part[wg * K4 + jb + lane] = v[0];
+            }
+          } else {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = 0.f;
+              if (jb + j < i) {
+#pragma unroll
+                for (int kk = 0; kk < NPT; ++kk) a = fmaf(z[kk], Qs[(size_t)(jb + j) * NS + t + kk * TPG], a);
+              }
+              v[j] = a;
+            }
+            multi_reduce<8>(v, lane);
+            const int j = jb + (lane >> 2);
+            if ((lane & 3) == 0 && j < i) {
+              if constexpr (TPG == 32) cs[j] = v[0] * iq[j];
+              else part[wg * K4 + j] = v[0];
+            }
+          }
+        }
         if constexpr (TPG == 32) {
-          // one warp: every projection is a warp reduction; 4 independent ones in flight
-          int j = 0;
-          for (; j + 3 < i; j += 4) {
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-            for (int kk = 0; kk < NPT; ++kk) {
-              const int n = t + kk * TPG;
-              d0 = fmaf(z[kk], Qs[(size_t)(j + 0) * NS + n], d0);
-              d1 = fmaf(z[kk], Qs[(size_t)(j + 1) * NS + n], d1);
-              d2 = fmaf(z[kk], Qs[(size_t)(j + 2) * NS + n], d2);
-              d3 = fmaf(z[kk], Qs[(size_t)(j + 3) * NS + n], d3);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              d0 += __shfl_xor_sync(kFull, d0, o); d1 += __shfl_xor_sync(kFull, d1, o);
-              d2 += __shfl_xor_sync(kFull, d2, o); d3 += __shfl_xor_sync(kFull, d3, o);
-            }
-            if (lane == 0) {
-              cs[j + 0] = d0 / (qq[j + 0] + kEps); cs[j + 1] = d1 / (qq[j + 1] + kEps);
-              cs[j + 2] = d2 / (qq[j + 2] + kEps); cs[j + 3] = d3 / (qq[j + 3] + kEps);
-            }
-          }
-          for (; j < i; ++j) {
-            float d0 = 0.f;
-#pragma unroll
-            for (int kk = 0; kk < NPT; ++kk) d0 = fmaf(z[kk], Qs[(size_t)j * NS + t + kk * TPG], d0);
-            d0 = lnb::warp_sum(d0);
-            if (lane == 0) cs[j] = d0 / (qq[j] + kEps);
-          }
           __syncwarp();
         } else {
-#pragma unroll
-          for (int kk = 0; kk < NPT; ++kk) zs[t + kk * TPG] = z[kk];
           gbar<TPG>(grp);
-          for (int j = wg; j < i; j += NWG) {
-            const float* qj = Qs + (size_t)j * NS;
-            float d0 = 0.f, d1 = 0.f;
+          for (int j = t; j < i; j += TPG) {
+            float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < NCH; c += 2) {
-              d0 = fmaf(zs[lane + 32 * c], qj[lane + 32 * c], d0);
-              d1 = fmaf(zs[lane + 32 * c + 32], qj[lane + 32 * c + 32], d1);
-            }
-            d0 = lnb::warp_sum(d0 + d1);
-            if (lane == 0) cs[j] = d0 / (qq[j] + kEps);
+            for (int w = 0; w < NWG; ++w) sum += part[w * K4 + j];
+            cs[j] = sum * iq[j];
           }
           gbar<TPG>(grp);
         }
@@ -280,7 +330,7 @@ lanczos_ritz_kernel(const FusedParams P) {
 #pragma unroll
           for (int kk = 0; kk < NPT; ++kk) z[kk] -= s0[kk] + s1[kk];
         }
-        if (TPG == 32) __syncwarp();            // cs is rewritten by the next pass
+        if constexpr (TPG == 32) __syncwarp();  // cs is rewritten by the next pass
       }
     }
     float pb = 0.f;
@@ -302,27 +352,40 @@ lanczos_ritz_kernel(const FusedParams P) {
 
   LNB_PHASE(2)
   // ---- 3. masking rules + tridiagonal outputs (ada_lanczos_net.py:207-245) ------------------------
-  const int idx = count < nreal ? count : nreal;
-  // basis: columns k >= idx (or >= iters) and rows n >= idx are zero
+  // reference rules: idx = min(#valid, #real nodes) directions AND node rows are kept, the alpha of
+  // the breakdown step is dropped while the beta in front of it stays (ada_lanczos_net.py:207-237).
+  // LNB_LANCZOS_PROPER: the textbook Krylov factorisation instead -- m = #valid + 1 basis vectors
+  // (q_0 and one per accepted beta), T_m with all m alphas and m-1 betas, no row masking -- whose
+  // Ritz values are eigenvalues of the operator (what an online (D, V) provider needs).
+  const bool proper = (P.flags & 1) != 0;
+  int idx = count < nreal ? count : nreal;
+  int kcols = idx, nrows_keep = idx, nbeta = idx < iters - 1 ? idx : iters - 1;
+  if (proper) {
+    idx = count + 1 < iters ? count + 1 : iters;
+    if (idx > nreal) idx = nreal;                // a Krylov space cannot outgrow the graph
+    if (idx < 1) idx = nreal > 0 ? 1 : 0;
+    kcols = idx; nrows_keep = NP; nbeta = idx - 1;
+  }
+  if (kcols > iters) kcols = iters;
   for (int k = 0; k < K; ++k) {
 #pragma unroll
     for (int kk = 0; kk < NPT; ++kk) {
       const int n = t + kk * TPG;
-      if (!(k < iters && k < idx && n < idx)) Qs[(size_t)k * NS + n] = 0.f;
+      if (!(k < kcols && n < nrows_keep)) Qs[(size_t)k * NS + n] = 0.f;
     }
   }
   gbar<TPG>(grp);                                // every al / be write of the loop is visible
   for (int k = t; k < K; k += TPG) {
-    const float av = (k < iters && k < idx) ? al[k] : 0.f;
-    const float bv = (k < iters - 1 && k < idx) ? be[k] : 0.f;
+    const float av = (k < kcols) ? al[k] : 0.f;
+    const float bv = (k < nbeta) ? be[k] : 0.f;
     cs[k] = av;                                  // staged: al / be are read by other threads below
-    qq[k] = bv;
+    iq[k] = bv;
   }
   gbar<TPG>(grp);
   for (int k = t; k < K; k += TPG) {
-    al[k] = cs[k]; be[k] = qq[k];
+    al[k] = cs[k]; be[k] = iq[k];
     P.alpha[(size_t)g * K + k] = cs[k];
-    P.beta[(size_t)g * K + k] = qq[k];
+    P.beta[(size_t)g * K + k] = iq[k];
   }
   if (t == 0) P.idx[g] = idx;
   gbar<TPG>(grp);
@@ -511,7 +574,10 @@ struct FusedPlan {
 static bool plan_fused(int N, int K, int tpg, int npt, FusedPlan& pl) {
   const int NP = tpg * npt, NS = NP + 1, K4 = (K + 3) & ~3;
   const int cta = tpg > 128 ? tpg : 128, gpc = cta / tpg;
-  const int fixed = K * NS + 2 * NP + 4 * K4 + 4 + 64 + 4;
+  const int nwg = tpg / 32;
+  int zw = nwg * K4 > NP ? nwg * K4 : NP;
+  zw = (zw + 3) & ~3;
+  const int fixed = K * NS + NP + zw + 4 * K4 + 4 + 64 + 4;
   const int ql_words = ((K * (K | 1) + 3) & ~3) + K * K4 + K + 4;
   const int smem_max = 227 * 1024;
   // target capacity: every non-zero of a dense operator if that is cheap, else 12 per row
@@ -551,6 +617,7 @@ static bool plan_fused(int N, int K, int tpg, int npt, FusedPlan& pl) {
   }
   pl.tpg = tpg; pl.npt = npt; pl.cta = cta; pl.gpc = gpc;
   pl.p.cap = (int)cap; pl.p.pool_words = pool_words; pl.p.per_graph = (int)per_graph;
+  pl.p.zw = zw;
   pl.smem = (size_t)per_graph * gpc * 4;
   return pl.smem <= (size_t)smem_max;
 }
@@ -575,7 +642,7 @@ static int launch_fused_k(cudaStream_t s, const FusedPlan& pl) {
 extern "C" {
 
 int lnb_lanczos_ritz(lnb_stream_t stream, const float* A, const uint8_t* mask, const float* q1,
-                     int B, int N, int K, float* T, float* Q, float* alpha, float* beta,
+                     int B, int N, int K, int flags, float* T, float* Q, float* alpha, float* beta,
                      int32_t* idx, float* theta, float* ritz_vec, int32_t* status) {
   LNB_REQUIRE(B >= 0 && N >= 1 && K >= 1, "lanczos_ritz: bad dims B=%d N=%d K=%d", B, N, K);
   if (B == 0) return LNB_OK;
@@ -597,7 +664,7 @@ int lnb_lanczos_ritz(lnb_stream_t stream, const float* A, const uint8_t* mask, c
     lnb::set_err("lanczos_ritz: Krylov basis (N=%d, K=%d) does not fit shared memory", N, K);
     return LNB_ERR_UNSUPPORTED;
   }
-  pl.p.A = A; pl.p.mask = mask; pl.p.q1 = q1; pl.p.B = B; pl.p.N = N; pl.p.K = K;
+  pl.p.A = A; pl.p.mask = mask; pl.p.q1 = q1; pl.p.B = B; pl.p.N = N; pl.p.K = K; pl.p.flags = flags;
   pl.p.T = T; pl.p.Q = Q; pl.p.alpha = alpha; pl.p.beta = beta; pl.p.idx = idx;
   pl.p.theta = theta; pl.p.V = ritz_vec; pl.p.status = status;
   pl.p.prof = lnb::prof_buffer();

@@ -4,7 +4,7 @@ constructor, parameter names and ``forward(node_feat, L, label=None, mask=None)`
 Per batch it builds its own operator: Gaussian-kernel Laplacian from the learned embeddings
 (:101-137), K-step Lanczos with double re-orthogonalisation (:139-247), the learned filter on
 powers of the tridiagonal T (:250-286).  B200 mapping: one fused Laplacian kernel (no
-B x N^2 x D pair tensors), one warp/CTA-per-graph Lanczos kernel, T^p computed once per
+B x N^2 x D pair tensors), one warp/CTA-per-graph Lanczos kernel (lnb_lanczos_ritz without the QL stage), T^p computed once per
 forward instead of once per layer (the reference recomputes 30 bmm per layer, :266-270),
 the 4096-wide MLP on the tcgen05 3xTF32 kernel, and Q G (Q^T X) applied in factored form.
 """
@@ -62,7 +62,8 @@ class AdaLanczosNet(SpectralNetBase):
     if S > 0:
       Le = ops.gaussian_laplacian(state, L)
       q1 = torch.randn(B, N, 1).to(dev)
-      lz = ops.lanczos_tridiag(Le, mask, q1, K)
+      # fused kernel, tridiagonalisation only (no QL / Ritz vectors for the learned filter)
+      lz = ops.lanczos_ritz(Le, mask, q1, K, want_ritz=False)
       Q = lz['Q']
       powers = ops.tridiag_powers(lz['T'], self.long_diffusion_dist)     # [B,K,S,K], once
       self.last_lanczos = lz

@@ -425,11 +425,13 @@ def tridiag_ritz(alpha, beta, Q):
   return theta, V, status
 
 
-def lanczos_ritz(A, mask, q1, K, want_ritz=True, want_T=True, want_Q=True):
+def lanczos_ritz(A, mask, q1, K, want_ritz=True, want_T=True, want_Q=True, proper=False):
   """adjacency operator -> Ritz pairs in ONE launch (Lanczos + QL + Ritz vectors fused).
   Returns dict(alpha, beta [B,K], idx [B] int32, T [B,K,K], Q [B,N,K] when asked for, and with
   want_ritz theta [B,K] by descending |theta|, V [B,N,K] = Q S, status [B] (bit 0: QL not
-  converged, bit 1: operator streamed because its non-zeros did not fit on chip))."""
+  converged, bit 1: operator streamed because its non-zeros did not fit on chip)).
+  proper=False reproduces the reference's masking rules of _lanczos_layer; proper=True returns the
+  textbook Krylov factorisation (LNB_LANCZOS_PROPER) whose Ritz values are eigenvalues of A."""
   _need_cuda(A, mask, q1)
   A = _f32c(A)
   B, N = A.shape[0], A.shape[1]
@@ -450,7 +452,8 @@ def lanczos_ritz(A, mask, q1, K, want_ritz=True, want_T=True, want_Q=True):
     out['status'] = torch.empty((B,), device=dev, dtype=torch.int32)
   with torch.cuda.device(dev):
     _lib.check(_lib.load().lnb_lanczos_ritz(
-        _stream(A), _ptr(A), _ptr(mask), _ptr(q1), B, N, K, _ptr(out.get('T')), _ptr(out.get('Q')),
+        _stream(A), _ptr(A), _ptr(mask), _ptr(q1), B, N, K, 1 if proper else 0,
+        _ptr(out.get('T')), _ptr(out.get('Q')),
         _ptr(out['alpha']), _ptr(out['beta']), _ptr(out['idx']), _ptr(out.get('theta')),
         _ptr(out.get('V')), _ptr(out.get('status'))), 'lnb_lanczos_ritz')
   return out

@@ -411,6 +411,49 @@ def test_fused_lanczos_ritz_dense_operator_streams_and_agrees():
                 out['beta'].cpu().numpy(), Q, T)
 
 
+def test_fused_lanczos_proper_mode_is_a_krylov_factorisation():
+  """LNB_LANCZOS_PROPER (the online (D, V) provider's mode): Q has m = idx orthonormal columns,
+  Q^T A Q = T_m (so the Ritz values are Rayleigh-Ritz values of A), exhausted Krylov spaces
+  (n_b <= K, simple spectrum) reproduce the operator, and columns / entries past m are zero."""
+  import bench
+  rng = np.random.RandomState(31)
+  B, N, K = 24, 30, 20
+  A = np.zeros((B, N, N), np.float32)
+  mask = np.zeros((B, N), np.uint8)
+  sizes = rng.randint(3, N + 1, size=B)
+  for b, n in enumerate(sizes):
+    A[b, :n, :n] = bench.gnp_operator(rng, int(n), 0.3)
+    mask[b, :n] = 1
+  q1 = rng.randn(B, N).astype(np.float32)
+  out = ops().lanczos_ritz(torch.from_numpy(A).to(dev()), torch.from_numpy(mask).to(dev()),
+                           torch.from_numpy(q1).to(dev()), K, proper=True)
+  idx = out['idx'].cpu().numpy()
+  Q = out['Q'].cpu().numpy().astype(np.float64)
+  T = out['T'].cpu().numpy().astype(np.float64)
+  th = out['theta'].cpu().numpy().astype(np.float64)
+  V = out['V'].cpu().numpy().astype(np.float64)
+  assert np.all(idx >= 1) and np.all(idx <= np.minimum(sizes, K))
+  beta = out['beta'].cpu().numpy().astype(np.float64)
+  for b in range(B):
+    m = idx[b]
+    # fp32 Lanczos loses orthogonality like eps / beta_min at a near-breakdown step (betas down to the
+    # 1e-4 acceptance threshold are kept): the stated tolerance scales accordingly
+    bmin = beta[b, :m - 1].min() if m > 1 else 1.0
+    tol = 2e-5 + 4e-6 / bmin
+    np.testing.assert_allclose(Q[b].T @ Q[b], np.diag((np.arange(K) < m).astype(np.float64)), atol=tol)
+    np.testing.assert_allclose(Q[b].T @ A[b].astype(np.float64) @ Q[b], T[b], atol=tol)
+    assert np.all(T[b, m:, :] == 0) and np.all(Q[b][:, m:] == 0)
+    lam = np.linalg.eigvalsh(A[b, :sizes[b], :sizes[b]].astype(np.float64))
+    if m == sizes[b]:                    # Krylov space exhausted the graph: exact decomposition
+      np.testing.assert_allclose((V[b] * th[b]) @ V[b].T, A[b], atol=2 * tol)
+      np.testing.assert_allclose(np.sort(th[b, :m]), lam, atol=tol)
+    elif m < K:                          # breakdown before K: invariant subspace -> exact eigenvalues
+      for v in th[b, :m]:
+        assert np.abs(lam - v).min() < 2 * tol
+  assert (idx == np.minimum(sizes, K)).mean() > 0.5
+  assert int((out['status'] & 1).sum()) == 0
+
+
 def test_fused_lanczos_ritz_edges():
   """Empty batch, N = 1, N < K (zero padding), all-masked graph next to a full one, unsupported
   sizes refused loudly."""
