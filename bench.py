@@ -8,8 +8,11 @@ Workload (BASELINE.json configs[1]): LanczosNet forward, config/qm8_lanczos_net.
 K=20 Ritz pairs, batch 1024 per GPU, synthetic QM8-shaped molecules (n_b in [3,26], N=26),
 numpy-seeded weights, fp32 (the big Linear runs as 3xTF32 on tcgen05 = fp32-grade accuracy).
 A step = one forward over one batch.  ``value`` = molecules/s with inputs resident in HBM;
-``e2e`` = the same through the module's public forward() with pinned HOST inputs (H2D of
-node_feat/L/D/V/mask and D2H of the scores inside the timed region).  Multi-GPU: one process
+``e2e`` = the same through the module's public ``forward_sparse()`` with pinned HOST inputs: the
+batch arrives as sparse per-molecule records (bond lists, node ids, Ritz rows: ~1.7 MB instead of
+the 21.8 MB padded tensors), is copied H2D, built on the device (L4 operators, padding, mask, ELL,
+tiles -- SURVEY 8f2) and the scores are copied back, all inside the timed region; ``e2e.padded_api``
+reports the reference's padded batch through ``forward()`` for comparison.  Multi-GPU: one process
 per GPU (torchrun), batch shards with no data-path collective; the per-step predictions stay on
 the device and ONE NCCL all-gather of all [steps*B,16] predictions closes the timed region
 (a single gather of per-graph predictions); weak scaling.
@@ -53,6 +56,18 @@ def load_peaks():
 def make_batches(num, batch, seed0):
   from lanczosnetwork_b200 import data
   return [data.synthetic_qm8_batch(batch, seed=seed0 + i) for i in range(num)]
+
+
+def make_batches_both(num, batch, seed0):
+  """The same molecules twice: the reference's padded batch (data.collate) and the sparse records
+  (bond lists + node ids + Ritz rows) of the GPU-side batch construction."""
+  from lanczosnetwork_b200 import data
+  dense, sparse = [], []
+  for i in range(num):
+    samples = data.synthetic_qm8_samples(batch, seed=seed0 + i)
+    dense.append(data.collate(samples, 20))
+    sparse.append(data.sparse_collate(samples, 20))
+  return dense, sparse
 
 
 def build_model():
@@ -345,11 +360,16 @@ def main():
   spec = oracle_spec(mod, 'LanczosNet')
   mod = mod.to(dev).eval()
   B = args.batch
-  host = make_batches(NUM_BATCHES, B, 1000 + 100 * rank)      # per-rank shard (weak scaling)
+  host, host_sparse = make_batches_both(NUM_BATCHES, B, 1000 + 100 * rank)   # per-rank shard (weak scaling)
   keys = ('node_feat', 'L', 'D', 'V', 'node_mask')
+  skeys = ('sizes', 'node_ptr', 'node_feat', 'edge_ptr', 'edges', 'V_rows', 'D')
   pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in keys} for b in host]
+  pinned_sparse = [dict({k: torch.from_numpy(b[k]).pin_memory() for k in skeys}, N=b['N'])
+                   for b in host_sparse]
   resident = [{k: v.to(dev) for k, v in p.items()} for p in pinned]
-  h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+  dense_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+  h2d_bytes = int(np.mean([sum(p[k].numel() * p[k].element_size() for k in skeys)
+                           for p in pinned_sparse]))
   P = 16
   out_host = torch.empty((B, P)).pin_memory()
   kept = []                  # this rank's per-step predictions, resident until the single gather
@@ -368,9 +388,17 @@ def main():
     kept.append(mod(b['node_feat'], b['L'], b['D'], b['V'], mask=b['node_mask']))
 
   def step_e2e(i):
+    # the public sparse-batch call: H2D of the bond lists / node ids / Ritz rows, batch construction
+    # on the device, forward, D2H of the step's predictions
+    score = mod.forward_sparse(pinned_sparse[i % NUM_BATCHES])
+    out_host.copy_(score, non_blocking=True)
+    kept.append(score)
+
+  def step_e2e_dense(i):
+    # the reference's padded batch (dataset/qm8.py collate) through forward(): 21.8 MB of H2D per step
     p = pinned[i % NUM_BATCHES]
-    score = mod(p['node_feat'], p['L'], p['D'], p['V'], mask=p['node_mask'])   # H2D inside
-    out_host.copy_(score, non_blocking=True)                                   # D2H of the step's result
+    score = mod(p['node_feat'], p['L'], p['D'], p['V'], mask=p['node_mask'])
+    out_host.copy_(score, non_blocking=True)
     kept.append(score)
 
   def barrier():
@@ -411,8 +439,14 @@ def main():
     # buffers is when the module captures its zero-copy graph for them
     for i in range(max(args.warmup, 2 * NUM_BATCHES)):
       step_resident(i)
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 2)):
       step_e2e(i)
+      step_e2e_dense(i)
+    if rank == 0:     # the sparse path must return the bits of the padded path
+      a = mod.forward_sparse(pinned_sparse[0])
+      b = mod(*[resident[0][k] for k in ('node_feat', 'L', 'D', 'V')], mask=resident[0]['node_mask'])
+      if not torch.equal(a, b):
+        raise SystemExit('bench: forward_sparse differs from forward on the collated batch')
     gather_once()
     del kept[:]
     sampler = ClockSampler(local)
@@ -421,6 +455,7 @@ def main():
     ms_total = timed(step_resident, args.steps)
     launches = ops.launch_count() - l0
     ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_dense = timed(step_e2e_dense, args.steps)
     clocks = sampler.stop()
 
     # dominant kernel: the whole 7-layer spectral-conv stack + readout as ONE persistent tcgen05
@@ -506,14 +541,21 @@ def main():
                  'global_batch': B * world, 'parallelism': 'dp%d' % world,
                  'cache': 'inputs larger than L2: %d distinct resident batches rotated '
                           '(%.0f MB > 126 MB L2); value: read in place by zero-copy CUDA graphs bound '
-                          'to the resident buffers; e2e: H2D from pinned host memory into the static '
-                          'input buffers of two alternating graph slots' %
-                          (NUM_BATCHES, NUM_BATCHES * h2d_bytes / 1e6),
+                          'to the resident buffers; e2e: sparse records (bond lists, node ids, Ritz '
+                          'rows) H2D from pinned host memory into the static buffers of two alternating '
+                          'graph slots, batch construction (L4 operators, padding, ELL, tiles) on the '
+                          'device' % (NUM_BATCHES, NUM_BATCHES * dense_bytes / 1e6),
                  'collective': 'one all_gather_into_tensor of [steps*B,16] per rank at the end of the '
                                'timed region' if world > 1 else 'none',
                  'numa_cpulist': numa},
       'e2e': {'value': e2e_value, 'unit': 'molecules/s', 'h2d_bytes_per_step': h2d_bytes,
-              'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
+              'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps,
+              'api': 'LanczosNet.forward_sparse(sparse_collate batch): GPU-side batch construction '
+                     '(SURVEY 8f2); bit-identical scores to forward() on the padded batch (checked in-run)',
+              'padded_api': {'value': total / (ms_e2e_dense * 1e-3), 'h2d_bytes_per_step': dense_bytes,
+                             'ms_per_step': ms_e2e_dense / args.steps,
+                             'api': 'LanczosNet.forward(node_feat, L, D, V, mask) on the reference\'s '
+                                    'padded host batch (dense B x N x N x 7 operators over PCIe)'}},
       'gpu_launches': int(launches),
       'clocks': clocks,
       'roofline': roof,

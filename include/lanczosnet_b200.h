@@ -134,6 +134,30 @@ int lnb_spectral_conv_fused(lnb_stream_t stream, const float* X, const float* Q,
                             int K, int S, int H, int relu, int write_pad, float* out);
 
 /* ---------------------------------------------------------------------------------------
+ * GPU-side batch construction from SPARSE per-molecule records (replaces, on the device, the host
+ * pipeline utils/data_helper.py:92-116,155-156 (L4 = D^-1/2 (A + I) D^-1/2 of every bond channel and
+ * of the simple graph) + dataset/qm8.py:57-90,220-291 (zero padding / stacking of node_feat,
+ * node_mask, L, (D, V)) and the dense pass of lnb_graph_prepare).  Inputs, all device pointers:
+ *   sizes [B] real nodes per graph; node_ptr [B+1] their prefix sums; node_feat [node_ptr[B]] atom
+ *   ids of the real nodes; edge_ptr [B+1]; edges [edge_ptr[B]][4] bytes {u, v, bond type, 0}
+ *   (undirected bonds listed once, local node indices); V_rows [node_ptr[B], K] Ritz vectors of the
+ *   real nodes; inv_sqrt_deg [256] fp64 table of deg^-1/2 (entry 0 = 0) from the host's numpy, so
+ *   the fp64 products (scale_i * m_ij) * scale_j and their single rounding to fp32 are bit-identical
+ *   to the reference's preprocessing.
+ * Outputs: everything lnb_graph_prepare emits (same layouts, same bits: ell_val / ell_idx / ell_max /
+ * gext / tiles / rowmap / nrows), the padded node_ids [B,N] int64, mask [B,N] uint8 and
+ * V [B,N,K] that lnb_spectral_stack_forward reads, and -- only when L_dense != NULL -- the padded dense
+ * operators [B,N,N,E1] exactly as the reference's collate builds them.  flags as lnb_graph_prepare.
+ * Limits: N <= 128, 2 <= E1 <= 16, degrees < 255.
+ * ------------------------------------------------------------------------------------- */
+int lnb_graph_prepare_sparse(lnb_stream_t stream, const int32_t* sizes, const int32_t* node_ptr,
+                             const int32_t* node_feat, const int32_t* edge_ptr, const uint8_t* edges,
+                             const float* V_rows, const double* inv_sqrt_deg, int B, int N, int E1,
+                             int K, int flags, float* ell_val, uint8_t* ell_idx, int32_t* ell_max,
+                             int32_t* gext, int32_t* tiles, int32_t* rowmap, int32_t* nrows,
+                             int64_t* node_ids, uint8_t* mask, float* V, float* L_dense);
+
+/* ---------------------------------------------------------------------------------------
  * The whole convolution stack (and optionally the embedding gather in front and the readout
  * behind it) in ONE persistent kernel: every CTA keeps its packed tile's state in shared memory
  * across layers, so between layers nothing touches HBM.  Layer l uses rows [l*H, (l+1)*H) of

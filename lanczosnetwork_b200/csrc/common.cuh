@@ -16,6 +16,9 @@ void count_launch(int n = 1);
 unsigned long long* prof_buffer();          // profiling aid (lnb_debug_set_prof), nullptr = off
 void set_prof_buffer(unsigned long long* p);
 
+void launch_tile_assign(cudaStream_t s, const int32_t* gext, int B, int K, int32_t* tiles,
+                        int32_t* rowmap, int32_t* nrows);   // spectral_conv_fused.cu
+
 inline int finish_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -827,6 +827,22 @@ struct SpectralPolicy {
 
 }  // namespace
 
+namespace lnb {
+// tile table + compact Ritz row list from the extents (shared by lnb_graph_prepare and
+// lnb_graph_prepare_sparse); tiles = [4*B + 2] ints: B + 2 table entries followed by 3*B scratch
+void launch_tile_assign(cudaStream_t s, const int32_t* gext, int B, int K, int32_t* tiles,
+                        int32_t* rowmap, int32_t* nrows) {
+  const size_t tbytes = (size_t)6 * (B + 1) * sizeof(int32_t);
+  const int tsm = tbytes <= 200 * 1024;
+  if (tsm && tbytes > 40 * 1024)
+    cudaFuncSetAttribute(tile_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);
+  if (tsm)
+    tile_assign_kernel<true><<<1, 1024, tbytes, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
+  else
+    tile_assign_kernel<false><<<1, 1024, 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
+}
+}  // namespace lnb
+
 extern "C" {
 
 // profiling aid: register (or clear with NULL) a device buffer of SMs x 32 uint64 phase timers
@@ -858,14 +874,7 @@ int lnb_graph_prepare(lnb_stream_t stream, const float* L, const float* Q, int B
     graph_prepare_kernel<false><<<B, 256, 0, s>>>(L, Q, N, E1, K, ell_val, ell_idx, ell_max, gext,
                                                   flags & 1);
   }
-  const size_t tbytes = (size_t)6 * (B + 1) * sizeof(int32_t);
-  const int tsm = tbytes <= 200 * 1024;
-  if (tsm && tbytes > 40 * 1024)
-    cudaFuncSetAttribute(tile_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes);
-  if (tsm)
-    tile_assign_kernel<true><<<1, 1024, tbytes, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
-  else
-    tile_assign_kernel<false><<<1, 1024, 0, s>>>(gext, B, K, tiles, tiles + B + 2, rowmap, nrows);
+  lnb::launch_tile_assign(s, gext, B, K, tiles, rowmap, nrows);
   lnb::count_launch(2);
   return lnb::finish_launch("graph_prepare");
 }

@@ -18,7 +18,8 @@ import numpy as np
 
 __all__ = [
     'check_dist', 'get_laplacian', 'get_graph_laplacian_eigs', 'prepare_graph',
-    'collate', 'synthetic_molecule', 'synthetic_qm8_batch', 'synthetic_regression_graphs',
+    'collate', 'sparse_collate', 'synthetic_molecule', 'synthetic_qm8_samples', 'synthetic_qm8_batch',
+    'synthetic_regression_graphs',
 ]
 
 EPS = float(np.finfo(np.float32).eps)
@@ -79,8 +80,11 @@ def prepare_graph(adjs, node_feat, label=None):
     adjs = adjs[:, :, None]
   D, V, L4 = get_graph_laplacian_eigs(adjs.sum(axis=2))
   L_multi = np.stack([get_laplacian(adjs[:, :, e]) for e in range(adjs.shape[2])], axis=2)
+  # bond list {u, v, type}, u <= v, each undirected bond once: the sparse record sparse_collate ships
+  edges = np.array([(u, v, c) for c in range(adjs.shape[2])
+                    for u, v in zip(*np.nonzero(np.triu(adjs[:, :, c])))], dtype=np.uint8).reshape(-1, 3)
   rec = {'node_feat': np.asarray(node_feat), 'L_multi': L_multi, 'L_simple_4': L4,
-         'D_simple': D, 'V_simple': V}
+         'D_simple': D, 'V_simple': V, 'edges': edges}
   if label is not None:
     rec['label'] = np.asarray(label)
   return rec
@@ -110,6 +114,39 @@ def collate(samples, num_eigs):
     D[b, :kk] = s['D_simple'][:kk]
     V[b, :n, :kk] = s['V_simple'][:, :kk]
   out = {'node_feat': node_feat, 'node_mask': mask, 'L': L, 'D': D, 'V': V}
+  if 'label' in samples[0]:
+    out['label'] = np.concatenate([np.asarray(s['label'], np.float32).reshape(1, -1)
+                                   for s in samples], axis=0)
+  return out
+
+
+def sparse_collate(samples, num_eigs):
+  """The same batch as ``collate`` in SPARSE form for the GPU-side batch construction
+  (ops.graph_prepare_sparse / LanczosNet.forward_sparse): nothing is padded on the host and the
+  dense operators are not shipped at all.
+
+  Returns numpy arrays: sizes [B] int32, node_ptr [B+1] int32 (prefix sums), node_feat [sum n] int32,
+  edge_ptr [B+1] int32, edges [sum E, 4] uint8 = {u, v, bond type, 0}, D [B,K] float32 (truncated /
+  zero padded like dataset/qm8.py:268-287), V_rows [sum n, K] float32 (rows of real nodes only),
+  N = batch-max node count (the reference's padding target), num_edgetype, label if present."""
+  sizes = np.array([s['L_simple_4'].shape[0] for s in samples], np.int32)
+  B = len(samples)
+  node_ptr = np.zeros(B + 1, np.int32)
+  node_ptr[1:] = np.cumsum(sizes)
+  edge_ptr = np.zeros(B + 1, np.int32)
+  edge_ptr[1:] = np.cumsum([len(s['edges']) for s in samples])
+  node_feat = np.concatenate([np.asarray(s['node_feat']).astype(np.int32) for s in samples])
+  edges = np.zeros((int(edge_ptr[-1]), 4), np.uint8)
+  D = np.zeros((B, num_eigs), np.float32)
+  V_rows = np.zeros((int(node_ptr[-1]), num_eigs), np.float32)
+  for b, s in enumerate(samples):
+    edges[edge_ptr[b]:edge_ptr[b + 1], :3] = s['edges']
+    kk = min(num_eigs, s['D_simple'].shape[0])
+    D[b, :kk] = s['D_simple'][:kk]
+    V_rows[node_ptr[b]:node_ptr[b + 1], :kk] = s['V_simple'][:, :kk]
+  out = {'sizes': sizes, 'node_ptr': node_ptr, 'node_feat': node_feat, 'edge_ptr': edge_ptr,
+         'edges': edges, 'D': D, 'V_rows': V_rows, 'N': int(sizes.max()),
+         'num_edgetype': int(samples[0]['L_multi'].shape[2])}
   if 'label' in samples[0]:
     out['label'] = np.concatenate([np.asarray(s['label'], np.float32).reshape(1, -1)
                                    for s in samples], axis=0)
@@ -155,16 +192,23 @@ def synthetic_qm8_sizes(rng, batch_size, min_nodes=3, max_nodes=26, mean_nodes=1
   return sizes
 
 
-def synthetic_qm8_batch(batch_size, seed=1234, num_eigs=20, num_bond_type=6, num_atom=70,
-                        num_label=16, max_nodes=26):
-  """QM8-shaped padded batch (SURVEY.md 8d config #2): n_b in [3,26], mean ~16."""
+def synthetic_qm8_samples(batch_size, seed=1234, num_bond_type=6, num_atom=70, num_label=16,
+                          max_nodes=26):
+  """Per-molecule records of a QM8-shaped batch (SURVEY.md 8d config #2): n_b in [3,26], mean ~16."""
   rng = np.random.RandomState(seed)
   sizes = synthetic_qm8_sizes(rng, batch_size, max_nodes=max_nodes)
   samples = []
   for n in sizes:
     nf, adjs = synthetic_molecule(rng, n, num_bond_type, num_atom)
     samples.append(prepare_graph(adjs, nf, label=rng.randn(1, num_label)))
-  return collate(samples, num_eigs)
+  return samples
+
+
+def synthetic_qm8_batch(batch_size, seed=1234, num_eigs=20, num_bond_type=6, num_atom=70,
+                        num_label=16, max_nodes=26):
+  """QM8-shaped padded batch: ``collate`` of ``synthetic_qm8_samples``."""
+  return collate(synthetic_qm8_samples(batch_size, seed, num_bond_type, num_atom, num_label,
+                                       max_nodes), num_eigs)
 
 
 def synthetic_regression_graphs(num_graphs=16, seed=123, min_num_nodes=20, max_num_nodes=100,

@@ -16,6 +16,31 @@ from ..spectral_conv import (GraphContext, WeightCache, graph_conv_layer,
                              ritz_filter_coefficients)
 
 
+class Ragged(object):
+  """A tensor whose leading dimension varies from batch to batch (bond lists, rows of real nodes).
+  CUDA-graph replay keeps a static buffer of ``capacity`` rows and copies only the rows present; the
+  consumer kernels read their extents from the pointer arrays that travel with the batch.  The
+  default capacity rounds the row count up to a bucket so batches of similar size share a graph."""
+
+  def __init__(self, tensor, capacity=None, bucket=4096):
+    self.tensor = tensor
+    rows = int(tensor.shape[0])
+    self.capacity = int(capacity) if capacity is not None else max(bucket, -(-rows // bucket) * bucket)
+    if rows > self.capacity:
+      raise ValueError('Ragged: %d rows exceed the capacity %d' % (rows, self.capacity))
+
+  @property
+  def rows(self):
+    return int(self.tensor.shape[0])
+
+  def static_shape(self):
+    return (self.capacity,) + tuple(self.tensor.shape[1:])
+
+
+def _raw(t):
+  return t.tensor if isinstance(t, Ragged) else t
+
+
 def _opt(obj, name, default):
   return getattr(obj, name) if hasattr(obj, name) else default
 
@@ -124,8 +149,8 @@ class SpectralNetBase(nn.Module):
   def _param_signature(self):
     return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-  def _graph_forward(self, impl, inputs):
-    """impl(*device_tensors) -> score; inputs: tuple of tensors / None (CPU or CUDA).
+  def _graph_forward(self, impl, inputs, extra_key=()):
+    """impl(*device_tensors) -> score; inputs: tuple of tensors / Ragged / None (CPU or CUDA).
 
     Two graph slots with their own static buffers alternate, and the input copies run on a
     dedicated copy stream: the H2D (or D2D) transfer of call i+1 overlaps the replay of call i
@@ -135,8 +160,10 @@ class SpectralNetBase(nn.Module):
                 not getattr(self, '_is_replica', False) and
                 not torch.cuda.is_current_stream_capturing())
     if not eligible:
-      return impl(*[self._to(dev, t) for t in inputs])
-    key = (dev.index,) + tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs)
+      return impl(*[self._to(dev, _raw(t)) for t in inputs])
+    key = (dev.index,) + tuple(extra_key) + tuple(
+        None if t is None else ((t.static_shape(), t.tensor.dtype, 'ragged') if isinstance(t, Ragged)
+                                else (tuple(t.shape), t.dtype)) for t in inputs)
     cache = self.__dict__.setdefault('_graphs', {})
     entry = cache.get(key)
     sig = self._param_signature()
@@ -145,8 +172,9 @@ class SpectralNetBase(nn.Module):
     # all.  Such a graph is captured the second time the same buffers show up (data loaders /
     # serving loops that recycle a few device buffers); any live tensor found at a captured
     # address with the captured shape and dtype is read correctly, so no reference is kept.
-    if all(t is None or (t.is_cuda and t.device == dev and t.is_contiguous()) for t in inputs):
-      pkey = key + tuple(None if t is None else t.data_ptr() for t in inputs)
+    raw = [_raw(t) for t in inputs]
+    if all(t is None or (t.is_cuda and t.device == dev and t.is_contiguous()) for t in raw):
+      pkey = key + tuple(None if t is None else t.data_ptr() for t in raw)
       zc = self.__dict__.setdefault('_graphs_resident', {})
       hit = zc.get(pkey)
       if hit is not None and hit['sig'] == sig:
@@ -166,7 +194,7 @@ class SpectralNetBase(nn.Module):
         graph = torch.cuda.CUDAGraph()
         n0 = int(_lib.load().lnb_launch_count())
         with torch.cuda.graph(graph, pool=self._resident_pool):
-          out = impl(*inputs)
+          out = impl(*raw)
         hit = {'graph': graph, 'out': out, 'sig': sig,
                'kernels': int(_lib.load().lnb_launch_count()) - n0}
         zc[pkey] = hit
@@ -176,10 +204,14 @@ class SpectralNetBase(nn.Module):
     if entry is None or entry['sig'] != sig:
       slots = []
       for _ in range(2):
-        static_in = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev)
+        static_in = [None if t is None else
+                     (torch.zeros(t.static_shape(), dtype=t.tensor.dtype, device=dev)
+                      if isinstance(t, Ragged) else torch.empty(t.shape, dtype=t.dtype, device=dev))
                      for t in inputs]
         for s_, t in zip(static_in, inputs):
-          if s_ is not None:
+          if isinstance(t, Ragged):
+            s_[:t.rows].copy_(t.tensor, non_blocking=True)
+          elif s_ is not None:
             s_.copy_(t, non_blocking=True)
         if not slots:
           side = torch.cuda.Stream(device=dev)
@@ -204,11 +236,13 @@ class SpectralNetBase(nn.Module):
     entry['next'] ^= 1
     copy = entry['copy']
     copy.wait_event(slot['free'])              # the previous replay of this slot has consumed its inputs
-    if any(t is not None and t.is_cuda for t in inputs):
+    if any(t is not None and t.is_cuda for t in raw):
       copy.wait_stream(cur)                    # device inputs produced on the caller's stream
     with torch.cuda.stream(copy):
       for s_, t in zip(slot['in'], inputs):
-        if s_ is not None:
+        if isinstance(t, Ragged):
+          s_[:t.rows].copy_(t.tensor, non_blocking=True)     # only the rows present cross PCIe
+        elif s_ is not None:
           s_.copy_(t, non_blocking=True)
       slot['ready'].record(copy)
     cur.wait_event(slot['ready'])
@@ -226,14 +260,20 @@ class SpectralNetBase(nn.Module):
                   for i in (0, 2, 4, 6)])
     return out
 
-  def _ritz_conv_stack(self, state, node_ids, L, D, V, mask):
+  def _ritz_conv_stack(self, state, node_ids, L, D, V, mask, prep=None, dims_hint=None):
     """Convolution stack + readout of the Ritz-pair models (LanczosNet, LanczosNetGeneral).
+    ``prep`` (ops.GraphPrep built on the device by ops.graph_prepare_sparse) replaces the pass over
+    the dense operators; ``L`` may then be None when every layer runs in the fused stack
+    (``dims_hint`` = (N, E1) of the absent tensor).
 
     Consecutive layers the fused kernel supports run as ONE persistent launch (embedding gather
     in front when every layer qualifies, readout behind); a leading layer with an unsupported
     input width (e.g. LanczosNetGeneral's 10 features) runs through the unfused ops first."""
     S, nl = self.num_scale_long, self.num_layer
-    N, K, E1 = L.shape[1], V.shape[2], L.shape[3]
+    if L is not None:
+      N, K, E1 = L.shape[1], V.shape[2], L.shape[3]
+    else:
+      (N, E1), K = dims_hint, V.shape[2]
     din0 = self.embedding.weight.shape[1] if node_ids is not None else state.shape[2]
     dims = [din0] + list(self.hidden_dim)
     ok = [ops.fused_conv_supported(N, dims[t], K, dims[t + 1], len(self.short_diffusion_dist),
@@ -248,7 +288,12 @@ class SpectralNetBase(nn.Module):
     if binarize and not (stack_ok and first == 0):
       L = (L != 0).to(L.dtype)          # shapes off the fused path read the dense operators
       binarize = False
+    if L is None and not (stack_ok and first == 0):
+      raise RuntimeError('sparse batches without the dense operators need every layer on the fused '
+                         'stack kernel; call ops.graph_prepare_sparse(..., want_dense=True)')
     ctx = GraphContext(L, V, binarize)
+    if prep is not None:
+      ctx._prep = prep
     coeffs = table = None
     if S > 0:
       mlp = self._filter_mlp_params() if self.spectral_filter_kind == 'MLP' else None
@@ -308,6 +353,16 @@ class SpectralNetBase(nn.Module):
         emb=self.embedding.weight if (node_ids is not None and first == 0) else None,
         readout=(head.weight, head.bias, att.weight.reshape(-1), att.bias), mask=mask)
     return score
+
+  def _sparse_stack_ok(self, N, E1, K):
+    """True when every layer of this model runs inside the one-launch stack kernel, so a sparse
+    batch never needs the dense operator tensor."""
+    S = self.num_scale_long
+    din0 = self.embedding.weight.shape[1]
+    dims = [din0] + list(self.hidden_dim)
+    ok = all(ops.fused_conv_supported(N, dims[t], K, dims[t + 1], len(self.short_diffusion_dist), False, S, E1)
+             for t in range(self.num_layer))
+    return ok and all(d == dims[1] for d in dims[1:]) and self.num_layer <= 8
 
   def _readout(self, state, mask):
     head = self.filter[self.num_layer]

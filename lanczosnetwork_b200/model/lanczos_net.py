@@ -3,7 +3,8 @@ constructor, parameter names and ``forward(node_feat, L, D, V, label=None, mask=
 the forward runs in hand-written sm_100a CUDA (no CPU path)."""
 import torch.nn as nn
 
-from ._common import SpectralNetBase
+from .. import ops
+from ._common import Ragged, SpectralNetBase
 
 __all__ = ['LanczosNet']
 
@@ -35,3 +36,29 @@ class LanczosNet(SpectralNetBase):
   def _forward_impl(self, node_feat, L, D, V, mask):
     return self._ritz_conv_stack(None, node_feat.long(), L.float().contiguous(),
                                  D.float().contiguous(), V.float().contiguous(), mask)
+
+  def forward_sparse(self, batch, label=None):
+    """Forward from a SPARSE batch (lanczosnetwork_b200.data.sparse_collate -> torch tensors, pinned
+    host or device): per-molecule node ids, bond lists and the Ritz pairs of the real nodes.  The
+    padded operators, mask, ELL rows and tile table are built on the device
+    (lnb_graph_prepare_sparse); the dense B x N x N x (E+1) tensor of the reference's collate
+    (dataset/qm8.py:220-262) is never materialised and never crosses PCIe.  Same scores as
+    ``forward`` on the collated batch, bit for bit.  Returns score or (score, loss)."""
+    self._check_mode()
+    dev = self._device()
+    N, B = int(batch['N']), int(batch['sizes'].shape[0])
+    inputs = (batch['sizes'], batch['node_ptr'], Ragged(batch['node_feat'], B * N), batch['edge_ptr'],
+              Ragged(batch['edges']), Ragged(batch['V_rows'], B * N), batch['D'])
+    score = self._graph_forward(lambda *a: self._forward_sparse_impl(N, *a), inputs,
+                                extra_key=('sparse', N))
+    return self._finish(score, self._to(dev, label))
+
+  def _forward_sparse_impl(self, N, sizes, node_ptr, node_feat, edge_ptr, edges, V_rows, D):
+    E1 = self.num_edgetype + 1
+    K = V_rows.shape[1]
+    dense = not self._sparse_stack_ok(N, E1, K)
+    prep, node_ids, mask, V, L = ops.graph_prepare_sparse(
+        sizes, node_ptr, node_feat, edge_ptr, edges, V_rows, N, E1,
+        binarize=getattr(self, '_binarize_operators', False), want_dense=dense)
+    return self._ritz_conv_stack(None, node_ids, L, D.float().contiguous(), V, mask, prep=prep,
+                                 dims_hint=(N, E1))

@@ -13,7 +13,7 @@ from ._lib import GemmDesc, SpectralStack
 
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
-    'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
+    'graph_prepare_sparse', 'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
     'operator_chain', 'operator_chain_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'lanczos_ritz', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
@@ -194,6 +194,59 @@ def graph_prepare(L, Q, binarize=False):
   prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
   prep.rowmap, prep.nrows = rowmap, nrows
   return prep
+
+
+_INV_SQRT_DEG = {}
+
+
+def _inv_sqrt_deg_table(device):
+  """deg^-1/2 in fp64 for deg = 0..255 exactly as the reference's host code computes it
+  (np.power(deg, -0.5) with inf -> 0, utils/data_helper.py:104-107), cached per device."""
+  key = device.index if device.index is not None else torch.cuda.current_device()
+  if key not in _INV_SQRT_DEG:
+    import numpy as np
+    deg = np.arange(256, dtype=np.float64)
+    with np.errstate(divide='ignore'):
+      t = np.power(deg, -0.5)
+    t[np.isinf(t)] = 0.0
+    _INV_SQRT_DEG[key] = torch.from_numpy(t).to(device)
+  return _INV_SQRT_DEG[key]
+
+
+def graph_prepare_sparse(sizes, node_ptr, node_feat, edge_ptr, edges, V_rows, N, E1, binarize=False,
+                         want_dense=False):
+  """GPU-side batch construction from sparse records (see lnb_graph_prepare_sparse).
+  sizes [B] int32, node_ptr [B+1] int32, node_feat [>= node_ptr[B]] int32, edge_ptr [B+1] int32,
+  edges [>= edge_ptr[B], 4] uint8, V_rows [>= node_ptr[B], K] fp32 -- all CUDA.
+  Returns (GraphPrep, node_ids [B,N] int64, mask [B,N] uint8, V [B,N,K], L [B,N,N,E1] or None)."""
+  _need_cuda(sizes, node_ptr, node_feat, edge_ptr, edges, V_rows)
+  dev = sizes.device
+  B = sizes.shape[0]
+  K = V_rows.shape[1]
+  assert sizes.dtype == torch.int32 and node_ptr.dtype == torch.int32 and node_feat.dtype == torch.int32
+  assert edge_ptr.dtype == torch.int32 and edges.dtype == torch.uint8 and edges.shape[1] == 4
+  assert V_rows.dtype == torch.float32 and V_rows.is_contiguous() and edges.is_contiguous()
+  ell_val = torch.empty((B, E1, N, N), device=dev, dtype=torch.float32)
+  ell_idx = torch.empty((B, E1, N, N), device=dev, dtype=torch.uint8)
+  ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
+  gext = torch.empty((B, 2), device=dev, dtype=torch.int32)
+  tiles = torch.empty((4 * B + 2,), device=dev, dtype=torch.int32)
+  rowmap = torch.empty((B * K,), device=dev, dtype=torch.int32)
+  nrows = torch.empty((1,), device=dev, dtype=torch.int32)
+  node_ids = torch.empty((B, N), device=dev, dtype=torch.int64)
+  mask = torch.empty((B, N), device=dev, dtype=torch.uint8)
+  V = torch.empty((B, N, K), device=dev, dtype=torch.float32)
+  L = torch.empty((B, N, N, E1), device=dev, dtype=torch.float32) if want_dense else None
+  with torch.cuda.device(dev):
+    _lib.check(_lib.load().lnb_graph_prepare_sparse(
+        _stream(sizes), _ptr(sizes), _ptr(node_ptr), _ptr(node_feat), _ptr(edge_ptr), _ptr(edges),
+        _ptr(V_rows), _ptr(_inv_sqrt_deg_table(dev)), B, int(N), int(E1), int(K),
+        1 if binarize else 0, _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max), _ptr(gext), _ptr(tiles),
+        _ptr(rowmap), _ptr(nrows), _ptr(node_ids), _ptr(mask), _ptr(V), _ptr(L)),
+               'lnb_graph_prepare_sparse')
+  prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
+  prep.rowmap, prep.nrows = rowmap, nrows
+  return prep, node_ids, mask, V, L
 
 
 def fused_conv_supported(N, Din, K, H, n_short, dense_filter, S=8, E1=7):

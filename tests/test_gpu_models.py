@@ -451,3 +451,107 @@ def test_online_ritz_provider_feeds_lanczosnet():
   assert torch.isfinite(s_r).all()
   fb = torch.from_numpy(full).to(dev())
   np.testing.assert_allclose(s_r[fb].cpu().numpy(), s_e[fb].cpu().numpy(), rtol=2e-3, atol=2e-4)
+
+
+def _sparse_tensors(sp, device=None, pin=False):
+  out = {}
+  for k, v in sp.items():
+    if isinstance(v, np.ndarray):
+      t = torch.from_numpy(v)
+      if pin:
+        t = t.pin_memory()
+      out[k] = t.to(device) if device is not None else t
+    else:
+      out[k] = v
+  return out
+
+
+def test_graph_prepare_sparse_is_bit_identical_to_collate_plus_prepare():
+  """GPU-side batch construction.  From bond lists + node ids + Ritz rows the device
+  builds (a) the reference's padded tensors -- node_feat, node_mask, V and, on request, the dense
+  L4 operators of every channel -- bit for bit what data.collate (itself bit-exact vs the reference
+  loader, tests/test_host_logic.py) produces on the host, and (b) every output of lnb_graph_prepare
+  run on that dense tensor: ELL values / indices / row maxima, extents, tile table, Ritz row list."""
+  from lanczosnetwork_b200 import ops
+  rng = np.random.RandomState(5)
+  samples = data.synthetic_qm8_samples(200, seed=77)
+  # hand-made corner cases: single atom, two atoms doubly bonded in two channels (multiplicity 2 in the
+  # simple graph), a duplicate bond record, an isolated atom next to a bonded pair
+  def mol(n, bonds):
+    adjs = np.zeros((n, n, 6))
+    for u, v, c in bonds:
+      adjs[u, v, c] = adjs[v, u, c] = 1.0
+    return data.prepare_graph(adjs, rng.randint(0, 70, size=n), label=rng.randn(1, 16))
+  samples += [mol(1, []), mol(2, [(0, 1, 0), (0, 1, 3)]), mol(3, [(0, 1, 2)]), mol(5, [(0, 4, 5), (1, 2, 5), (2, 3, 0)])]
+  dup = mol(4, [(0, 1, 1), (1, 2, 1)])
+  dup['edges'] = np.concatenate([dup['edges'], dup['edges'][:1]], axis=0)      # same bond listed twice
+  samples.append(dup)
+  dense = data.collate(samples, 20)
+  sp = _sparse_tensors(data.sparse_collate(samples, 20), dev())
+  B, N = dense['node_feat'].shape
+  prep_s, ids, mask, V, L = ops.graph_prepare_sparse(sp['sizes'], sp['node_ptr'], sp['node_feat'],
+                                                     sp['edge_ptr'], sp['edges'], sp['V_rows'], N, 7,
+                                                     want_dense=True)
+  assert torch.equal(ids.cpu(), _t(dense['node_feat']))
+  assert torch.equal(mask.cpu(), _t(dense['node_mask']))
+  assert torch.equal(V.cpu(), _t(dense['V']))
+  assert torch.equal(L.cpu(), _t(dense['L']))                 # values: identical bits, not 1 ulp
+  prep_d = ops.graph_prepare(_t(dense['L']).to(dev()), _t(dense['V']).to(dev()))
+  assert torch.equal(prep_s[2], prep_d[2]) and torch.equal(prep_s[3], prep_d[3])       # ell_max, gext
+  T = int(prep_d[4][0])
+  assert torch.equal(prep_s[4][:T + 2], prep_d[4][:T + 2])                              # tile table
+  nr = int(prep_d.nrows)
+  assert int(prep_s.nrows) == nr and torch.equal(prep_s.rowmap[:nr], prep_d.rowmap[:nr])
+  emax = prep_d[2].cpu().numpy()
+  vs, vd = prep_s[0].cpu().numpy(), prep_d[0].cpu().numpy()
+  js, jd = prep_s[1].cpu().numpy(), prep_d[1].cpu().numpy()
+  for b in range(B):
+    for e in range(7):
+      m = emax[b, e]
+      assert np.array_equal(vs[b, e, :m], vd[b, e, :m]) and np.array_equal(js[b, e, :m], jd[b, e, :m])
+  # GCNFP's binarisation flag
+  pb_s = ops.graph_prepare_sparse(sp['sizes'], sp['node_ptr'], sp['node_feat'], sp['edge_ptr'],
+                                  sp['edges'], sp['V_rows'], N, 7, binarize=True)[0]
+  pb_d = ops.graph_prepare(_t(dense['L']).to(dev()), _t(dense['V']).to(dev()), True)
+  for b in range(0, B, 17):
+    for e in range(7):
+      m = emax[b, e]
+      assert torch.equal(pb_s[0][b, e, :m], pb_d[0][b, e, :m])
+
+
+def test_forward_sparse_equals_forward_on_the_collated_batch():
+  """LanczosNet.forward_sparse (device-side batch construction, no dense operators anywhere) returns
+  the same bits as forward on the reference's padded batch: eager, CUDA-graph replay from pinned host
+  records (ragged copies), zero-copy replay on resident records; H2D payload < 1/10 of the dense one."""
+  samples = data.synthetic_qm8_samples(300, seed=5)
+  dense = data.collate(samples, 20)
+  spn = data.sparse_collate(samples, 20)
+  mod, params = _build(LanczosNet, configs.qm8_lanczos_net(), 1234)
+  spec = oracle_spec(mod, 'LanczosNet')
+  ref = orc.lanczos_net_forward(params, spec, dense['node_feat'], dense['L'], dense['D'], dense['V'],
+                                dense['node_mask']).numpy()
+  args = [_t(dense[k]).to(dev()) for k in ('node_feat', 'L', 'D', 'V')]
+  with torch.no_grad():
+    mod.use_cuda_graph = False
+    want = mod(*args, mask=_t(dense['node_mask']).to(dev()))
+    eager = mod.forward_sparse(_sparse_tensors(spn, dev()))
+    assert torch.equal(eager, want)
+    np.testing.assert_allclose(eager.cpu().numpy(), ref, rtol=FWD_RTOL, atol=FWD_ATOL)
+    mod.use_cuda_graph = True
+    host = _sparse_tensors(spn, pin=True)
+    for _ in range(3):
+      assert torch.equal(mod.forward_sparse(host), want)
+    # a second batch of the same B with different sizes goes through the same static buffers
+    samples2 = data.synthetic_qm8_samples(300, seed=6)
+    d2 = data.collate(samples2, 20)
+    want2 = mod(*[_t(d2[k]).to(dev()) for k in ('node_feat', 'L', 'D', 'V')], mask=_t(d2['node_mask']).to(dev()))
+    assert torch.equal(mod.forward_sparse(_sparse_tensors(data.sparse_collate(samples2, 20), pin=True)), want2)
+    assert torch.equal(mod.forward_sparse(host), want)
+    res = _sparse_tensors(spn, dev())
+    for _ in range(3):
+      assert torch.equal(mod.forward_sparse(res), want)
+    score, loss = mod.forward_sparse(host, label=_t(dense['label']).to(dev()))
+    assert torch.equal(score, want) and loss.ndim == 0
+  h2d_sparse = sum(v.nbytes for v in spn.values() if isinstance(v, np.ndarray) and v.dtype != np.float64) - spn['label'].nbytes
+  h2d_dense = sum(dense[k].nbytes for k in ('node_feat', 'L', 'D', 'V', 'node_mask'))
+  assert h2d_sparse * 10 < h2d_dense, (h2d_sparse, h2d_dense)
