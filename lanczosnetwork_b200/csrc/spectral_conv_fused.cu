@@ -764,7 +764,7 @@ struct SpectralPolicy {
     {
       const int warp = tid >> 5, lane = tid & 31;
       const int rb = warp & 3, og = warp >> 2;
-      const int per = (P1 + 2) / 3;
+      const int per = (P1 + tcg::NGROUPS - 1) / tcg::NGROUPS;
       const int o_end = min(P1, (og + 1) * per);
       const int row = rb * 32 + lane;
       const float4* x4 = reinterpret_cast<const float4*>(Xs + (size_t)(row < Rtot ? row : 0) * XP);
