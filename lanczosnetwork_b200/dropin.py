@@ -30,16 +30,22 @@ def register_native_op():
     setattr(ops_pkg, '_ext', _ext_pkg)
 
 
-def patch_namespace(module):
-  """Rebind the three class names in ``module``'s globals to the B200 drop-ins."""
+def patch_namespace(module, training=False):
+  """Rebind the class names in ``module``'s globals to the B200 drop-ins.  ``training=True`` (a
+  run without ``-t``) rebinds only the classes that have a differentiable training path
+  (LanczosNet, LanczosNetGeneral, GCN, GCNFP); the others keep the reference's trainable class
+  instead of failing on the first ``loss.backward()``."""
   for name in DROPIN_CLASSES:
     if hasattr(module, name):
-      setattr(module, name, getattr(_models, name))
+      cls = getattr(_models, name)
+      if training and not hasattr(cls, '_train_impl'):
+        continue
+      setattr(module, name, cls)
   return module
 
 
 def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.graph_runner'),
-            compat=False):
+            compat=False, training=False):
   """Returns the list of patched modules.  ``reference_root`` is put on sys.path if given.
   ``compat=True`` first installs the shims of ``lanczosnetwork_b200.compat`` (missing easydict /
   tensorboardX, PyYAML >= 6, numpy >= 2) so the 2019 checkout imports under a current stack.
@@ -56,7 +62,7 @@ def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.gr
   register_native_op()
   patched = []
   ref_model = importlib.import_module('model')
-  patched.append(patch_namespace(ref_model))
+  patched.append(patch_namespace(ref_model, training))
   errors = []
   for name in runner_modules:
     try:
@@ -64,7 +70,7 @@ def install(reference_root=None, runner_modules=('runner.qm8_runner', 'runner.gr
     except ImportError as exc:      # e.g. tensorboardX absent: that runner cannot be used anyway
       errors.append('%s: %s' % (name, exc))
       continue
-    patched.append(patch_namespace(mod))
+    patched.append(patch_namespace(mod, training))
   if runner_modules and len(patched) == 1:
     raise ImportError('dropin.install: no runner module could be imported, nothing would call the '
                       'B200 classes (%s); pass compat=True for the shims of '
@@ -77,7 +83,7 @@ def main(argv=None):
   if not argv:
     raise SystemExit(__doc__)
   root = argv.pop(0)
-  install(root, compat=True)
+  install(root, compat=True, training=('-t' not in argv and '--test' not in argv))
   os.chdir(root)
   sys.argv = ['run_exp.py'] + argv
   run_exp = importlib.import_module('run_exp')

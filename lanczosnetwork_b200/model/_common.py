@@ -120,13 +120,20 @@ class SpectralNetBase(nn.Module):
     return dev
 
   def _check_mode(self):
+    """Returns True when this call has to be differentiable (autograd on, trainable parameters):
+    the forward then runs the training path of lanczosnetwork_b200.train (unfused, every
+    contraction and its adjoint in this library's kernels) instead of the fused inference kernels.
+    Models without a training path raise."""
     if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-      raise NotImplementedError(
-          '%s is forward-only in this build: call it under torch.no_grad() (as '
-          'runner.test() / the validation loop do). The backward of the fused ops is the '
-          'next scope row (SURVEY.md 8f1).' % type(self).__name__)
+      if not hasattr(self, '_train_impl'):
+        raise NotImplementedError(
+            '%s has no training path in this build: call it under torch.no_grad() (as '
+            'runner.test() / the validation loop do).' % type(self).__name__)
+      return True
     if self.training and self.dropout > 0.0:
-      raise NotImplementedError('dropout > 0 in training mode is not supported (forward-only)')
+      raise NotImplementedError('dropout > 0 in training mode needs autograd enabled (the inference '
+                                'kernels implement eval() semantics)')
+    return False
 
   @staticmethod
   def _to(dev, t, dtype=None):

@@ -41,10 +41,18 @@ class GCN(SpectralNetBase):
       node_feat: long B x N (atom ids); L: float B x N x N x (E+1); label: B x P;
       mask: B x N (uint8 / bool / float).  Returns score (B x P) or (score, loss).
     """
-    self._check_mode()
     dev = self._device()
-    score = self._graph_forward(self._forward_impl, (node_feat, L, mask))
+    if self._check_mode():
+      score = self._train_impl(*[self._to(dev, t) for t in (node_feat, L, mask)])
+    else:
+      score = self._graph_forward(self._forward_impl, (node_feat, L, mask))
     return self._finish(score, self._to(dev, label))
+
+  def _train_impl(self, node_feat, L, mask):
+    from ..train import ritz_stack_train
+    if getattr(self, '_binarize_operators', False):
+      L = (L != 0).to(torch.float32)                 # model/gcnfp.py:83
+    return ritz_stack_train(self, None, node_feat, L, None, None, mask)
 
   def _forward_impl(self, node_feat, L, mask):
     L = L.float().contiguous()

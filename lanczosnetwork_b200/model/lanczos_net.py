@@ -28,10 +28,16 @@ class LanczosNet(SpectralNetBase):
       V: Ritz vectors B x N x K; label: B x P; mask: B x N (uint8 / bool / float).
       Returns score (B x P) or (score, loss) when label is given.
     """
-    self._check_mode()
     dev = self._device()
-    score = self._graph_forward(self._forward_impl, (node_feat, L, D, V, mask))
+    if self._check_mode():
+      score = self._train_impl(*[self._to(dev, t) for t in (node_feat, L, D, V, mask)])
+    else:
+      score = self._graph_forward(self._forward_impl, (node_feat, L, D, V, mask))
     return self._finish(score, self._to(dev, label))
+
+  def _train_impl(self, node_feat, L, D, V, mask):
+    from ..train import ritz_stack_train
+    return ritz_stack_train(self, None, node_feat, L, D, V, mask)
 
   def _forward_impl(self, node_feat, L, D, V, mask):
     return self._ritz_conv_stack(None, node_feat.long(), L.float().contiguous(),
@@ -44,7 +50,8 @@ class LanczosNet(SpectralNetBase):
     (lnb_graph_prepare_sparse); the dense B x N x N x (E+1) tensor of the reference's collate
     (dataset/qm8.py:220-262) is never materialised and never crosses PCIe.  Same scores as
     ``forward`` on the collated batch, bit for bit.  Returns score or (score, loss)."""
-    self._check_mode()
+    if self._check_mode():
+      raise NotImplementedError('forward_sparse is an inference path; train through forward()')
     dev = self._device()
     N, B = int(batch['N']), int(batch['sizes'].shape[0])
     inputs = (batch['sizes'], batch['node_ptr'], Ragged(batch['node_feat'], B * N), batch['edge_ptr'],

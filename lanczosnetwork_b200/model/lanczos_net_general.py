@@ -27,10 +27,16 @@ class LanczosNetGeneral(SpectralNetBase):
       node_feat: float B x N x D node features; L: B x N x N x (E+1); D: Ritz values B x K;
       V: Ritz vectors B x N x K; label: B x P; mask: B x N.
     """
-    self._check_mode()
     dev = self._device()
-    score = self._graph_forward(self._forward_impl, (node_feat, L, D, V, mask))
+    if self._check_mode():
+      score = self._train_impl(*[self._to(dev, t) for t in (node_feat, L, D, V, mask)])
+    else:
+      score = self._graph_forward(self._forward_impl, (node_feat, L, D, V, mask))
     return self._finish(score, self._to(dev, label))
+
+  def _train_impl(self, node_feat, L, D, V, mask):
+    from ..train import ritz_stack_train
+    return ritz_stack_train(self, node_feat, None, L, D, V, mask)
 
   def _forward_impl(self, node_feat, L, D, V, mask):
     return self._ritz_conv_stack(node_feat.float().contiguous(), None, L.float().contiguous(),

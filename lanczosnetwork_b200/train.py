@@ -1,0 +1,222 @@
+"""Training path: the forward AND backward of the spectral-convolution models as
+``torch.autograd.Function``s whose arithmetic runs in this library's CUDA kernels.
+
+The reference trains through autograd over ``torch.bmm`` / ``nn.Linear``
+(runner/qm8_runner.py:188-259, ``train_loss.backward()`` at :247).  Here every contraction of the
+forward and of its adjoint goes through the C ABI:
+
+  * dense layers ``act(x W^T + b)`` and their two adjoint products (``g W`` and ``g^T x``): the
+    tcgen05 3xTF32 kernel (lnb_linear_tf32x3) -- the big Linear of the graph-conv layer is 97 % of
+    the flops of a training step;
+  * operator products ``L_e X``, ``L_e^T G`` (channel-innermost operators read in place through
+    their strides), ``V^T X``, ``V diag(f) U`` and their adjoints: the strided batched GEMM
+    (lnb_batched_gemm);
+  * the embedding gradient: the scatter-add of the reference's own ``unsorted_segment_sum`` op
+    (lnb_unsorted_segment_sum_forward).
+
+PyTorch supplies what it supplies everywhere in this package -- tensor memory, streams, the autograd
+tape -- plus the pointwise glue of the adjoint (ReLU masks, sigmoid gate, masked mean, the loss).
+The training forward is the UNFUSED formulation (activations have to exist to be differentiated);
+the one-launch fused stack remains the inference path.  Gradients are checked against
+``torch.autograd`` over the fp64 CPU oracle in tests/test_gpu_train.py.
+"""
+import torch
+
+from . import ops
+
+__all__ = ['dense', 'operator_messages', 'spectral_messages', 'embedding', 'ritz_stack_train']
+
+
+def _pad_cols(x, mult=4):
+  k = x.shape[1]
+  if k % mult == 0:
+    return x.contiguous()
+  return torch.nn.functional.pad(x, (0, mult - k % mult)).contiguous()
+
+
+def _matmul_nt(a, w):
+  """a [M,K] @ w[N,K]^T on the tcgen05 3xTF32 kernel; K is zero padded to a multiple of 4."""
+  a, w = _pad_cols(a.float()), _pad_cols(w.float())
+  w_hi, w_lo = ops.split_tf32(w)
+  return ops.linear_tf32x3(a, w_hi, w_lo, None, False)
+
+
+class _Dense(torch.autograd.Function):
+  """y = act(x W^T + b): nn.Linear (+ ReLU) of model/lanczos_net.py:109-113,180-181,188-189."""
+
+  @staticmethod
+  def forward(ctx, x, weight, bias, relu):
+    xp, wp = _pad_cols(x.float()), _pad_cols(weight.float())
+    w_hi, w_lo = ops.split_tf32(wp)
+    y = ops.linear_tf32x3(xp, w_hi, w_lo, bias, relu)
+    ctx.relu = bool(relu)
+    ctx.save_for_backward(x, weight, y if relu else None)
+    ctx.has_bias = bias is not None
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, weight, y = ctx.saved_tensors
+    gy = gy.contiguous()
+    if ctx.relu:
+      gy = gy * (y > 0).to(gy.dtype)
+    gx = gw = gb = None
+    if ctx.needs_input_grad[0]:
+      gx = _matmul_nt(gy, weight.t())[:, :x.shape[1]]               # g W
+    if ctx.needs_input_grad[1]:
+      gw = _matmul_nt(gy.t(), x.t())[:, :weight.shape[1]]           # g^T x
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+      gb = gy.sum(dim=0)
+    return gx, gw, gb, None
+
+
+def dense(x, weight, bias, relu=False):
+  return _Dense.apply(x, weight, bias, relu)
+
+
+class _OperatorMessages(torch.autograd.Function):
+  """msg[b, n, e*D:(e+1)*D] = (L[b, :, :, e] X[b])[n]   for the channels e in ``channels``
+  (model/lanczos_net.py:177-178); adjoint: gX = sum_e L_e^T g_e."""
+
+  @staticmethod
+  def forward(ctx, L, X, c0, nc):
+    B, N, D = X.shape
+    E1 = L.shape[3]
+    X = X.contiguous()
+    msg = torch.empty((B, N, nc * D), device=X.device, dtype=torch.float32)
+    ops.bgemm(L, (N * N * E1, 1, N * E1, E1), X, (N * D, 0, D, 1), msg, (N * nc * D, D, nc * D, 1),
+              B, nc, N, D, N, a_off=c0)
+    ctx.save_for_backward(L)
+    ctx.c0, ctx.nc = c0, nc
+    return msg
+
+  @staticmethod
+  def backward(ctx, g):
+    (L,) = ctx.saved_tensors
+    B, N, E1 = L.shape[0], L.shape[1], L.shape[3]
+    nc = ctx.nc
+    D = g.shape[2] // nc
+    g = g.contiguous()
+    tmp = torch.empty((B, nc, N, D), device=g.device, dtype=torch.float32)
+    # A[m = column c][k = row r] = L[b, r, c, e]: the transpose through swapped strides
+    ops.bgemm(L, (N * N * E1, 1, E1, N * E1), g, (N * nc * D, D, nc * D, 1), tmp,
+              (nc * N * D, N * D, D, 1), B, nc, N, D, N, a_off=ctx.c0)
+    return None, tmp.sum(dim=1), None, None
+
+
+def operator_messages(L, X, c0=0, nc=None):
+  return _OperatorMessages.apply(L, X, c0, L.shape[3] - c0 if nc is None else nc)
+
+
+class _SpectralMessages(torch.autograd.Function):
+  """msg[b, n, s*D:(s+1)*D] = (V diag(F[:, :, s]) V^T X)[b, n]  in factored form
+  (model/lanczos_net.py:114-123,172-175); F = filter coefficients [B,K,S] (differentiable: they are
+  the output of the learned spectral filter), V is data."""
+
+  @staticmethod
+  def forward(ctx, V, X, F):
+    B, N, D = X.shape
+    K, S = V.shape[2], F.shape[2]
+    X, F = X.contiguous(), F.contiguous()
+    U = torch.empty((B, K, D), device=X.device, dtype=torch.float32)
+    ops.bgemm(V, (N * K, 0, 1, K), X, (N * D, 0, D, 1), U, (K * D, 0, D, 1), B, 1, K, D, N)
+    msg = torch.empty((B, N, S * D), device=X.device, dtype=torch.float32)
+    ops.bgemm(V, (N * K, 0, K, 1), U, (K * D, 0, D, 1), msg, (N * S * D, D, S * D, 1), B, S, N, D, K,
+              kscale=F, s_str=(K * S, 1, S))
+    ctx.save_for_backward(V, U, F)
+    return msg
+
+  @staticmethod
+  def backward(ctx, g):
+    V, U, F = ctx.saved_tensors
+    B, N, K = V.shape
+    S = F.shape[2]
+    D = U.shape[2]
+    g = g.contiguous()
+    T = torch.empty((B, S, K, D), device=g.device, dtype=torch.float32)        # T_s = V^T g_s
+    ops.bgemm(V, (N * K, 0, 1, K), g, (N * S * D, D, S * D, 1), T, (S * K * D, K * D, D, 1),
+              B, S, K, D, N)
+    gF = (T * U.unsqueeze(1)).sum(dim=3).permute(0, 2, 1).contiguous()         # [B,K,S]
+    gU = (T * F.permute(0, 2, 1).unsqueeze(3)).sum(dim=1).contiguous()         # [B,K,D]
+    gX = torch.empty((B, N, D), device=g.device, dtype=torch.float32)
+    ops.bgemm(V, (N * K, 0, K, 1), gU, (K * D, 0, D, 1), gX, (N * D, 0, D, 1), B, 1, N, D, K)
+    return None, gX, gF
+
+
+def spectral_messages(V, X, F):
+  return _SpectralMessages.apply(V, X, F)
+
+
+class _Embedding(torch.autograd.Function):
+  """state = table[ids] (model/lanczos_net.py:154); the gradient of the table is the scatter-add of
+  the reference's own unsorted_segment_sum op."""
+
+  @staticmethod
+  def forward(ctx, ids, table):
+    ctx.save_for_backward(ids)
+    ctx.rows = table.shape[0]
+    return ops.embedding_rows(ids, table)
+
+  @staticmethod
+  def backward(ctx, g):
+    (ids,) = ctx.saved_tensors
+    D = g.shape[-1]
+    flat = g.reshape(1, -1, D).contiguous()
+    seg = ids.reshape(1, -1).clamp(0, ctx.rows - 1)
+    return None, ops.segment_sum_forward(flat, seg, ctx.rows)[0]
+
+
+def embedding(ids, table):
+  return _Embedding.apply(ids.long(), table)
+
+
+def ritz_stack_train(model, state, node_ids, L, D, V, mask):
+  """Differentiable convolution stack + readout of LanczosNet / LanczosNetGeneral / GCN
+  (model/lanczos_net.py:125-199): same math, same parameter tensors as the inference path."""
+  L = L.float().contiguous()
+  if node_ids is not None:
+    state = embedding(node_ids, model.embedding.weight)
+  else:
+    state = state.float().contiguous()
+  B, N = state.shape[0], state.shape[1]
+  S = model.num_scale_long
+  short = list(model.short_diffusion_dist)
+  table = None
+  if S > 0:
+    V = V.float().contiguous()
+    table = ops.ritz_power_table(D.float().contiguous(), model.long_diffusion_dist)   # [B,K,S], data
+    K = table.shape[1]
+  for t in range(model.num_layer):
+    msgs = []
+    if short:                                   # walk <- L0 walk (lanczos_net.py:164-169)
+      walk = state
+      for step in range(1, max(short) + 1):
+        walk = operator_messages(L, walk, 0, 1)
+        if step in short:
+          msgs.append(walk)
+    if S > 0:
+      if model.spectral_filter_kind == 'MLP':
+        seq = model.spectral_filter[t]
+        h = table.reshape(B * K, S)
+        for i in (0, 2, 4, 6):
+          h = dense(h, seq[i].weight, seq[i].bias, i != 6)
+        F = h.reshape(B, K, S)
+      else:
+        F = table
+      msgs.append(spectral_messages(V, state, F))
+    msgs.append(operator_messages(L, state))
+    msg = torch.cat(msgs, dim=2) if len(msgs) > 1 else msgs[0]
+    lin = model.filter[t]
+    state = dense(msg.reshape(B * N, -1), lin.weight, lin.bias, True).reshape(B, N, -1)
+    if model.training and model.dropout > 0.0:
+      state = torch.nn.functional.dropout(state, model.dropout, True)
+  # gated readout (lanczos_net.py:185-194): pointwise glue on the autograd tape
+  head, att = model.filter[model.num_layer], model.att_func[0]
+  flat = state.reshape(B * N, -1)
+  y = dense(flat, head.weight, head.bias, False).reshape(B, N, -1)
+  gate = torch.sigmoid(dense(flat, att.weight, att.bias, False)).reshape(B, N, 1)
+  y = y * gate
+  if mask is None:
+    return y.mean(dim=1)
+  m = (mask != 0).to(y.dtype).unsqueeze(2)
+  return (y * m).sum(dim=1) / m.sum(dim=1)

@@ -127,9 +127,14 @@ def test_dropin_surface_and_checkpoint_compat(tmp_path):
                           _t(g['V']).cuda(), label=_t(g['label']).cuda(),
                           mask=_t(g['node_mask']).cuda())
   assert score.shape == (8, 16) and torch.isfinite(score).all() and loss.ndim == 0
-  with pytest.raises(NotImplementedError):
-    wrapped.module(_t(g['node_feat']).cuda(), _t(g['L']).cuda(), _t(g['D']).cuda(),
-                   _t(g['V']).cuda(), mask=_t(g['node_mask']).cuda())   # grad enabled -> forward-only
+  train_score = wrapped.module(_t(g['node_feat']).cuda(), _t(g['L']).cuda(), _t(g['D']).cuda(),
+                               _t(g['V']).cuda(), mask=_t(g['node_mask']).cuda())
+  assert train_score.requires_grad            # grad enabled -> the differentiable training path
+  torch.testing.assert_close(train_score.detach(), score, rtol=1e-4, atol=2e-5)
+  ada = AdaLanczosNet(configs.qm8_ada_lanczos_net(num_layer=1, hidden_dim=[32], num_eig_vec=8,
+                                                  long_diffusion_dist=[2], short_diffusion_dist=[])).cuda()
+  with pytest.raises(NotImplementedError):    # models without a training path say so
+    ada(_t(g['node_feat']).cuda(), _t(g['L']).cuda(), mask=_t(g['node_mask']).cuda())
   with pytest.raises(RuntimeError):
     LanczosNet(cfg)(_t(g['node_feat']), _t(g['L']), _t(g['D']), _t(g['V']))   # CPU module: loud
 
