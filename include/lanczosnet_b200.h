@@ -242,6 +242,23 @@ int lnb_operator_chain(lnb_stream_t stream, const float* L, const float* X, int 
                        float* out, int64_t out_batch_stride, int64_t out_row_stride, int out_col0);
 
 /* ---------------------------------------------------------------------------------------
+ * The whole message matrix of a general-shape spectral convolution layer in one launch
+ * (model/lanczos_net.py:157-180, model/ada_lanczos_net.py:321-345):
+ *   out[b, n, :] = [ (L_0^k X)[n] : k selected ] ++ [ (Q G_s Q^T X)[n] : s < S ] ++ [ (L_e X)[n] : e < E1 ]
+ * L [B,N,N,E1], X [B,N,D], Q [B,N,K]; filt = G [B,S,K,K] symmetric blocks when dense_filter != 0
+ * (AdaLanczosNet's learned filter), else the diagonal coefficients [B,K,S] (LanczosNet).  Short walk:
+ * step i (1-based) goes to column block block_of_step[i-1] (< 0: not stored; host array of
+ * short_steps ints), the long scales to blocks n_short + s, the edge types to n_short + S + e; every
+ * block is D columns wide; out strides in elements.  One CTA per graph, thread per feature column,
+ * operators and filters in shared memory, every intermediate in registers.  N <= 32, K <= 32,
+ * E1 <= 16, S <= 8 (LNB_ERR_UNSUPPORTED otherwise: callers compose lnb_batched_gemm calls).
+ * ------------------------------------------------------------------------------------- */
+int lnb_graph_messages(lnb_stream_t stream, const float* L, const float* X, const float* Q,
+                       const float* filt, int B, int N, int E1, int D, int K, int S, int dense_filter,
+                       int short_steps, const int* block_of_step /* host */, int n_short, float* out,
+                       int64_t out_batch_stride, int64_t out_row_stride);
+
+/* ---------------------------------------------------------------------------------------
  * Gaussian-kernel graph Laplacian (model/ada_lanczos_net.py:101-137, adjacency from :310-311):
  *   adj = (L[b,i,j,0] != 0);  dist2 = |x_i - x_j|^2;  sigma2 = mean over all N^2 pairs;
  *   A = exp(-dist2/sigma2) * adj;  d = (rowsum + [rowsum==0])^-1/2;  out = d_i A_ij d_j

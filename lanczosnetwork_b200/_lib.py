@@ -88,6 +88,8 @@ SIGNATURES = {
                             c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_operator_chain': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    ctypes.POINTER(c_int), c_f32p, c_i64, c_i64, c_int]),
+    'lnb_graph_messages': (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, c_f32p, c_i64, c_i64]),
     'lnb_gaussian_laplacian': (c_int, [c_stream, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_f32p]),
     'lnb_lanczos_tridiag': (c_int, [c_stream, c_f32p, ctypes.c_void_p, c_f32p, c_int, c_int, c_int,
                                     c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),

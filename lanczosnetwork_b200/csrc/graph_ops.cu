@@ -227,6 +227,158 @@ operator_chain_kernel(const float* __restrict__ L, const float* __restrict__ X, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Whole message matrix of a general-shape spectral convolution layer in ONE launch
+// (model/lanczos_net.py:157-180, model/ada_lanczos_net.py:321-345):
+//   msg = [ L_0^k X  (k in short) ] ++ [ Q G_s Q^T X  (s < S) ] ++ [ L_e X  (e < E1) ]
+// with G_s either dense symmetric K x K blocks (AdaLanczosNet's learned filter) or diag(f[:, s])
+// (LanczosNet).  One CTA per graph, thread <-> feature column d: the column X[:, d] and every
+// intermediate (walk, U = Q^T x, G u, Q w) live in registers with fully unrolled static indexing;
+// the operators (transposed), Q, Q^T and the filters are staged once in shared memory and read as
+// 16-byte broadcasts.  Replaces five launches of the FFMA batched GEMM per layer (36 us each at
+// B = 256, tiles of 64 x 64 for 26-row operands) by one.
+constexpr int MSG_NMAX = 32, MSG_KMAX = 32;
+
+struct MsgParams {
+  const float* L; const float* X; const float* Q; const float* G; const float* coeff;
+  int N, E1, D, K, S, dense_filter, short_steps, n_short;
+  ChainSel sel;
+  float* out; int64_t out_sb, out_sn;
+};
+
+__device__ __forceinline__ void msg_matvec(const float* __restrict__ Mt /* [32][32]: Mt[i][n] */,
+                                           const float (&in)[MSG_NMAX], float (&acc)[MSG_NMAX]) {
+#pragma unroll
+  for (int n = 0; n < MSG_NMAX; ++n) acc[n] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MSG_NMAX; ++i) {
+    const float o = in[i];
+    const float4* l4 = reinterpret_cast<const float4*>(Mt + i * MSG_NMAX);
+#pragma unroll
+    for (int q = 0; q < MSG_NMAX / 4; ++q) {
+      const float4 l = l4[q];
+      acc[4 * q + 0] = fmaf(l.x, o, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(l.y, o, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(l.z, o, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(l.w, o, acc[4 * q + 3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+graph_messages_kernel(const MsgParams P) {
+  extern __shared__ __align__(16) float msg_smem[];
+  const int N = P.N, E1 = P.E1, D = P.D, K = P.K, S = P.S;
+  float* Lt = msg_smem;                                   // [E1][32][32]  Lt[e][i][n] = L[n][i][e]
+  float* Qs = Lt + (size_t)E1 * MSG_NMAX * MSG_NMAX;      // [32 n][32 k]
+  float* Qt = Qs + MSG_NMAX * MSG_KMAX;                   // [32 k][32 n]
+  float* Gs = Qt + MSG_NMAX * MSG_KMAX;                   // [S][32][32] dense blocks, or [S][32] diagonals
+  const int g = blockIdx.x, d = blockIdx.y * blockDim.x + threadIdx.x, t = threadIdx.x, nt = blockDim.x;
+  // blockIdx.z: 0 = edge types + short walk, 1 = long scales (two CTAs per graph halve the serial
+  // work of a column; each stages only what it reads)
+  const bool do_edges = blockIdx.z == 0, do_long = (gridDim.z == 1 || blockIdx.z == 1) && S > 0;
+  const bool live = d < D;
+  const float* Lg = P.L + (int64_t)g * N * N * E1;
+  if (do_edges) for (int e = t; e < E1 * MSG_NMAX * MSG_NMAX; e += nt) Lt[e] = 0.f;
+  if (do_long) for (int e = t; e < 2 * MSG_NMAX * MSG_KMAX; e += nt) Qs[e] = 0.f;
+  __syncthreads();
+  if (do_edges) for (int e = t; e < N * N * E1; e += nt) {              // coalesced read, transposed scatter
+    const int ch = e % E1, ij = e / E1, r = ij / N, c = ij - r * N;
+    Lt[((size_t)ch * MSG_NMAX + c) * MSG_NMAX + r] = __ldg(Lg + e);
+  }
+  if (do_long) {
+    const float* Qg = P.Q + (int64_t)g * N * K;
+    for (int e = t; e < N * K; e += nt) {
+      const int n = e / K, k = e - n * K;
+      const float v = __ldg(Qg + e);
+      Qs[n * MSG_KMAX + k] = v;
+      Qt[k * MSG_NMAX + n] = v;
+    }
+    if (P.dense_filter) {
+      const float* Gg = P.G + (int64_t)g * S * K * K;
+      for (int e = t; e < S * MSG_KMAX * MSG_KMAX; e += nt) {
+        const int s = e / (MSG_KMAX * MSG_KMAX), rc = e - s * MSG_KMAX * MSG_KMAX;
+        const int r = rc / MSG_KMAX, c = rc - r * MSG_KMAX;
+        // row r of Gs = column r of G_s (what the unrolled product over the input index reads)
+        Gs[e] = (r < K && c < K) ? __ldg(Gg + ((int64_t)s * K + c) * K + r) : 0.f;
+      }
+    } else {
+      const float* fg = P.coeff + (int64_t)g * K * S;       // [K][S]
+      for (int e = t; e < S * MSG_KMAX; e += nt) {
+        const int s = e / MSG_KMAX, k = e - s * MSG_KMAX;
+        Gs[e] = (k < K) ? __ldg(fg + (int64_t)k * S + s) : 0.f;
+      }
+    }
+  }
+  float x[MSG_NMAX];
+  const float* Xg = P.X + (int64_t)g * N * D + d;
+#pragma unroll
+  for (int n = 0; n < MSG_NMAX; ++n) x[n] = (live && n < N) ? __ldg(Xg + (int64_t)n * D) : 0.f;
+  __syncthreads();
+  float* og = P.out + (int64_t)g * P.out_sb + d;
+  float y[MSG_NMAX];
+  // ---- edge types (and the first step of the short walk: both are L_0 X) ------------------------
+  if (do_edges)
+  for (int e = E1 - 1; e >= 0; --e) {                      // channel 0 last: its result seeds the walk
+    msg_matvec(Lt + (size_t)e * MSG_NMAX * MSG_NMAX, x, y);
+    if (live) {
+#pragma unroll
+      for (int n = 0; n < MSG_NMAX; ++n)
+        if (n < N) og[(int64_t)n * P.out_sn + (int64_t)(P.n_short + S + e) * D] = y[n];
+    }
+  }
+  // ---- short diffusion walk: w_k = L_0 w_{k-1} (lanczos_net.py:164-169) ---------------------------
+  for (int step = 1; do_edges && step <= P.short_steps; ++step) {
+    if (step > 1) {
+      float w[MSG_NMAX];
+#pragma unroll
+      for (int n = 0; n < MSG_NMAX; ++n) w[n] = y[n];
+      msg_matvec(Lt, w, y);
+    }
+    const int blk = P.sel.blk[step - 1];
+    if (blk >= 0 && live) {
+#pragma unroll
+      for (int n = 0; n < MSG_NMAX; ++n)
+        if (n < N) og[(int64_t)n * P.out_sn + (int64_t)blk * D] = y[n];
+    }
+  }
+  // ---- long scales: Q G_s (Q^T x) -------------------------------------------------------------------
+  if (do_long) {
+    float u[MSG_KMAX];
+#pragma unroll
+    for (int k = 0; k < MSG_KMAX; ++k) u[k] = 0.f;
+#pragma unroll
+    for (int n = 0; n < MSG_NMAX; ++n) {                   // u = Q^T x
+      const float o = x[n];
+      const float4* q4 = reinterpret_cast<const float4*>(Qs + n * MSG_KMAX);
+#pragma unroll
+      for (int q = 0; q < MSG_KMAX / 4; ++q) {
+        const float4 l = q4[q];
+        u[4 * q + 0] = fmaf(l.x, o, u[4 * q + 0]); u[4 * q + 1] = fmaf(l.y, o, u[4 * q + 1]);
+        u[4 * q + 2] = fmaf(l.z, o, u[4 * q + 2]); u[4 * q + 3] = fmaf(l.w, o, u[4 * q + 3]);
+      }
+    }
+    for (int s = 0; s < S; ++s) {
+      float w[MSG_KMAX];
+      if (P.dense_filter) {
+        msg_matvec(Gs + (size_t)s * MSG_KMAX * MSG_KMAX, u, w);        // w = G_s u
+      } else {
+        const float4* f4 = reinterpret_cast<const float4*>(Gs + s * MSG_KMAX);
+#pragma unroll
+        for (int q = 0; q < MSG_KMAX / 4; ++q) {
+          const float4 f = f4[q];
+          w[4 * q + 0] = f.x * u[4 * q + 0]; w[4 * q + 1] = f.y * u[4 * q + 1];
+          w[4 * q + 2] = f.z * u[4 * q + 2]; w[4 * q + 3] = f.w * u[4 * q + 3];
+        }
+      }
+      msg_matvec(Qt, w, y);                                             // y = Q w
+      if (live) {
+#pragma unroll
+        for (int n = 0; n < MSG_NMAX; ++n)
+          if (n < N) og[(int64_t)n * P.out_sn + (int64_t)(P.n_short + s) * D] = y[n];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -335,6 +487,38 @@ int lnb_operator_chain(lnb_stream_t stream, const float* L, const float* X, int 
       L, X, N, E1, D, steps, chebyshev ? 1 : 0, sel, out, out_batch_stride, out_row_stride, out_col0);
   lnb::count_launch();
   return lnb::finish_launch("operator_chain");
+}
+
+int lnb_graph_messages(lnb_stream_t stream, const float* L, const float* X, const float* Q,
+                       const float* filt, int B, int N, int E1, int D, int K, int S, int dense_filter,
+                       int short_steps, const int* block_of_step, int n_short, float* out,
+                       int64_t out_batch_stride, int64_t out_row_stride) {
+  LNB_REQUIRE(L && X && out, "graph_messages: null pointer");
+  LNB_REQUIRE(S == 0 || (Q && filt), "graph_messages: long scales need Q and the filters");
+  LNB_REQUIRE(short_steps == 0 || block_of_step, "graph_messages: block_of_step missing");
+  LNB_REQUIRE(B >= 0 && N >= 1 && E1 >= 1 && D >= 1 && S >= 0 && short_steps >= 0 && n_short >= 0,
+              "graph_messages: bad dims");
+  if (N > MSG_NMAX || (S > 0 && K > MSG_KMAX) || E1 > 16 || S > 8 || short_steps > CHAIN_STEPS_MAX) {
+    lnb::set_err("graph_messages: N=%d K=%d E1=%d S=%d outside the one-launch kernel (N,K <= 32, E1 <= 16, S <= 8)",
+                 N, K, E1, S);
+    return LNB_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return LNB_OK;
+  MsgParams p;
+  p.L = L; p.X = X; p.Q = Q; p.G = dense_filter ? filt : nullptr; p.coeff = dense_filter ? nullptr : filt;
+  p.N = N; p.E1 = E1; p.D = D; p.K = K; p.S = S; p.dense_filter = dense_filter;
+  p.short_steps = short_steps; p.n_short = n_short;
+  for (int s = 0; s < CHAIN_STEPS_MAX; ++s) p.sel.blk[s] = s < short_steps ? (int8_t)block_of_step[s] : (int8_t)-1;
+  p.out = out; p.out_sb = out_batch_stride; p.out_sn = out_row_stride;
+  const int threads = 128;
+  const size_t shm = ((size_t)E1 * MSG_NMAX * MSG_NMAX + 2 * MSG_NMAX * MSG_KMAX +
+                      (S > 0 ? (dense_filter ? (size_t)S * MSG_KMAX * MSG_KMAX : (size_t)S * MSG_KMAX) : 0)) * sizeof(float);
+  if (shm > 48 * 1024)
+    cudaFuncSetAttribute(graph_messages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+  dim3 grid((unsigned)B, (unsigned)lnb::ceil_div(D, threads), S > 0 ? 2u : 1u);
+  graph_messages_kernel<<<grid, threads, shm, (cudaStream_t)stream>>>(p);
+  lnb::count_launch();
+  return lnb::finish_launch("graph_messages");
 }
 
 int lnb_split_tf32(lnb_stream_t stream, const float* x, int64_t n, float* hi, float* lo) {

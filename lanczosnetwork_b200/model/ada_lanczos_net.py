@@ -50,10 +50,17 @@ class AdaLanczosNet(SpectralNetBase):
     """
     self._check_mode()
     dev = self._device()
-    L = self._to(dev, L, torch.float32).contiguous()
-    mask = self._to(dev, mask)
-    label = self._to(dev, label)
-    state = ops.embedding_rows(self._to(dev, node_feat).long(), self.embedding.weight)
+    B, N = node_feat.shape[0], node_feat.shape[1]
+    # drawn exactly like the reference (CPU generator, ada_lanczos_net.py:161); it enters the captured
+    # CUDA graph as an input buffer
+    q1 = torch.randn(B, N, 1) if self.num_scale_long > 0 else None
+    score = self._graph_forward(self._forward_impl, (node_feat, L, mask, q1))
+    return self._finish(score, self._to(dev, label))
+
+  def _forward_impl(self, node_feat, L, mask, q1):
+    dev = L.device
+    L = L.float().contiguous()
+    state = ops.embedding_rows(node_feat.long(), self.embedding.weight)
     B, N = state.shape[0], state.shape[1]
     K, S = self.num_eig_vec, self.num_scale_long
 
@@ -61,7 +68,6 @@ class AdaLanczosNet(SpectralNetBase):
     powers = None
     if S > 0:
       Le = ops.gaussian_laplacian(state, L)
-      q1 = torch.randn(B, N, 1).to(dev)
       # fused kernel, tridiagonalisation only (no QL / Ritz vectors for the learned filter)
       lz = ops.lanczos_ritz(Le, mask, q1, K, want_ritz=False)
       Q = lz['Q']
@@ -84,5 +90,4 @@ class AdaLanczosNet(SpectralNetBase):
       state = graph_conv_layer(state, ctx, G, True, self.short_diffusion_dist, S,
                                self.filter[tt].weight, self.filter[tt].bias, self._wcache,
                                'filter.%d' % tt)
-    score = self._readout(state, mask)
-    return self._finish(score, label)
+    return self._readout(state, mask)

@@ -14,7 +14,7 @@ from ._lib import GemmDesc, SpectralStack
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
     'graph_prepare_sparse', 'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
-    'operator_chain', 'operator_chain_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'lanczos_ritz', 'tridiag_ritz', 'tridiag_powers',
+    'operator_chain', 'operator_chain_supported', 'graph_messages', 'graph_messages_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'lanczos_ritz', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
 
@@ -428,6 +428,36 @@ def operator_chain(L, X, steps, block_of_step, out, out_col0, chebyshev=False):
                                               1 if chebyshev else 0, sel, _ptr(out),
                                               out.stride(0), out.stride(1), int(out_col0)),
                'lnb_operator_chain')
+  return out
+
+
+def graph_messages_supported(N, K, E1, S, max_short):
+  return N <= 32 and (S == 0 or K <= 32) and E1 <= 16 and S <= 8 and max_short <= 64
+
+
+def graph_messages(L, X, Q, filt, dense_filter, short_dist, out):
+  """The whole message matrix [short walk | long scales | edge types] of a general-shape layer in one
+  launch (see lnb_graph_messages).  filt: [B,S,K,K] dense blocks (dense_filter) or [B,K,S] diagonal
+  coefficients, None when there are no long scales; out [B,N,>=C*D] contiguous."""
+  _need_cuda(L, X, Q, filt, out)
+  L, X = _f32c(L), _f32c(X)
+  B, N, D = X.shape
+  E1 = L.shape[3]
+  S = K = 0
+  if filt is not None:
+    filt, Q = _f32c(filt), _f32c(Q)
+    K = Q.shape[2]
+    S = filt.shape[1] if dense_filter else filt.shape[2]
+  steps = sorted(short_dist)
+  max_short = max(steps) if steps else 0
+  sel = [steps.index(s) if s in steps else -1 for s in range(1, max_short + 1)]
+  arr = (ctypes.c_int * max(1, max_short))(*([int(v) for v in sel] or [0]))
+  assert out.dtype == torch.float32 and out.is_contiguous()
+  with torch.cuda.device(X.device):
+    _lib.check(_lib.load().lnb_graph_messages(
+        _stream(X), _ptr(L), _ptr(X), _ptr(Q), _ptr(filt), B, N, E1, D, K, S,
+        1 if dense_filter else 0, max_short, arr, len(steps), _ptr(out), out.stride(0), out.stride(1)),
+               'lnb_graph_messages')
   return out
 
 

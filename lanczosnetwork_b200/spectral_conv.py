@@ -213,6 +213,12 @@ def graph_conv_layer_unfused(state, L, Qv, coeff, dense_filter, short_dist, num_
     msg = torch.zeros((B, N, CD), device=dev, dtype=torch.float32)
   else:
     msg = torch.empty((B, N, CD), device=dev, dtype=torch.float32)
+  if ops.graph_messages_supported(N, Qv.shape[2] if (S and Qv is not None) else 0, E1, S,
+                                  max(short_dist) if n_short else 0):
+    # small graphs: the whole message matrix in ONE launch (operators, filters on chip)
+    ops.graph_messages(L, state, Qv if S else None, coeff if S else None, dense_filter, short_dist, msg)
+    out = dense(msg.reshape(B * N, CD), weight, bias, True, cache, name)
+    return out.reshape(B, N, -1)
   x_str = (N * Din, 0, Din, 1)
   col = 0
   # ---- short diffusion chain: walk <- L0 walk (lanczos_net.py:164-169) --------------------

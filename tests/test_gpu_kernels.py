@@ -485,6 +485,48 @@ def test_fused_lanczos_ritz_edges():
     o.lanczos_ritz(torch.zeros(1, 8, 8), None, torch.ones(1, 8), 4)          # CPU tensors: loud
 
 
+@pytest.mark.parametrize('dense_filter', [True, False])
+def test_graph_messages_one_launch_matches_bmm_composition(dense_filter):
+  """lnb_graph_messages (whole message matrix of a general-shape layer in one launch) against the
+  reference formulation in fp64: [L_0^k X] ++ [Q G_s Q^T X] ++ [L_e X] (model/lanczos_net.py:157-180,
+  ada_lanczos_net.py:321-345), dense symmetric and diagonal filters, ragged feature widths."""
+  rng = np.random.RandomState(3 + int(dense_filter))
+  for B, N, E1, D, K, S, short in ((5, 26, 7, 128, 20, 5, [1, 2, 3]), (3, 32, 2, 70, 32, 8, []),
+                                   (4, 9, 16, 10, 8, 1, [2, 5]), (2, 17, 3, 33, 4, 0, [1])):
+    L = (rng.randn(B, N, N, E1) * (rng.rand(B, N, N, E1) < 0.3) / 3).astype(np.float32)
+    X = rng.randn(B, N, D).astype(np.float32)
+    Q = rng.randn(B, N, K).astype(np.float32) / np.sqrt(N)
+    if dense_filter:
+      G = rng.randn(B, S, K, K).astype(np.float32)
+      filt = ((G + G.transpose(0, 1, 3, 2)) * 0.5).astype(np.float32)
+    else:
+      filt = rng.randn(B, K, S).astype(np.float32)
+    C = len(short) + S + E1
+    out = torch.full((B, N, C * D + 3), 7.0, device=dev())[:, :, :C * D].contiguous()   # any row stride
+    o = ops()
+    o.graph_messages(torch.from_numpy(L).to(dev()), torch.from_numpy(X).to(dev()),
+                     torch.from_numpy(Q).to(dev()) if S else None,
+                     torch.from_numpy(filt).to(dev()) if S else None, dense_filter, short, out)
+    L64, X64, Q64 = L.astype(np.float64), X.astype(np.float64), Q.astype(np.float64)
+    blocks, walk = [], X64
+    for step in range(1, (max(short) if short else 0) + 1):
+      walk = np.einsum('bnm,bmd->bnd', L64[..., 0], walk)
+      if step in short:
+        blocks.append(walk)
+    U = np.einsum('bnk,bnd->bkd', Q64, X64)
+    for s_ in range(S):
+      Wk = np.einsum('bkj,bjd->bkd', filt[:, s_].astype(np.float64), U) if dense_filter else \
+          filt[:, :, s_].astype(np.float64)[:, :, None] * U
+      blocks.append(np.einsum('bnk,bkd->bnd', Q64, Wk))
+    for e in range(E1):
+      blocks.append(np.einsum('bnm,bmd->bnd', L64[..., e], X64))
+    ref = np.concatenate(blocks, axis=2)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-5 * max(1.0, np.abs(ref).max()))
+  with pytest.raises(RuntimeError):
+    ops().graph_messages(torch.zeros(1, 40, 40, 2, device=dev()), torch.zeros(1, 40, 8, device=dev()),
+                         None, None, False, [], torch.zeros(1, 40, 16, device=dev()))
+
+
 def test_tridiag_powers_and_symmetrize():
   g = load_golden('ada_lanczos_layer.npz')
   T = torch.from_numpy(g['qm8_T'])

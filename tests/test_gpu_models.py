@@ -315,10 +315,17 @@ def test_ada_full_qm8_config_vs_oracle():
   ref, aux = orc.ada_lanczos_net_forward(params, spec, batch['node_feat'], batch['L'],
                                          batch['node_mask'], q1[:, :, 0], return_aux=True)
   torch.manual_seed(5)
+  mod.use_cuda_graph = False          # eager: last_lanczos then holds this call's tensors
   with torch.no_grad():
     out = mod(_t(batch['node_feat']).to(dev()), _t(batch['L']).to(dev()),
               mask=_t(batch['node_mask']).to(dev()))
-  lz = mod.last_lanczos
+    lz = mod.last_lanczos
+    torch.manual_seed(5)
+    mod.use_cuda_graph = True         # and the captured graph reproduces it bit for bit
+    replay = [mod(_t(batch['node_feat']).to(dev()), _t(batch['L']).to(dev()),
+                  mask=_t(batch['node_mask']).to(dev())) for _ in range(1)]
+    mod.use_cuda_graph = False
+  assert torch.equal(replay[0], out)
   assert np.array_equal(lz['idx'].cpu().numpy(), aux['idx'].numpy())
   # the learned Laplacian agrees with the oracle's to summation-order rounding ...
   from lanczosnetwork_b200 import ops
