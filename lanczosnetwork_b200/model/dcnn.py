@@ -75,7 +75,8 @@ class DCNN(SpectralNetBase):
     L = L.float().contiguous()
     B, N, _, E1 = L.shape
     state = ops.embedding_rows(node_feat.long(), self.embedding.weight)
-    if ops.operator_chain_supported(N, self.max_dist):
+    if (ops.operator_chain_supported(N, self.max_dist) and
+        not ops.graph_messages_supported(N, 0, E1, 0, self.max_dist)):
       # reference column order: [edge types | diffusion scales] (dcnn.py:98), no weight permutation
       # scales are emitted in ascending step order like the reference loop (dcnn.py:88-92) and the
       # general-shape path, whatever the order of the config list
