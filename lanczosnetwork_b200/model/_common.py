@@ -117,7 +117,27 @@ class SpectralNetBase(nn.Module):
       raise RuntimeError(
           '%s runs on CUDA (sm_100a) only -- move the module with .cuda(); there is no CPU '
           'fallback (the CPU reference is the oracle).' % type(self).__name__)
+    # DataParallel replicas share the master's WeightCache object: bypass it there (see WeightCache)
+    if getattr(self, '_is_replica', False) and hasattr(self, '_wcache') and not self._wcache.bypass:
+      self._wcache = type(self._wcache)()
+      self._wcache.bypass = True
     return dev
+
+  def invalidate_caches(self):
+    """Drop the cached tf32 weight splits and the captured CUDA graphs (call after editing weights
+    through ``p.data`` or any other route that does not bump the parameters' version counters)."""
+    if hasattr(self, '_wcache'):
+      self._wcache.invalidate()
+    for name in ('_graphs', '_graphs_resident', '_resident_seen'):
+      self.__dict__.pop(name, None)
+
+  def graph_stats(self):
+    """Counters of the CUDA-graph cache: captures (each costs a warm-up, two captures and two device
+    synchronisations), replays, and live graphs -- a capture count that keeps growing means the input
+    shapes thrash the cache (pad / bucket the batch shapes)."""
+    st = self.__dict__.setdefault('_graph_stats', {'captures': 0, 'replays': 0})
+    return dict(st, live=len(self.__dict__.get('_graphs', {})),
+                live_resident=len(self.__dict__.get('_graphs_resident', {})))
 
   def _check_mode(self):
     """Returns True when this call has to be differentiable (autograd on, trainable parameters):
@@ -172,7 +192,10 @@ class SpectralNetBase(nn.Module):
         None if t is None else ((t.static_shape(), t.tensor.dtype, 'ragged') if isinstance(t, Ragged)
                                 else (tuple(t.shape), t.dtype)) for t in inputs)
     cache = self.__dict__.setdefault('_graphs', {})
+    stats = self.__dict__.setdefault('_graph_stats', {'captures': 0, 'replays': 0})
     entry = cache.get(key)
+    if entry is not None:
+      cache[key] = cache.pop(key)               # LRU: most recently used last
     sig = self._param_signature()
     cur = torch.cuda.current_stream(dev)
     # Inputs already resident on this device: a graph bound to their addresses needs no copy at
@@ -185,6 +208,8 @@ class SpectralNetBase(nn.Module):
       zc = self.__dict__.setdefault('_graphs_resident', {})
       hit = zc.get(pkey)
       if hit is not None and hit['sig'] == sig:
+        zc[pkey] = zc.pop(pkey)
+        stats['replays'] += 1
         hit['graph'].replay()
         _lib.note_graph_replay(hit['kernels'])
         return hit['out'].clone()
@@ -205,6 +230,7 @@ class SpectralNetBase(nn.Module):
         hit = {'graph': graph, 'out': out, 'sig': sig,
                'kernels': int(_lib.load().lnb_launch_count()) - n0}
         zc[pkey] = hit
+        stats['captures'] += 1
         graph.replay()
         _lib.note_graph_replay(hit['kernels'])
         return out.clone()
@@ -236,7 +262,9 @@ class SpectralNetBase(nn.Module):
                       'free': torch.cuda.Event(), 'ready': torch.cuda.Event()})
         slots[-1]['free'].record(cur)
       entry = {'sig': sig, 'slots': slots, 'next': 0, 'copy': torch.cuda.Stream(device=dev)}
-      if len(cache) >= 8:                      # bound the number of live graphs
+      stats['captures'] += 1
+      cache.pop(key, None)
+      if len(cache) >= 8:                      # bound the number of live graphs: evict the LRU entry
         cache.pop(next(iter(cache)))
       cache[key] = entry
     slot = entry['slots'][entry['next']]
@@ -253,6 +281,7 @@ class SpectralNetBase(nn.Module):
           s_.copy_(t, non_blocking=True)
       slot['ready'].record(copy)
     cur.wait_event(slot['ready'])
+    stats['replays'] += 1
     slot['graph'].replay()
     slot['free'].record(cur)
     _lib.note_graph_replay(slot['kernels'])

@@ -20,37 +20,57 @@ __all__ = ['WeightCache', 'GraphContext', 'dense', 'graph_conv_layer', 'graph_co
 
 
 class WeightCache(object):
-  """tf32 hi/lo splits of nn.Linear weights, refreshed when the parameter changes
-  (keyed on storage pointer + in-place version counter)."""
+  """tf32 hi/lo splits of nn.Linear weights, refreshed when the parameter changes.
+
+  An entry is keyed on (name, device) and tagged with (storage pointer, in-place version) of its
+  source tensors; it also HOLDS those tensors, so an address cannot be recycled for a different weight
+  while its split is cached.  ``nn.DataParallel`` replicas share this object with the master and get
+  freshly broadcast parameter tensors (version 0, recycled addresses) on every forward: for them the
+  cache is bypassed (``bypass=True``) -- a stale hit would silently use old weights.  In-place edits
+  through ``p.data`` do not bump ``_version``; call ``invalidate()`` (``model.invalidate_caches()``)
+  after such an edit.  Mutations are serialised by a lock (one Python thread per device under
+  DataParallel)."""
 
   def __init__(self):
+    import threading
     self._store = {}
+    self._lock = threading.Lock()
+    self.bypass = False
+
+  def _get(self, key, tag, build, sources):
+    if self.bypass:
+      return build()
+    with self._lock:
+      hit = self._store.get(key)
+    if hit is None or hit[0] != tag:
+      hit = (tag,) + tuple(build()) + (tuple(sources),)
+      with self._lock:
+        self._store[key] = hit
+    return hit[1:-1]
+
+  def invalidate(self):
+    with self._lock:
+      self._store.clear()
 
   def split(self, name, weight, pad_to=None):
-    key = (name, weight.device.index)
-    tag = (weight.data_ptr(), weight._version, pad_to)
-    hit = self._store.get(key)
-    if hit is None or hit[0] != tag:
+    def build():
       w = weight.detach()
       if pad_to is not None and pad_to != w.shape[1]:
         w = torch.nn.functional.pad(w, (0, pad_to - w.shape[1]))   # zero input columns
-      hi, lo = ops.split_tf32(w)
-      hit = (tag, hi, lo)
-      self._store[key] = hit
-    return hit[1], hit[2]
+      return ops.split_tf32(w)
+    return self._get((name, weight.device.index), (weight.data_ptr(), weight._version, pad_to), build,
+                     [weight])
 
   def split_stacked(self, name, weights, biases):
     """(hi, lo, bias) of torch.cat(weights, 0) / torch.cat(biases) -- the stacked form the
     grouped dense kernel consumes (one launch for the same MLP stage of every layer)."""
     dev = weights[0].device
-    key = (name, dev.index)
     tag = tuple((w.data_ptr(), w._version) for w in list(weights) + list(biases))
-    hit = self._store.get(key)
-    if hit is None or hit[0] != tag:
+
+    def build():
       hi, lo = ops.split_tf32(torch.cat([w.detach() for w in weights], dim=0))
-      hit = (tag, hi, lo, torch.cat([b.detach() for b in biases], dim=0).contiguous())
-      self._store[key] = hit
-    return hit[1], hit[2], hit[3]
+      return hi, lo, torch.cat([b.detach() for b in biases], dim=0).contiguous()
+    return self._get((name, dev.index), tag, build, list(weights) + list(biases))
 
   def split_mlp_chain(self, name, mlp_layers):
     """Stacked weights of the chain-fused filter MLP kernel: per layer the rows of stage 0
@@ -58,11 +78,9 @@ class WeightCache(object):
     (w_hi, w_lo, bias_all)."""
     ws = [w for layer in mlp_layers for (_, w, _) in layer]
     bs = [b for layer in mlp_layers for (_, _, b) in layer]
-    dev = ws[0].device
-    key = (name, dev.index)
     tag = tuple((t.data_ptr(), t._version) for t in ws + bs)
-    hit = self._store.get(key)
-    if hit is None or hit[0] != tag:
+
+    def build():
       hd = ws[1].shape[0]
       rows = []
       for layer in mlp_layers:
@@ -70,27 +88,23 @@ class WeightCache(object):
         rows.append(torch.nn.functional.pad(w0, (0, hd - w0.shape[1])))
         rows += [layer[1][1].detach(), layer[2][1].detach(), layer[3][1].detach()]
       hi, lo = ops.split_tf32(torch.cat(rows, dim=0).contiguous())
-      hit = (tag, hi, lo, torch.cat([b.detach() for b in bs], dim=0).contiguous())
-      self._store[key] = hit
-    return hit[1], hit[2], hit[3]
+      return hi, lo, torch.cat([b.detach() for b in bs], dim=0).contiguous()
+    return self._get((name, ws[0].device.index), tag, build, ws + bs)
 
   def split_conv_stack(self, name, weights, biases, kw):
     """Stacked convolution weights of consecutive layers for the one-kernel stack: rows
     [l*H, (l+1)*H) = layer l's filter weight, columns zero-padded to kw; returns
     (w_hi, w_lo, bias [L*H])."""
-    dev = weights[0].device
-    key = (name, dev.index)
     tag = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases)) + (kw,)
-    hit = self._store.get(key)
-    if hit is None or hit[0] != tag:
+
+    def build():
       rows = [torch.nn.functional.pad(w.detach(), (0, kw - w.shape[1])) for w in weights]
       hi, lo = ops.split_tf32(torch.cat(rows, dim=0).contiguous())
-      hit = (tag, hi, lo, torch.cat([b.detach() for b in biases], dim=0).contiguous())
-      self._store[key] = hit
-    return hit[1], hit[2], hit[3]
+      return hi, lo, torch.cat([b.detach() for b in biases], dim=0).contiguous()
+    return self._get((name, weights[0].device.index), tag, build, list(weights) + list(biases))
 
   def clear(self):
-    self._store.clear()
+    self.invalidate()
 
 
 def dense(x2d, weight, bias, relu, cache, name):

@@ -567,3 +567,25 @@ def test_forward_sparse_equals_forward_on_the_collated_batch():
   h2d_sparse = sum(v.nbytes for v in spn.values() if isinstance(v, np.ndarray) and v.dtype != np.float64) - spn['label'].nbytes
   h2d_dense = sum(dense[k].nbytes for k in ('node_feat', 'L', 'D', 'V', 'node_mask'))
   assert h2d_sparse * 10 < h2d_dense, (h2d_sparse, h2d_dense)
+
+
+def test_invalidate_caches_after_data_edit_and_graph_stats():
+  """An in-place edit through ``p.data`` bumps no version counter: cached tf32 splits and captured
+  graphs keep the old weights until ``invalidate_caches()``; the graph cache reports its
+  captures / replays so shape thrash is visible."""
+  g = load_golden('lanczosnet_qm8.npz')
+  mod, _ = _build(LanczosNet, configs.qm8_lanczos_net(), 77)
+  args = [_t(g[k]).to(dev()) for k in ('node_feat', 'L', 'D', 'V')]
+  mask = _t(g['node_mask']).to(dev())
+  with torch.no_grad():
+    a = mod(*args, mask=mask)
+    b = mod(*args, mask=mask)
+    c = mod(*args, mask=mask)
+    st = mod.graph_stats()
+    assert st['captures'] == 2 and st['replays'] >= 2 and torch.equal(a, b) and torch.equal(a, c)
+    mod.filter[3].weight.data.mul_(0.5)              # silent edit
+    mod.invalidate_caches()
+    d = mod(*args, mask=mask)
+    assert not torch.equal(d, a)
+    mod.use_cuda_graph = False
+    assert torch.equal(mod(*args, mask=mask), d)
