@@ -21,6 +21,7 @@
 // together with alpha_{i+1}.
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ float2 gsum2(float a, float b, float* red, int& flip,
   a = lnb::warp_sum(a);
   b = lnb::warp_sum(b);
   if (TPG == 32) return make_float2(a, b);
-  float* buf = red + flip * 32;
+  float* buf = red + flip * 64;
   flip ^= 1;
   if (lane == 0) { buf[2 * wg] = a; buf[2 * wg + 1] = b; }
   gbar<TPG>(grp);
@@ -108,8 +109,8 @@ lanczos_ritz_kernel(const FusedParams P) {
   float* al = cs + K4;                          // K4
   float* be = al + K4;                          // K4
   float* iq = be + K4;                          // K4 + 4   1 / (q_j . q_j + EPS)
-  float* red = iq + K4 + 4;                     // 64
-  int* ctl = reinterpret_cast<int*>(red + 64);  // 4  : cursor, overflow
+  float* red = iq + K4 + 4;                     // 128: two flip buffers x (2 values x up to 32 warps)
+  int* ctl = reinterpret_cast<int*>(red + 128); // 4  : cursor, overflow
   uint32_t* rinfo = reinterpret_cast<uint32_t*>(ctl + 4);    // NP : start | len << 16
   float* zs = reinterpret_cast<float*>(rinfo + NP);          // ZW   z of the streamed matvec; aliased by
   float* part = zs;                                          //      the per-warp partial projections [NWG][K4]
@@ -132,7 +133,65 @@ lanczos_ritz_kernel(const FusedParams P) {
 
   // ---- 1. compress: dense rows (HBM, read once) -> CSR pool --------------------------------------
   const float* Ag = P.A + (size_t)g * N * N;
-  {
+  if (NCH >= 4 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(P.A) & 15) == 0) {
+    // 16-byte row loads: lane l holds columns 4l..4l+3 (+128 per chunk) of RB rows; the row's non-zeros
+    // are packed lane-major (deterministic), offsets from one shuffle scan of the per-lane counts
+    constexpr int NC4 = NCH >= 4 ? NCH / 4 : 1;
+    constexpr int RB = NC4 >= 4 ? 2 : 4;
+    int cursor = 0;
+    for (int r0 = wg; r0 < N; r0 += NWG * RB) {
+      float4 v[RB][NC4];
+#pragma unroll
+      for (int b = 0; b < RB; ++b) {
+        const int r = r0 + b * NWG;
+        const float4* row = reinterpret_cast<const float4*>(Ag + (size_t)r * N);
+#pragma unroll
+        for (int k = 0; k < NC4; ++k) {
+          const int c = 4 * lane + 128 * k;
+          v[b][k] = (r < N && c < N) ? __ldcs(row + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < RB; ++b) {
+        const int r = r0 + b * NWG;
+        if (r >= N) break;                       // warp-uniform
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < NC4; ++k)
+          mine += (v[b][k].x != 0.f) + (v[b][k].y != 0.f) + (v[b][k].z != 0.f) + (v[b][k].w != 0.f);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const int cnt = __shfl_sync(kFull, incl, 31);
+        int start;
+        if constexpr (TPG == 32) {
+          start = cursor;
+          cursor += cnt;
+        } else {
+          start = 0;
+          if (lane == 0) start = atomicAdd(&ctl[0], cnt);
+          start = __shfl_sync(kFull, start, 0);
+        }
+        if (start + cnt <= P.cap) {
+          int p = start + incl - mine;
+#pragma unroll
+          for (int k = 0; k < NC4; ++k) {
+            const int c = 4 * lane + 128 * k;
+            const float vv[4] = {v[b][k].x, v[b][k].y, v[b][k].z, v[b][k].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (vv[u] != 0.f) { pval[p] = vv[u]; pcol[p] = (uint16_t)(c + u); ++p; }
+          }
+          if (lane == 0) rinfo[r] = (uint32_t)start | ((uint32_t)cnt << 16);
+        } else if (lane == 0) {
+          ctl[1] = 1;
+        }
+      }
+    }
+  } else {
     // RB rows per warp in flight (RB * NCH independent coalesced loads) before any is consumed
     constexpr int RB = NCH >= 16 ? 2 : (NCH >= 8 ? 4 : 8);
     int cursor = 0;                              // single-warp groups allocate from a register
@@ -465,12 +524,13 @@ lanczos_ritz_kernel(const FusedParams P) {
           const float f = s * e_i;
           const float b = c * e_i;
           const float r2 = fmaf(f, f, gq * gq);
-          if (r2 == 0.f) {
+          if (r2 < 1.0e-36f) {                   // f = g = 0 up to underflow: the reference QL's r == 0 exit
             if (lane == 0) { e[i + 1] = 0.f; d[i + 1] = d_ip1 - p; e[m] = 0.f; }
             underflow = true;
             break;
           }
-          float rinv = rsqrtf(r2);
+          float rinv;                            // MUFU.RSQ without the denormal pre-scaling + one Newton step
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
           rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);
           s = f * rinv;
           c = gq * rinv;
@@ -577,7 +637,7 @@ static bool plan_fused(int N, int K, int tpg, int npt, FusedPlan& pl) {
   const int nwg = tpg / 32;
   int zw = nwg * K4 > NP ? nwg * K4 : NP;
   zw = (zw + 3) & ~3;
-  const int fixed = K * NS + NP + zw + 4 * K4 + 4 + 64 + 4;
+  const int fixed = K * NS + NP + zw + 4 * K4 + 4 + 128 + 4;
   const int ql_words = ((K * (K | 1) + 3) & ~3) + K * K4 + K + 4;
   const int smem_max = 227 * 1024;
   // target capacity: every non-zero of a dense operator if that is cheap, else 12 per row
@@ -653,11 +713,15 @@ int lnb_lanczos_ritz(lnb_stream_t stream, const float* A, const uint8_t* mask, c
     lnb::set_err("lanczos_ritz: N=%d K=%d outside the fused kernel (N <= 1024, K <= 64)", N, K);
     return LNB_ERR_UNSUPPORTED;
   }
+  // (a 1024-thread group was measured at N = 1024: 49.8 ms against 39.7 ms -- 32-warp barriers and
+  // a 64-register cap cost more than the extra parallelism buys)
   static const int cfgs[][2] = {{32, 1}, {32, 2}, {64, 2}, {128, 2}, {256, 2}, {512, 2}};
   FusedPlan pl;
   int sel = -1;
+  const char* force = getenv("LNB_LANCZOS_TPG");     // profiling aid: force a thread-group size
   for (int c = 0; c < 6; ++c) {
     if (cfgs[c][0] * cfgs[c][1] < N) continue;
+    if (force && atoi(force) != cfgs[c][0]) continue;
     if (plan_fused(N, K, cfgs[c][0], cfgs[c][1], pl)) { sel = c; break; }
   }
   if (sel < 0) {
