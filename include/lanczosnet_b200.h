@@ -157,6 +157,21 @@ int lnb_graph_prepare_sparse(lnb_stream_t stream, const int32_t* sizes, const in
                              int32_t* gext, int32_t* tiles, int32_t* rowmap, int32_t* nrows,
                              int64_t* node_ids, uint8_t* mask, float* V, float* L_dense);
 
+/* Packed variant: the whole sparse batch in ONE contiguous, 16-byte aligned device buffer, so a step
+ * costs a single H2D copy of exactly the bytes present (eight ranks issuing seven small copies each
+ * were host-bound).  Layout, all offsets in bytes and multiples of 16, int32 header first:
+ *   hdr[0] = 0x4c4e4231 ("LNB1"), hdr[1] = B, hdr[2] = K, hdr[3] = off(sizes [B] i32),
+ *   hdr[4] = off(node_ptr [B+1] i32), hdr[5] = off(edge_ptr [B+1] i32), hdr[6] = off(D [B,K] f32),
+ *   hdr[7] = off(node_feat [sum n] i32), hdr[8] = off(V_rows [sum n, K] f32),
+ *   hdr[9] = off(edges [sum E][4] u8), hdr[10] = total bytes; hdr[3..6] depend on (B, K) only, so D
+ *   sits at a fixed address of a reused buffer (lnb_ritz_power_table reads it there).
+ * The kernel derives its input pointers from the header on the device. */
+int lnb_graph_prepare_sparse_packed(lnb_stream_t stream, const uint8_t* blob, const double* inv_sqrt_deg,
+                                    int B, int N, int E1, int K, int flags, float* ell_val,
+                                    uint8_t* ell_idx, int32_t* ell_max, int32_t* gext, int32_t* tiles,
+                                    int32_t* rowmap, int32_t* nrows, int64_t* node_ids, uint8_t* mask,
+                                    float* V, float* L_dense);
+
 /* ---------------------------------------------------------------------------------------
  * The whole convolution stack (and optionally the embedding gather in front and the readout
  * behind it) in ONE persistent kernel: every CTA keeps its packed tile's state in shared memory

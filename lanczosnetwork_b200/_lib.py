@@ -73,6 +73,8 @@ SIGNATURES = {
                                   ctypes.c_void_p, ctypes.c_void_p, c_int]),
     'lnb_graph_prepare_sparse': (c_int, [c_stream] + [ctypes.c_void_p] * 7 + [c_int] * 5 +
                                  [ctypes.c_void_p] * 11),
+    'lnb_graph_prepare_sparse_packed': (c_int, [c_stream] + [ctypes.c_void_p] * 2 + [c_int] * 5 +
+                                        [ctypes.c_void_p] * 11),
     'lnb_spectral_conv_fused':
         (c_int, [c_stream, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
                  ctypes.c_void_p, ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int,

@@ -29,6 +29,8 @@ struct SparseBatchParams {
   const uint8_t* edges;        // [edge_ptr[B]][4] = {u, v, bond type, 0}, undirected, listed once
   const float* V_rows;         // [node_ptr[B], K] Ritz vectors, rows of real nodes only
   const double* inv_sqrt_deg;  // [256] deg^-1/2 in fp64 (entry 0 = 0)
+  const uint8_t* blob;         // packed batch (lnb_graph_prepare_sparse_packed): the pointers above are derived
+                               // from its header on the device, so ONE H2D copy ships a whole batch
   int B, N, E1, K, flags;
   float* ell_val; uint8_t* ell_idx; int32_t* ell_max; int32_t* gext;
   int64_t* node_ids; uint8_t* mask; float* V;     // padded [B,N], [B,N], [B,N,K]
@@ -55,7 +57,18 @@ batch_prepare_sparse_kernel(const SparseBatchParams P) {
   __shared__ int s_ke;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int N = P.N, E1 = P.E1, E = E1 - 1, K = P.K;
-  const int nb = min(max(P.sizes[b], 0), N);
+  const int32_t* sizes = P.sizes; const int32_t* node_ptr = P.node_ptr; const int32_t* node_feat = P.node_feat;
+  const int32_t* edge_ptr = P.edge_ptr; const uint8_t* edges = P.edges; const float* V_rows = P.V_rows;
+  if (P.blob) {                                  // header: byte offsets of the segments (see the C header)
+    const int32_t* hdr = reinterpret_cast<const int32_t*>(P.blob);
+    sizes = reinterpret_cast<const int32_t*>(P.blob + hdr[3]);
+    node_ptr = reinterpret_cast<const int32_t*>(P.blob + hdr[4]);
+    edge_ptr = reinterpret_cast<const int32_t*>(P.blob + hdr[5]);
+    node_feat = reinterpret_cast<const int32_t*>(P.blob + hdr[7]);
+    V_rows = reinterpret_cast<const float*>(P.blob + hdr[8]);
+    edges = P.blob + hdr[9];
+  }
+  const int nb = min(max(sizes[b], 0), N);
   uint32_t* rowmask = reinterpret_cast<uint32_t*>(bp_smem);              // [E][NMAX][NW]
   double* scale = reinterpret_cast<double*>(rowmask + (size_t)E * BP_NMAX * BP_NW);   // [E1][NMAX]
   uint8_t* cnt_s = reinterpret_cast<uint8_t*>(scale + (size_t)E1 * BP_NMAX);          // [N*E1]
@@ -65,9 +78,9 @@ batch_prepare_sparse_kernel(const SparseBatchParams P) {
   if (tid == 0) s_ke = 0;
   __syncthreads();
   // ---- adjacency bitmaps from the bond list (idempotent: duplicates do not double count) ----------
-  const int e0 = P.edge_ptr[b], e1 = P.edge_ptr[b + 1];
+  const int e0 = edge_ptr[b], e1 = edge_ptr[b + 1];
   for (int e = e0 + tid; e < e1; e += BP_THREADS) {
-    const uchar4 ed = reinterpret_cast<const uchar4*>(P.edges)[e];
+    const uchar4 ed = reinterpret_cast<const uchar4*>(edges)[e];
     const int u = ed.x, v = ed.y, c = ed.z;
     if (u < nb && v < nb && c < E) {
       atomicOr(&rowmask[(c * BP_NMAX + u) * BP_NW + (v >> 5)], 1u << (v & 31));
@@ -129,16 +142,16 @@ batch_prepare_sparse_kernel(const SparseBatchParams P) {
     if (cnt) atomicMax(&s_max[ch], cnt);
   }
   // ---- padded node ids, mask, Ritz vectors; k_eff ---------------------------------------------------
-  const int r0 = P.node_ptr[b];
+  const int r0 = node_ptr[b];
   for (int n = tid; n < N; n += BP_THREADS) {
-    P.node_ids[(int64_t)b * N + n] = (n < nb) ? (int64_t)P.node_feat[r0 + n] : 0;
+    P.node_ids[(int64_t)b * N + n] = (n < nb) ? (int64_t)node_feat[r0 + n] : 0;
     P.mask[(int64_t)b * N + n] = (n < nb) ? 1 : 0;
   }
   int ke = 0;
   for (int i = tid; i < N * K; i += BP_THREADS) {
     const int n = i / K, k = i - n * K;
     float v = 0.f;
-    if (n < nb) v = P.V_rows[(int64_t)(r0 + n) * K + k];
+    if (n < nb) v = V_rows[(int64_t)(r0 + n) * K + k];
     P.V[(int64_t)b * N * K + i] = v;
     if (v != 0.f) ke = max(ke, k + 1);
   }
@@ -171,6 +184,18 @@ batch_prepare_sparse_kernel(const SparseBatchParams P) {
   }
 }
 
+static int launch_sparse(lnb_stream_t stream, const SparseBatchParams& p, int32_t* tiles, int32_t* rowmap,
+                         int32_t* nrows) {
+  const size_t smem = (size_t)(p.E1 - 1) * BP_NMAX * BP_NW * 4 + (size_t)p.E1 * BP_NMAX * 8 + (size_t)p.N * p.E1 + 16;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(batch_prepare_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  batch_prepare_sparse_kernel<<<p.B, BP_THREADS, smem, s>>>(p);
+  lnb::launch_tile_assign(s, p.gext, p.B, p.K, tiles, rowmap, nrows);
+  lnb::count_launch(2);
+  return lnb::finish_launch("graph_prepare_sparse");
+}
+
 }  // namespace
 
 extern "C" {
@@ -191,18 +216,32 @@ int lnb_graph_prepare_sparse(lnb_stream_t stream, const int32_t* sizes, const in
   LNB_REQUIRE((rowmap == nullptr) == (nrows == nullptr), "graph_prepare_sparse: rowmap and nrows go together");
   SparseBatchParams p;
   p.sizes = sizes; p.node_ptr = node_ptr; p.node_feat = node_feat; p.edge_ptr = edge_ptr;
-  p.edges = edges; p.V_rows = V_rows; p.inv_sqrt_deg = inv_sqrt_deg;
+  p.edges = edges; p.V_rows = V_rows; p.inv_sqrt_deg = inv_sqrt_deg; p.blob = nullptr;
   p.B = B; p.N = N; p.E1 = E1; p.K = K; p.flags = flags;
   p.ell_val = ell_val; p.ell_idx = ell_idx; p.ell_max = ell_max; p.gext = gext;
   p.node_ids = node_ids; p.mask = mask; p.V = V; p.L = L_dense;
-  const size_t smem = (size_t)(E1 - 1) * BP_NMAX * BP_NW * 4 + (size_t)E1 * BP_NMAX * 8 + (size_t)N * E1 + 16;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(batch_prepare_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  batch_prepare_sparse_kernel<<<B, BP_THREADS, smem, s>>>(p);
-  lnb::launch_tile_assign(s, gext, B, K, tiles, rowmap, nrows);
-  lnb::count_launch(2);
-  return lnb::finish_launch("graph_prepare_sparse");
+  return launch_sparse(stream, p, tiles, rowmap, nrows);
+}
+
+int lnb_graph_prepare_sparse_packed(lnb_stream_t stream, const uint8_t* blob, const double* inv_sqrt_deg,
+                                    int B, int N, int E1, int K, int flags, float* ell_val,
+                                    uint8_t* ell_idx, int32_t* ell_max, int32_t* gext, int32_t* tiles,
+                                    int32_t* rowmap, int32_t* nrows, int64_t* node_ids, uint8_t* mask,
+                                    float* V, float* L_dense) {
+  LNB_REQUIRE(B >= 0 && N >= 1 && N <= BP_NMAX && E1 >= 2 && E1 <= BP_EMAX && K >= 1,
+              "graph_prepare_sparse_packed: bad dims B=%d N=%d E1=%d K=%d", B, N, E1, K);
+  if (B == 0) return LNB_OK;
+  LNB_REQUIRE(blob && inv_sqrt_deg && ell_val && ell_idx && ell_max && gext && tiles && node_ids && mask && V,
+              "graph_prepare_sparse_packed: null pointer");
+  LNB_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0, "graph_prepare_sparse_packed: blob must be 16-byte aligned");
+  LNB_REQUIRE((rowmap == nullptr) == (nrows == nullptr), "graph_prepare_sparse_packed: rowmap and nrows go together");
+  SparseBatchParams p;
+  p.sizes = nullptr; p.node_ptr = nullptr; p.node_feat = nullptr; p.edge_ptr = nullptr;
+  p.edges = nullptr; p.V_rows = nullptr; p.inv_sqrt_deg = inv_sqrt_deg; p.blob = blob;
+  p.B = B; p.N = N; p.E1 = E1; p.K = K; p.flags = flags;
+  p.ell_val = ell_val; p.ell_idx = ell_idx; p.ell_max = ell_max; p.gext = gext;
+  p.node_ids = node_ids; p.mask = mask; p.V = V; p.L = L_dense;
+  return launch_sparse(stream, p, tiles, rowmap, nrows);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ import numpy as np
 
 __all__ = [
     'check_dist', 'get_laplacian', 'get_graph_laplacian_eigs', 'prepare_graph',
-    'collate', 'sparse_collate', 'synthetic_molecule', 'synthetic_qm8_samples', 'synthetic_qm8_batch',
+    'collate', 'sparse_collate', 'pack_sparse', 'packed_offsets', 'synthetic_molecule', 'synthetic_qm8_samples', 'synthetic_qm8_batch',
     'synthetic_regression_graphs',
 ]
 
@@ -150,6 +150,48 @@ def sparse_collate(samples, num_eigs):
   if 'label' in samples[0]:
     out['label'] = np.concatenate([np.asarray(s['label'], np.float32).reshape(1, -1)
                                    for s in samples], axis=0)
+  return out
+
+
+PACK_MAGIC = 0x4c4e4231          # "LNB1"
+
+
+def _align16(x):
+  return (int(x) + 15) & ~15
+
+
+def packed_offsets(B, K):
+  """Byte offsets of the fixed-position segments of a packed batch (they depend on B and K only):
+  (off_sizes, off_node_ptr, off_edge_ptr, off_D, off_variable)."""
+  off_sizes = 64
+  off_node_ptr = off_sizes + _align16(4 * B)
+  off_edge_ptr = off_node_ptr + _align16(4 * (B + 1))
+  off_D = off_edge_ptr + _align16(4 * (B + 1))
+  off_var = off_D + _align16(4 * B * K)
+  return off_sizes, off_node_ptr, off_edge_ptr, off_D, off_var
+
+
+def pack_sparse(sp):
+  """A ``sparse_collate`` batch as ONE contiguous uint8 buffer (layout: include/lanczosnet_b200.h,
+  lnb_graph_prepare_sparse_packed): a 16-int header with the byte offsets of the segments, the
+  fixed-size segments (sizes, node_ptr, edge_ptr, D), then node ids, Ritz rows and the bond list.
+  One H2D copy per step ships the whole batch.  Returns dict(blob, B, N, K, num_edgetype[, label])."""
+  B, K = sp['D'].shape
+  off_sizes, off_node_ptr, off_edge_ptr, off_D, off = packed_offsets(B, K)
+  off_nf = off
+  off_v = off_nf + _align16(sp['node_feat'].nbytes)
+  off_e = off_v + _align16(sp['V_rows'].nbytes)
+  total = off_e + _align16(sp['edges'].nbytes)
+  blob = np.zeros(total, np.uint8)
+  hdr = blob[:64].view(np.int32)
+  hdr[:11] = [PACK_MAGIC, B, K, off_sizes, off_node_ptr, off_edge_ptr, off_D, off_nf, off_v, off_e, total]
+  for off_, arr in ((off_sizes, sp['sizes']), (off_node_ptr, sp['node_ptr']), (off_edge_ptr, sp['edge_ptr']),
+                    (off_D, sp['D']), (off_nf, sp['node_feat']), (off_v, sp['V_rows']), (off_e, sp['edges'])):
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    blob[off_:off_ + raw.size] = raw
+  out = {'blob': blob, 'B': int(B), 'N': int(sp['N']), 'K': int(K), 'num_edgetype': int(sp['num_edgetype'])}
+  if 'label' in sp:
+    out['label'] = sp['label']
   return out
 
 

@@ -1,8 +1,10 @@
 """Drop-in for the reference ``model.LanczosNet`` (model/lanczos_net.py:13-199): same
 constructor, parameter names and ``forward(node_feat, L, D, V, label=None, mask=None)``;
 the forward runs in hand-written sm_100a CUDA (no CPU path)."""
+import torch
 import torch.nn as nn
 
+from .. import data as data_mod
 from .. import ops
 from ._common import Ragged, SpectralNetBase
 
@@ -53,12 +55,30 @@ class LanczosNet(SpectralNetBase):
     if self._check_mode():
       raise NotImplementedError('forward_sparse is an inference path; train through forward()')
     dev = self._device()
+    if 'blob' in batch:
+      # packed batch (data.pack_sparse): ONE H2D copy of exactly the bytes present
+      B, N, K = int(batch['B']), int(batch['N']), int(batch['K'])
+      cap = data_mod.packed_offsets(B, K)[4] + 16 * 3 + 4 * B * N + 4 * B * N * K + 4 * B * N * 4
+      blob = batch['blob']
+      score = self._graph_forward(lambda b_: self._forward_packed_impl(B, N, K, b_),
+                                  (Ragged(blob, max(cap, int(blob.shape[0]))),),
+                                  extra_key=('packed', B, N, K))
+      return self._finish(score, self._to(dev, label))
     N, B = int(batch['N']), int(batch['sizes'].shape[0])
     inputs = (batch['sizes'], batch['node_ptr'], Ragged(batch['node_feat'], B * N), batch['edge_ptr'],
               Ragged(batch['edges']), Ragged(batch['V_rows'], B * N), batch['D'])
     score = self._graph_forward(lambda *a: self._forward_sparse_impl(N, *a), inputs,
                                 extra_key=('sparse', N))
     return self._finish(score, self._to(dev, label))
+
+  def _forward_packed_impl(self, B, N, K, blob):
+    E1 = self.num_edgetype + 1
+    dense = not self._sparse_stack_ok(N, E1, K)
+    off_D = data_mod.packed_offsets(B, K)[3]
+    D = blob[off_D:off_D + 4 * B * K].view(torch.float32).reshape(B, K)     # fixed address in the buffer
+    prep, node_ids, mask, V, L = ops.graph_prepare_sparse_packed(
+        blob, B, N, E1, K, binarize=getattr(self, '_binarize_operators', False), want_dense=dense)
+    return self._ritz_conv_stack(None, node_ids, L, D, V, mask, prep=prep, dims_hint=(N, E1))
 
   def _forward_sparse_impl(self, N, sizes, node_ptr, node_feat, edge_ptr, edges, V_rows, D):
     E1 = self.num_edgetype + 1

@@ -13,7 +13,7 @@ from ._lib import GemmDesc, SpectralStack
 
 __all__ = [
     'bgemm', 'split_tf32', 'linear_tf32x3', 'linear_tf32x3_grouped', 'graph_prepare', 'spectral_conv_fused',
-    'graph_prepare_sparse', 'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
+    'graph_prepare_sparse', 'graph_prepare_sparse_packed', 'fused_conv_supported', 'spectral_stack_forward', 'ritz_rowmap', 'ritz_filter_mlp', 'embedding_rows', 'ritz_power_table', 'readout',
     'operator_chain', 'operator_chain_supported', 'graph_messages', 'graph_messages_supported', 'gaussian_laplacian', 'lanczos_tridiag', 'lanczos_ritz', 'tridiag_ritz', 'tridiag_powers',
     'symmetrize_filters', 'segment_sum_forward', 'segment_sum_backward', 'launch_count',
 ]
@@ -244,6 +244,34 @@ def graph_prepare_sparse(sizes, node_ptr, node_feat, edge_ptr, edges, V_rows, N,
         1 if binarize else 0, _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max), _ptr(gext), _ptr(tiles),
         _ptr(rowmap), _ptr(nrows), _ptr(node_ids), _ptr(mask), _ptr(V), _ptr(L)),
                'lnb_graph_prepare_sparse')
+  prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
+  prep.rowmap, prep.nrows = rowmap, nrows
+  return prep, node_ids, mask, V, L
+
+
+def graph_prepare_sparse_packed(blob, B, N, E1, K, binarize=False, want_dense=False):
+  """graph_prepare_sparse on a packed batch (data.pack_sparse: one contiguous uint8 buffer, see
+  lnb_graph_prepare_sparse_packed).  Returns (GraphPrep, node_ids, mask, V, L or None)."""
+  _need_cuda(blob)
+  assert blob.dtype == torch.uint8 and blob.is_contiguous()
+  dev = blob.device
+  ell_val = torch.empty((B, E1, N, N), device=dev, dtype=torch.float32)
+  ell_idx = torch.empty((B, E1, N, N), device=dev, dtype=torch.uint8)
+  ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
+  gext = torch.empty((B, 2), device=dev, dtype=torch.int32)
+  tiles = torch.empty((4 * B + 2,), device=dev, dtype=torch.int32)
+  rowmap = torch.empty((B * K,), device=dev, dtype=torch.int32)
+  nrows = torch.empty((1,), device=dev, dtype=torch.int32)
+  node_ids = torch.empty((B, N), device=dev, dtype=torch.int64)
+  mask = torch.empty((B, N), device=dev, dtype=torch.uint8)
+  V = torch.empty((B, N, K), device=dev, dtype=torch.float32)
+  L = torch.empty((B, N, N, E1), device=dev, dtype=torch.float32) if want_dense else None
+  with torch.cuda.device(dev):
+    _lib.check(_lib.load().lnb_graph_prepare_sparse_packed(
+        _stream(blob), _ptr(blob), _ptr(_inv_sqrt_deg_table(dev)), int(B), int(N), int(E1), int(K),
+        1 if binarize else 0, _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max), _ptr(gext), _ptr(tiles),
+        _ptr(rowmap), _ptr(nrows), _ptr(node_ids), _ptr(mask), _ptr(V), _ptr(L)),
+               'lnb_graph_prepare_sparse_packed')
   prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
   prep.rowmap, prep.nrows = rowmap, nrows
   return prep, node_ids, mask, V, L

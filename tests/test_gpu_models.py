@@ -564,6 +564,21 @@ def test_forward_sparse_equals_forward_on_the_collated_batch():
       assert torch.equal(mod.forward_sparse(res), want)
     score, loss = mod.forward_sparse(host, label=_t(dense['label']).to(dev()))
     assert torch.equal(score, want) and loss.ndim == 0
+    # packed batches: the same records as ONE buffer (one H2D copy per step)
+    pk = data.pack_sparse(spn)
+    pk2 = data.pack_sparse(data.sparse_collate(samples2, 20))
+    hp = dict(pk, blob=_t(pk['blob']).pin_memory())
+    hp2 = dict(pk2, blob=_t(pk2['blob']).pin_memory())
+    for _ in range(2):
+      assert torch.equal(mod.forward_sparse(hp), want)
+      assert torch.equal(mod.forward_sparse(hp2), want2)
+    rp = dict(pk, blob=_t(pk['blob']).to(dev()))
+    for _ in range(3):
+      assert torch.equal(mod.forward_sparse(rp), want)
+    mod.use_cuda_graph = False
+    assert torch.equal(mod.forward_sparse(rp), want)
+    mod.use_cuda_graph = True
+    assert pk['blob'].nbytes < 1.1 * sum(spn[k].nbytes for k in ('sizes', 'node_ptr', 'node_feat', 'edge_ptr', 'edges', 'V_rows', 'D')) + 512
   h2d_sparse = sum(v.nbytes for v in spn.values() if isinstance(v, np.ndarray) and v.dtype != np.float64) - spn['label'].nbytes
   h2d_dense = sum(dense[k].nbytes for k in ('node_feat', 'L', 'D', 'V', 'node_mask'))
   assert h2d_sparse * 10 < h2d_dense, (h2d_sparse, h2d_dense)
