@@ -612,6 +612,7 @@ struct SpectralPolicy {
   __device__ void pre_epilogue(int sub) {
     if ((sub & 1) == 0) return;
     tcg::producers_sync();              // every producer is done reading X
+    if (ptm) ptm->lap(22);              // (profiling) wait for the slowest producer group
     if (S == 0) return;
     const int hv = H / 4;
     for (int task = tid; task < tb->nquads * hv; task += tcg::PRODUCER_THREADS) {

@@ -50,10 +50,16 @@ class ChebyNet(SpectralNetBase):
       node_feat: long B x N (atom ids); L: float B x N x N x (E+1) (channel 0: the rescaled
       simple-graph operator); label: B x P; mask: B x N.  Returns score or (score, loss).
     """
-    self._check_mode()
     dev = self._device()
-    score = self._graph_forward(self._forward_impl, (node_feat, L, mask))
+    if self._check_mode():
+      score = self._train_impl(*[self._to(dev, t) for t in (node_feat, L, mask)])
+    else:
+      score = self._graph_forward(self._forward_impl, (node_feat, L, mask))
     return self._finish(score, self._to(dev, label))
+
+  def _train_impl(self, node_feat, L, mask):
+    from ..train import cheby_train
+    return cheby_train(self, node_feat, L, mask)
 
   def _forward_impl(self, node_feat, L, mask):
     L = L.float().contiguous()

@@ -54,10 +54,16 @@ class DCNN(SpectralNetBase):
       node_feat: long B x N (atom ids); L: float B x N x N x (E+1); label: B x P;
       mask: B x N (uint8 / bool / float).  Returns score (B x P) or (score, loss).
     """
-    self._check_mode()
     dev = self._device()
-    score = self._graph_forward(self._forward_impl, (node_feat, L, mask))
+    if self._check_mode():
+      score = self._train_impl(*[self._to(dev, t) for t in (node_feat, L, mask)])
+    else:
+      score = self._graph_forward(self._forward_impl, (node_feat, L, mask))
     return self._finish(score, self._to(dev, label))
+
+  def _train_impl(self, node_feat, L, mask):
+    from ..train import dcnn_train
+    return dcnn_train(self, node_feat, L, mask)
 
   def _layer_weight(self, t):
     """The reference concatenates edge types first and diffusion scales last (dcnn.py:98); the

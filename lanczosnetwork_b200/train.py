@@ -24,7 +24,8 @@ import torch
 
 from . import ops
 
-__all__ = ['dense', 'operator_messages', 'spectral_messages', 'embedding', 'ritz_stack_train']
+__all__ = ['dense', 'operator_messages', 'spectral_messages', 'embedding', 'ritz_stack_train',
+           'dcnn_train', 'cheby_train', 'gated_readout']
 
 
 def _pad_cols(x, mult=4):
@@ -210,7 +211,13 @@ def ritz_stack_train(model, state, node_ids, L, D, V, mask):
     state = dense(msg.reshape(B * N, -1), lin.weight, lin.bias, True).reshape(B, N, -1)
     if model.training and model.dropout > 0.0:
       state = torch.nn.functional.dropout(state, model.dropout, True)
-  # gated readout (lanczos_net.py:185-194): pointwise glue on the autograd tape
+  return gated_readout(model, state, mask)
+
+
+def gated_readout(model, state, mask):
+  """Gated masked-mean readout shared by all models (lanczos_net.py:185-194): the two Linears in the
+  library's dense kernel, the pointwise gate / mean on the autograd tape."""
+  B, N = state.shape[0], state.shape[1]
   head, att = model.filter[model.num_layer], model.att_func[0]
   flat = state.reshape(B * N, -1)
   y = dense(flat, head.weight, head.bias, False).reshape(B, N, -1)
@@ -220,3 +227,46 @@ def ritz_stack_train(model, state, node_ids, L, D, V, mask):
     return y.mean(dim=1)
   m = (mask != 0).to(y.dtype).unsqueeze(2)
   return (y * m).sum(dim=1) / m.sum(dim=1)
+
+
+def dcnn_train(model, node_ids, L, mask):
+  """Differentiable DCNN (model/dcnn.py:64-124): per layer the edge-type products, then the walk
+  L_0^k X for k in diffusion_dist, concatenated EDGES FIRST (:98), Linear + ReLU."""
+  L = L.float().contiguous()
+  state = embedding(node_ids, model.embedding.weight)
+  B, N = state.shape[0], state.shape[1]
+  dist = set(model.diffusion_dist)
+  for t in range(model.num_layer):
+    msgs = [operator_messages(L, state)]
+    walk = state
+    for step in range(1, model.max_dist + 1):
+      walk = operator_messages(L, walk, 0, 1)
+      if step in dist:
+        msgs.append(walk)
+    lin = model.filter[t]
+    state = dense(torch.cat(msgs, dim=2).reshape(B * N, -1), lin.weight, lin.bias, True).reshape(B, N, -1)
+    if model.training and model.dropout > 0.0:
+      state = torch.nn.functional.dropout(state, model.dropout, True)
+  return gated_readout(model, state, mask)
+
+
+def cheby_train(model, node_ids, L, mask):
+  """Differentiable ChebyNet (model/cheby_net.py:64-124): s_0 = L_0 X, s_k = 2 L_0 s_{k-1} - s_{k-2}
+  with s_{-1} = X (the reference's index -1 is its LAST slot, :88-93), bond-type products for e >= 1,
+  cat(edges + [s_0 .. s_{order-1}] + [X]) (:99), Linear + ReLU."""
+  L = L.float().contiguous()
+  state = embedding(node_ids, model.embedding.weight)
+  B, N, E1 = state.shape[0], state.shape[1], L.shape[3]
+  order = model.polynomial_order
+  for t in range(model.num_layer):
+    scale = [None] * (order + 1)
+    scale[-1] = state
+    scale[0] = operator_messages(L, state, 0, 1)
+    for kk in range(1, order):
+      scale[kk] = 2.0 * operator_messages(L, scale[kk - 1], 0, 1) - scale[kk - 2]
+    msgs = ([operator_messages(L, state, 1, E1 - 1)] if E1 > 1 else []) + scale
+    lin = model.filter[t]
+    state = dense(torch.cat(msgs, dim=2).reshape(B * N, -1), lin.weight, lin.bias, True).reshape(B, N, -1)
+    if model.training and model.dropout > 0.0:
+      state = torch.nn.functional.dropout(state, model.dropout, True)
+  return gated_readout(model, state, mask)

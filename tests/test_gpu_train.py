@@ -7,7 +7,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs, data
-from lanczosnetwork_b200.model import GCN, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import ChebyNet, DCNN, GCN, LanczosNet, LanczosNetGeneral
 from oracle import lanczos_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -144,3 +144,26 @@ def test_reference_training_loop_body_runs_and_learns():
     after = model(t['node_feat'], t['L'], t['D'], t['V'], label=t['label'], mask=t['node_mask'])[1]
     again = model(t['node_feat'], t['L'], t['D'], t['V'], label=t['label'], mask=t['node_mask'])[1]
   assert float(after) < losses[0] and float(after) == float(again)
+
+
+def test_dcnn_and_cheby_gradients_match_oracle(monkeypatch):
+  """The operator-chain models train through the same adjoint kernels (L_0^T g chains)."""
+  g = load_golden('lanczosnet_qm8.npz')
+  label = _t(g['label'])
+  dc_cfg = configs.qm8_dcnn(num_layer=2, hidden_dim=[32, 32], diffusion_dist=[2, 5])
+  ch_cfg = configs.qm8_cheby_net(num_layer=2, hidden_dim=[32, 32], polynomial_order=4)
+  cases = (
+      (DCNN, dc_cfg, lambda p: orc.dcnn_forward(p, dc_cfg.model.diffusion_dist, 6, 2, g['node_feat'], g['L'],
+                                                g['node_mask'], dtype=torch.float64)),
+      (ChebyNet, ch_cfg, lambda p: orc.cheby_net_forward(p, 4, 6, 2, g['node_feat'], g['L'], g['node_mask'],
+                                                         dtype=torch.float64)))
+  for cls, cfg, fwd in cases:
+    mod = cls(cfg)
+    params = deterministic_state_dict(mod, 3)
+    mod.load_state_dict(params)
+    mod = mod.to(dev()).train()
+    _, grads_ref = _oracle_grads(lambda p: torch.nn.functional.mse_loss(fwd(p), label.double()), params, monkeypatch)
+    _, loss = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), label=label.to(dev()),
+                  mask=_t(g['node_mask']).to(dev()))
+    loss.backward()
+    _compare(mod, grads_ref)

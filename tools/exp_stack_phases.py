@@ -50,7 +50,7 @@ names = ['stage issue', 'stage wait', 'U', 'k-loop s0', 'pre_epi', 'acc wait s0'
 print('stack kernel %.1f us (with timers); clock64 totals per CTA (cycles)' % times[-1])
 for i in range(11):
   print('  %-12s cta0 %8d cta1 %8d cta100 %8d  mean %8d  max %8d' % (names[i], p[0, i], p[1, i], p[100, i], p[:, i].mean(), p[:, i].max()))
-for i, nm in [(16, 'stage: tables'), (17, 'stage: X/Q issue'), (18, 'stage: ELL lines'), (19, 'readout: wait'), (20, 'readout: W stage'), (21, 'readout: dots')]:
+for i, nm in [(22, 'pre_epi: wait for producers'), (16, 'stage: tables'), (17, 'stage: X/Q issue'), (18, 'stage: ELL lines'), (19, 'readout: wait'), (20, 'readout: W stage'), (21, 'readout: dots')]:
   print('  %-18s mean %8d  max %8d' % (nm, p[:, i].mean(), p[:, i].max()))
 print('  sum cta0 %d, mean %d, max %d' % (p[0, :11].sum(), p[:, :11].sum(1).mean(), p[:, :11].sum(1).max()))
 act = p[:, 12] > 0
