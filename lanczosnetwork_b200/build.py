@@ -53,12 +53,32 @@ def build(force=False, verbose=False):
     with open(STAMP) as fh:
       if fh.read().strip() == digest:
         return LIB_PATH
-  cmd = [nvcc_path()] + NVCC_FLAGS + ['-o', LIB_PATH] + sources()
-  proc = subprocess.run(cmd, capture_output=True, text=True)
-  log = proc.stdout + proc.stderr
+  # one nvcc per translation unit, in parallel, then one link (a single nvcc invocation compiles its
+  # inputs one after the other: 70 s for the 11 files; the slowest single file takes ~20 s)
+  from concurrent.futures import ThreadPoolExecutor
+  objdir = os.path.join(HERE, 'build')
+  os.makedirs(objdir, exist_ok=True)
+  compile_flags = [f for f in NVCC_FLAGS if f != '-shared']
+
+  def compile_one(src):
+    obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+    cmd = [nvcc_path()] + compile_flags + ['-c', '-o', obj, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    return obj, ' '.join(cmd) + '\n' + proc.stdout + proc.stderr, proc.returncode
+
+  with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+    results = list(pool.map(compile_one, sources()))
+  log = ''.join(r[1] for r in results)
+  rc = max(r[2] for r in results)
+  if rc == 0:
+    link = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC',
+            '-o', LIB_PATH] + [r[0] for r in results]
+    proc = subprocess.run(link, capture_output=True, text=True)
+    log += ' '.join(link) + '\n' + proc.stdout + proc.stderr
+    rc = proc.returncode
   with open(os.path.join(HERE, 'build.log'), 'w') as fh:
-    fh.write(' '.join(cmd) + '\n' + log)
-  if proc.returncode != 0:
+    fh.write(log)
+  if rc != 0:
     raise RuntimeError('nvcc failed:\n' + log[-6000:])
   if verbose:
     print(log)
