@@ -1,6 +1,8 @@
-// Batched Lanczos tridiagonalisation, tridiagonal QL eigensolve (Ritz pairs) and tridiagonal
-// powers.  One warp per graph for N <= 32 (operator rows live in registers, reductions are
-// warp shuffles, the Krylov basis lives in shared memory); one CTA per graph for larger N.
+// Batched Lanczos tridiagonalisation for DENSE operators (two-launch path: lnb_lanczos_tridiag, then
+// lnb_tridiag_ritz), tridiagonal QL eigensolve (Ritz pairs) and tridiagonal powers.  One CTA per
+// graph: operator resident in registers / shared memory for 32 < N <= 256, streamed above; N <= 32
+// goes through the fused kernel of lanczos_fused.cu (the product path for every size is
+// lnb_lanczos_ritz: operator packed on chip, one launch).
 //
 // Reference behaviour reproduced (model/ada_lanczos_net.py:139-247), including its masking
 // rules: cumulative validity from beta >= 1e-4 (:193-199), idx = min(#valid, #real nodes)
@@ -14,108 +16,6 @@ namespace {
 
 constexpr float kEps = 1.1920928955078125e-07f;  // np.finfo(np.float32).eps (ada_lanczos_net.py:8)
 constexpr float kBetaLowerBound = 1.0e-4f;       // ada_lanczos_net.py:169
-
-// ------------------------------------------------------------------------------------------
-// Warp-per-graph kernel, N <= 32.
-//   lane n owns node n: row n of A in 32 registers, z_n / q_n scalars.
-//   Krylov basis Qs[j][n] in shared memory (conflict-free: lane-contiguous).
-//   Modified Gram-Schmidt in the reference's order (j ascending, two passes).
-// ------------------------------------------------------------------------------------------
-constexpr int WARPS_PER_CTA = 4;
-
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA)
-lanczos_warp_kernel(const float* __restrict__ A, const uint8_t* __restrict__ mask,
-                    const float* __restrict__ q1, int B, int N, int K,
-                    float* __restrict__ T, float* __restrict__ Q, float* __restrict__ alpha_out,
-                    float* __restrict__ beta_out, int32_t* __restrict__ idx_out) {
-  extern __shared__ float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * WARPS_PER_CTA + warp;
-  const int iters = N < K ? N : K;
-  // per-warp shared: basis (iters+1) x 32, alpha K, beta K, qq (iters+1)
-  const int per_warp = (iters + 1) * 32 + 2 * K + (iters + 1);
-  float* Qs = smem + warp * per_warp;
-  float* al = Qs + (iters + 1) * 32;
-  float* be = al + K;
-  float* qq = be + K;
-  if (g >= B) return;
-
-  const float* Ag = A + (int64_t)g * N * N;
-  float a[32];
-#pragma unroll
-  for (int m = 0; m < 32; ++m) a[m] = (lane < N && m < N) ? Ag[(int64_t)lane * N + m] : 0.f;
-
-  float mk = 1.f;
-  int nreal = N;
-  if (mask) {
-    mk = (lane < N && mask[(int64_t)g * N + lane]) ? 1.f : 0.f;
-    nreal = __popc(__ballot_sync(0xffffffffu, mk != 0.f));
-  }
-  float q = (lane < N) ? q1[(int64_t)g * N + lane] * mk : 0.f;
-  float nrm = sqrtf(lnb::warp_sum(q * q));
-  q = q / nrm;
-  if (lane >= N) q = 0.f;
-  Qs[lane] = q;
-  float qq0 = lnb::warp_sum(q * q);
-  if (lane == 0) qq[0] = qq0;
-  __syncwarp();
-
-  float q_prev = 0.f, beta_prev = 0.f, valid = 1.f;
-  int count = 0;
-  for (int i = 0; i < iters; ++i) {
-    // z = A q_i
-    float z = 0.f;
-#pragma unroll
-    for (int m = 0; m < 32; ++m) z = fmaf(a[m], __shfl_sync(0xffffffffu, q, m), z);
-    float alpha = lnb::warp_sum(q * z);
-    z = z - alpha * q - beta_prev * q_prev;
-    if (i > 0) {
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < i; ++j) {
-          float qj = Qs[j * 32 + lane];
-          float c = lnb::warp_sum(z * qj) / (qq[j] + kEps);
-          z = z - c * qj;
-        }
-      }
-    }
-    float beta = sqrtf(lnb::warp_sum(z * z));
-    valid = (beta >= kBetaLowerBound) ? valid : 0.f;
-    count += (valid != 0.f) ? 1 : 0;
-    float qn = (z * valid) / (beta + kEps);
-    if (lane == 0) { al[i] = alpha; be[i] = beta; }
-    Qs[(i + 1) * 32 + lane] = qn;
-    float qqn = lnb::warp_sum(qn * qn);
-    if (lane == 0) qq[i + 1] = qqn;
-    __syncwarp();
-    q_prev = q; q = qn; beta_prev = beta;
-  }
-
-  const int idx = count < nreal ? count : nreal;
-  if (lane == 0) idx_out[g] = idx;
-  // alpha, beta, dense T
-  for (int k = lane; k < K; k += 32) {
-    float av = (k < iters && k < idx) ? al[k] : 0.f;
-    float bv = (k < iters - 1 && k < idx) ? be[k] : 0.f;
-    alpha_out[(int64_t)g * K + k] = av;
-    beta_out[(int64_t)g * K + k] = bv;
-  }
-  float* Tg = T + (int64_t)g * K * K;
-  for (int e = lane; e < K * K; e += 32) {
-    int r = e / K, c = e % K;
-    float v = 0.f;
-    if (r == c) v = (r < iters && r < idx) ? al[r] : 0.f;
-    else if (c == r + 1) v = (r < iters - 1 && r < idx) ? be[r] : 0.f;
-    else if (r == c + 1) v = (c < iters - 1 && c < idx) ? be[c] : 0.f;
-    Tg[e] = v;
-  }
-  float* Qg = Q + (int64_t)g * N * K;
-  for (int e = lane; e < N * K; e += 32) {
-    int n = e / K, k = e % K;
-    float v = 0.f;
-    if (k < iters && k < idx && n < idx) v = Qs[k * 32 + n];
-    Qg[e] = v;
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // CTA-per-graph kernel, any N.  Krylov basis in shared memory; the operator is staged in
@@ -684,15 +584,10 @@ int lnb_lanczos_tridiag(lnb_stream_t stream, const float* A, const uint8_t* mask
   if (B == 0) return LNB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int iters = N < K ? N : K;
-  if (N <= 32) {
-    size_t per_warp = ((size_t)(iters + 1) * 32 + 2 * K + (iters + 1)) * sizeof(float);
-    size_t shm = per_warp * WARPS_PER_CTA;
-    LNB_REQUIRE(shm <= 227 * 1024, "lanczos_tridiag: K=%d too large for the warp kernel", K);
-    if (shm > 48 * 1024)
-      cudaFuncSetAttribute(lanczos_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)shm);
-    lanczos_warp_kernel<<<lnb::ceil_div(B, WARPS_PER_CTA), 32 * WARPS_PER_CTA, shm, s>>>(
-        A, mask, q1, B, N, K, T, Q, alpha, beta, idx);
+  if (N <= 32 && K <= 64) {
+    // small graphs: the fused kernel without its QL stage (operator rows loaded coalesced and packed
+    // on chip -- a dense 32 x 32 operator fits its pool --, butterfly projections)
+    return lnb_lanczos_ritz(stream, A, mask, q1, B, N, K, 0, T, Q, alpha, beta, idx, nullptr, nullptr, nullptr);
   } else if (N <= 64 && launch_resident<64, 128>(s, A, mask, q1, B, N, K, T, Q, alpha, beta, idx)) {
   } else if (N <= 128 && launch_resident<128, 512>(s, A, mask, q1, B, N, K, T, Q, alpha, beta, idx)) {
   } else if (N <= 256 && launch_resident<256, 512>(s, A, mask, q1, B, N, K, T, Q, alpha, beta, idx)) {

@@ -640,10 +640,11 @@ static bool plan_fused(int N, int K, int tpg, int npt, FusedPlan& pl) {
   const int fixed = K * NS + NP + zw + 4 * K4 + 4 + 128 + 4;
   const int ql_words = ((K * (K | 1) + 3) & ~3) + K * K4 + K + 4;
   const int smem_max = 227 * 1024;
-  // target capacity: every non-zero of a dense operator if that is cheap, else 12 per row
+  // target capacity: every entry of a dense operator while that is cheap (N <= 48: <= 13.5 KB),
+  // else 12 non-zeros per row
   long want = (long)N * N;
   const long sparse_want = (long)N * 12;
-  if (want > sparse_want) want = sparse_want;
+  if (N > 48 && want > sparse_want) want = sparse_want;
   if (want > 65535) want = 65535;
   auto pool_words_for = [&](long cap) { long w = (cap * 6 + 3) / 4; return (int)(w > ql_words ? w : ql_words); };
   int pool_words = pool_words_for(want);
