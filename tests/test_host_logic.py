@@ -170,3 +170,38 @@ def test_sharded_predict_world_size_2_gloo(tmp_path):
   proc = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
   assert proc.returncode == 0, proc.stdout + proc.stderr
   assert proc.stdout.count('ok') == 2
+
+
+def test_sparse_collate_and_pack_describe_the_same_batch():
+  """Host side of the GPU-side batch construction: the bond lists of ``sparse_collate``
+  rebuild the reference's padded operators bit for bit through the host mirror, sizes / pointers /
+  Ritz rows agree with ``collate``, and ``pack_sparse`` lays the same arrays out behind its header."""
+  samples = data.synthetic_qm8_samples(40, seed=9)
+  dense = data.collate(samples, 20)
+  sp = data.sparse_collate(samples, 20)
+  B, N = dense['node_feat'].shape
+  assert sp['N'] == N and sp['num_edgetype'] == 6
+  assert np.array_equal(sp['sizes'], dense['node_mask'].sum(axis=1).astype(np.int32))
+  assert np.array_equal(sp['node_ptr'][1:], np.cumsum(sp['sizes'])) and sp['node_ptr'][0] == 0
+  assert np.array_equal(sp['D'], dense['D'])
+  for b in range(B):
+    n, r0 = int(sp['sizes'][b]), int(sp['node_ptr'][b])
+    assert np.array_equal(sp['node_feat'][r0:r0 + n], dense['node_feat'][b, :n])
+    assert np.array_equal(sp['V_rows'][r0:r0 + n], dense['V'][b, :n])
+    adjs = np.zeros((n, n, 6))
+    for u, v, c, pad in sp['edges'][sp['edge_ptr'][b]:sp['edge_ptr'][b + 1]]:
+      assert u <= v and pad == 0
+      adjs[u, v, c] = adjs[v, u, c] = 1.0
+    assert np.array_equal(data.get_laplacian(adjs.sum(axis=2)).astype(np.float32), dense['L'][b, :n, :n, 0])
+    for c in range(6):
+      assert np.array_equal(data.get_laplacian(adjs[:, :, c]).astype(np.float32), dense['L'][b, :n, :n, 1 + c])
+  pk = data.pack_sparse(sp)
+  hdr = pk['blob'][:64].view(np.int32)
+  assert hdr[0] == data.PACK_MAGIC and hdr[1] == B and hdr[2] == 20 and hdr[10] == pk['blob'].size
+  assert tuple(hdr[3:7]) == data.packed_offsets(B, 20)[:4] and all(int(o) % 16 == 0 for o in hdr[3:11])
+  for off, key in ((3, 'sizes'), (4, 'node_ptr'), (5, 'edge_ptr'), (6, 'D'), (7, 'node_feat'), (8, 'V_rows'), (9, 'edges')):
+    raw = np.ascontiguousarray(sp[key]).view(np.uint8).reshape(-1)
+    assert np.array_equal(pk['blob'][hdr[off]:hdr[off] + raw.size], raw), key
+  # the fp64 table the device kernel multiplies with is numpy's own deg ** -0.5
+  deg = np.arange(1, 12, dtype=np.float64)
+  assert np.array_equal(np.power(deg, -0.5), deg ** -0.5)
