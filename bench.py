@@ -376,13 +376,10 @@ def main():
   kept = []                  # this rank's per-step predictions, resident until the single gather
 
   def gather_once():
-    """ONE collective for the whole timed region: [steps*B, P] per rank -> [world*steps*B, P]."""
+    """ONE collective for the whole timed region: [steps*B, P] per rank -> [world, steps*B, P]."""
     if world == 1 or not kept:
       return None
-    local_pred = torch.cat(kept, dim=0)
-    full = torch.empty((world * local_pred.shape[0], P), device=dev)
-    dist.all_gather_into_tensor(full, local_pred)
-    return full
+    return sharded.gather_once(kept, world)
 
   def step_resident(i):
     b = resident[i % NUM_BATCHES]

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ['init_from_env', 'shard_indices', 'shard_batch', 'gather_predictions',
-           'sharded_predict']
+           'sharded_predict', 'gather_once']
 
 
 def init_from_env(backend=None):
@@ -67,3 +67,16 @@ def sharded_predict(predict_fn, batch, rank, world):
   local, _ = shard_batch(batch, rank, world)
   pred = predict_fn(local)
   return gather_predictions(pred, n, rank, world)
+
+
+def gather_once(local_preds, world):
+  """ONE collective for a whole shard: the per-step predictions a rank kept on its device
+  ([n_step, P] each, the same shapes on every rank) are concatenated and all-gathered in a single
+  ``all_gather_into_tensor``.  Returns [world, steps * n_step, P] (rank-major), or the local stack for
+  a single process."""
+  local = torch.cat(list(local_preds), dim=0)
+  if world == 1:
+    return local.unsqueeze(0)
+  out = local.new_empty((world * local.shape[0], local.shape[1]))
+  dist.all_gather_into_tensor(out, local)
+  return out.reshape(world, local.shape[0], local.shape[1])

@@ -156,6 +156,13 @@ ref = full['x'] * 2.0 + 1.0
 assert torch.equal(pred, ref), (rank, pred.shape)
 lo, hi, per = sharded.shard_indices(n, rank, world)
 assert per == 19 and (lo, hi) == ((0, 19) if rank == 0 else (19, 37))
+# one gather for a whole shard of per-step predictions (what bench.py times)
+steps = [torch.full((4, 3), float(10 * rank + i)) for i in range(5)]
+allp = sharded.gather_once(steps, world)
+assert allp.shape == (world, 20, 3)
+for r in range(world):
+  for i in range(5):
+    assert torch.equal(allp[r, 4 * i:4 * i + 4], torch.full((4, 3), float(10 * r + i)))
 dist.barrier()
 dist.destroy_process_group()
 print('rank', rank, 'ok')
