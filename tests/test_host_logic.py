@@ -138,6 +138,12 @@ def test_dropin_rebinds_names_in_a_runner_namespace():
   from lanczosnetwork_b200.model import GCN, LanczosNet
   assert fake_runner.LanczosNet is LanczosNet and fake_runner.GCN is GCN
   assert fake_runner.MPNN == 'untouched'
+  # a training run (no -t): classes without a differentiable path keep the reference's class
+  train_ns = types.ModuleType('fake_train_runner')
+  train_ns.LanczosNet, train_ns.AdaLanczosNet, train_ns.DCNN = 'ref', 'ref', 'ref'
+  dropin.patch_namespace(train_ns, training=True)
+  from lanczosnetwork_b200.model import DCNN
+  assert train_ns.LanczosNet is LanczosNet and train_ns.DCNN is DCNN and train_ns.AdaLanczosNet == 'ref'
   dropin.register_native_op()
   import importlib
   sr = importlib.import_module('operators._ext.segment_reduction')
