@@ -163,9 +163,17 @@ int lnb_graph_prepare_sparse(lnb_stream_t stream, const int32_t* sizes, const in
  *   hdr[0] = 0x4c4e4231 ("LNB1"), hdr[1] = B, hdr[2] = K, hdr[3] = off(sizes [B] i32),
  *   hdr[4] = off(node_ptr [B+1] i32), hdr[5] = off(edge_ptr [B+1] i32), hdr[6] = off(D [B,K] f32),
  *   hdr[7] = off(node_feat [sum n] i32), hdr[8] = off(V_rows [sum n, K] f32),
- *   hdr[9] = off(edges [sum E][4] u8), hdr[10] = total bytes; hdr[3..6] depend on (B, K) only, so D
- *   sits at a fixed address of a reused buffer (lnb_ritz_power_table reads it there).
- * The kernel derives its input pointers from the header on the device. */
+ *   hdr[9] = off(edges [sum E][4] u8), hdr[10] = total bytes, hdr[11] = off(tiles [B+2] i32),
+ *   hdr[12] = off(krow_ptr [B+1] i32) (both 0 when absent); hdr[3..6], hdr[11], hdr[12] depend on (B, K)
+ *   only, so D and the tile table sit at fixed addresses of a reused buffer (lnb_ritz_power_table and
+ *   lnb_spectral_stack_forward read them there).
+ * The kernel derives its input pointers from the header on the device.  flags bit 1
+ * (LNB_PACKED_HOST_TILES): the host knows every graph's extents, so it ships the packed-tile table
+ * (same next-fit rule as lnb_graph_prepare: consecutive graphs, sum n <= 128, sum ceil4(k_eff) <= 128,
+ * <= 32 graphs) and the prefix sums krow_ptr of k_eff; the kernel expands the Ritz row list itself and
+ * NO tile-assignment launch follows (the `tiles` argument is then unused: pass the blob's segment to
+ * the stack kernel). */
+#define LNB_PACKED_HOST_TILES 2
 int lnb_graph_prepare_sparse_packed(lnb_stream_t stream, const uint8_t* blob, const double* inv_sqrt_deg,
                                     int B, int N, int E1, int K, int flags, float* ell_val,
                                     uint8_t* ell_idx, int32_t* ell_max, int32_t* gext, int32_t* tiles,

@@ -35,6 +35,7 @@ struct SparseBatchParams {
   float* ell_val; uint8_t* ell_idx; int32_t* ell_max; int32_t* gext;
   int64_t* node_ids; uint8_t* mask; float* V;     // padded [B,N], [B,N], [B,N,K]
   float* L;                                        // optional dense [B,N,N,E1]
+  int32_t* rowmap; int32_t* nrows;                 // written here when the packed batch carries krow_ptr
 };
 
 // multiplicity of entry (i, j) of channel ch (0 = simple graph = sum over bond types)
@@ -67,6 +68,14 @@ batch_prepare_sparse_kernel(const SparseBatchParams P) {
     node_feat = reinterpret_cast<const int32_t*>(P.blob + hdr[7]);
     V_rows = reinterpret_cast<const float*>(P.blob + hdr[8]);
     edges = P.blob + hdr[9];
+    if ((P.flags & 2) && hdr[12] > 0 && P.rowmap) {
+      // compact Ritz row list {b*K + k : k < k_eff(b)} from the host's prefix sums (the host also ships
+      // the tile table, so no tile-assignment launch follows)
+      const int32_t* krow = reinterpret_cast<const int32_t*>(P.blob + hdr[12]);
+      const int k0 = krow[b], k1 = krow[b + 1];
+      for (int i = threadIdx.x; i < k1 - k0; i += BP_THREADS) P.rowmap[k0 + i] = b * P.K + i;
+      if (b == 0 && threadIdx.x == 0) P.nrows[0] = krow[P.B];
+    }
   }
   const int nb = min(max(sizes[b], 0), N);
   uint32_t* rowmask = reinterpret_cast<uint32_t*>(bp_smem);              // [E][NMAX][NW]
@@ -184,15 +193,20 @@ batch_prepare_sparse_kernel(const SparseBatchParams P) {
   }
 }
 
-static int launch_sparse(lnb_stream_t stream, const SparseBatchParams& p, int32_t* tiles, int32_t* rowmap,
+static int launch_sparse(lnb_stream_t stream, SparseBatchParams p, int32_t* tiles, int32_t* rowmap,
                          int32_t* nrows) {
+  p.rowmap = rowmap; p.nrows = nrows;
   const size_t smem = (size_t)(p.E1 - 1) * BP_NMAX * BP_NW * 4 + (size_t)p.E1 * BP_NMAX * 8 + (size_t)p.N * p.E1 + 16;
   cudaStream_t s = (cudaStream_t)stream;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(batch_prepare_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   batch_prepare_sparse_kernel<<<p.B, BP_THREADS, smem, s>>>(p);
-  lnb::launch_tile_assign(s, p.gext, p.B, p.K, tiles, rowmap, nrows);
-  lnb::count_launch(2);
+  if (p.blob && (p.flags & 2)) {                   // tile table + row-list offsets came with the batch
+    lnb::count_launch(1);
+  } else {
+    lnb::launch_tile_assign(s, p.gext, p.B, p.K, tiles, rowmap, nrows);
+    lnb::count_launch(2);
+  }
   return lnb::finish_launch("graph_prepare_sparse");
 }
 
@@ -231,7 +245,7 @@ int lnb_graph_prepare_sparse_packed(lnb_stream_t stream, const uint8_t* blob, co
   LNB_REQUIRE(B >= 0 && N >= 1 && N <= BP_NMAX && E1 >= 2 && E1 <= BP_EMAX && K >= 1,
               "graph_prepare_sparse_packed: bad dims B=%d N=%d E1=%d K=%d", B, N, E1, K);
   if (B == 0) return LNB_OK;
-  LNB_REQUIRE(blob && inv_sqrt_deg && ell_val && ell_idx && ell_max && gext && tiles && node_ids && mask && V,
+  LNB_REQUIRE(blob && inv_sqrt_deg && ell_val && ell_idx && ell_max && gext && (tiles || (flags & 2)) && node_ids && mask && V,
               "graph_prepare_sparse_packed: null pointer");
   LNB_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0, "graph_prepare_sparse_packed: blob must be 16-byte aligned");
   LNB_REQUIRE((rowmap == nullptr) == (nrows == nullptr), "graph_prepare_sparse_packed: rowmap and nrows go together");

@@ -167,8 +167,31 @@ def packed_offsets(B, K):
   off_node_ptr = off_sizes + _align16(4 * B)
   off_edge_ptr = off_node_ptr + _align16(4 * (B + 1))
   off_D = off_edge_ptr + _align16(4 * (B + 1))
-  off_var = off_D + _align16(4 * B * K)
-  return off_sizes, off_node_ptr, off_edge_ptr, off_D, off_var
+  off_tiles = off_D + _align16(4 * B * K)
+  off_krow = off_tiles + _align16(4 * (B + 2))
+  off_var = off_krow + _align16(4 * (B + 1))
+  return off_sizes, off_node_ptr, off_edge_ptr, off_D, off_var, off_tiles, off_krow
+
+
+def host_tile_table(sizes, k_eff, rows_per_tile=128, graphs_per_tile=32):
+  """Packed-tile table of the fused convolution kernel, computed on the host with the rule of
+  lnb_graph_prepare (csrc/spectral_conv_fused.cu: next-fit over consecutive graphs, sum n_eff <= 128,
+  sum ceil4(k_eff) <= 128, <= 32 graphs per tile; the first graph of a tile always fits).
+  Returns int32 [B+2]: [T, first graph of tile 0..T-1, B, 0 ...]."""
+  B = len(sizes)
+  k4 = (np.asarray(k_eff, np.int64) + 3) // 4 * 4
+  tiles = np.zeros(B + 2, np.int32)
+  T, i = 0, 0
+  while i < B:
+    tiles[1 + T] = i
+    T += 1
+    n_sum, k_sum, j = int(sizes[i]), int(k4[i]), i + 1
+    while j < min(B, i + graphs_per_tile) and n_sum + sizes[j] <= rows_per_tile and k_sum + k4[j] <= rows_per_tile:
+      n_sum += int(sizes[j]); k_sum += int(k4[j]); j += 1
+    i = j
+  tiles[0] = T
+  tiles[1 + T] = B
+  return tiles
 
 
 def pack_sparse(sp):
@@ -177,15 +200,25 @@ def pack_sparse(sp):
   fixed-size segments (sizes, node_ptr, edge_ptr, D), then node ids, Ritz rows and the bond list.
   One H2D copy per step ships the whole batch.  Returns dict(blob, B, N, K, num_edgetype[, label])."""
   B, K = sp['D'].shape
-  off_sizes, off_node_ptr, off_edge_ptr, off_D, off = packed_offsets(B, K)
+  off_sizes, off_node_ptr, off_edge_ptr, off_D, off, off_tiles, off_krow = packed_offsets(B, K)
+  # extents the device would measure: k_eff = last non-zero column of the graph's Ritz rows + 1
+  nz_col = (sp['V_rows'] != 0)
+  k_eff = np.zeros(B, np.int64)
+  for b in range(B):
+    cols = np.flatnonzero(nz_col[sp['node_ptr'][b]:sp['node_ptr'][b + 1]].any(axis=0))
+    k_eff[b] = cols[-1] + 1 if cols.size else 0
+  tiles = host_tile_table(sp['sizes'], k_eff)
+  krow = np.zeros(B + 1, np.int32)
+  krow[1:] = np.cumsum(np.minimum(k_eff, K))
   off_nf = off
   off_v = off_nf + _align16(sp['node_feat'].nbytes)
   off_e = off_v + _align16(sp['V_rows'].nbytes)
   total = off_e + _align16(sp['edges'].nbytes)
   blob = np.zeros(total, np.uint8)
   hdr = blob[:64].view(np.int32)
-  hdr[:11] = [PACK_MAGIC, B, K, off_sizes, off_node_ptr, off_edge_ptr, off_D, off_nf, off_v, off_e, total]
-  for off_, arr in ((off_sizes, sp['sizes']), (off_node_ptr, sp['node_ptr']), (off_edge_ptr, sp['edge_ptr']),
+  hdr[:13] = [PACK_MAGIC, B, K, off_sizes, off_node_ptr, off_edge_ptr, off_D, off_nf, off_v, off_e, total,
+              off_tiles, off_krow]
+  for off_, arr in ((off_tiles, tiles), (off_krow, krow), (off_sizes, sp['sizes']), (off_node_ptr, sp['node_ptr']), (off_edge_ptr, sp['edge_ptr']),
                     (off_D, sp['D']), (off_nf, sp['node_feat']), (off_v, sp['V_rows']), (off_e, sp['edges'])):
     raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
     blob[off_:off_ + raw.size] = raw

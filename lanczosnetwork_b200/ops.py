@@ -249,9 +249,11 @@ def graph_prepare_sparse(sizes, node_ptr, node_feat, edge_ptr, edges, V_rows, N,
   return prep, node_ids, mask, V, L
 
 
-def graph_prepare_sparse_packed(blob, B, N, E1, K, binarize=False, want_dense=False):
+def graph_prepare_sparse_packed(blob, B, N, E1, K, binarize=False, want_dense=False, host_tiles=True):
   """graph_prepare_sparse on a packed batch (data.pack_sparse: one contiguous uint8 buffer, see
-  lnb_graph_prepare_sparse_packed).  Returns (GraphPrep, node_ids, mask, V, L or None)."""
+  lnb_graph_prepare_sparse_packed).  host_tiles: the batch carries the tile table and the Ritz-row
+  prefix sums (data.pack_sparse always writes them), so no tile-assignment kernel is launched and the
+  stack kernel reads the table in place.  Returns (GraphPrep, node_ids, mask, V, L or None)."""
   _need_cuda(blob)
   assert blob.dtype == torch.uint8 and blob.is_contiguous()
   dev = blob.device
@@ -259,7 +261,12 @@ def graph_prepare_sparse_packed(blob, B, N, E1, K, binarize=False, want_dense=Fa
   ell_idx = torch.empty((B, E1, N, N), device=dev, dtype=torch.uint8)
   ell_max = torch.empty((B, E1), device=dev, dtype=torch.int32)
   gext = torch.empty((B, 2), device=dev, dtype=torch.int32)
-  tiles = torch.empty((4 * B + 2,), device=dev, dtype=torch.int32)
+  if host_tiles:
+    from .data import packed_offsets
+    off_tiles = packed_offsets(B, K)[5]
+    tiles = blob[off_tiles:off_tiles + 4 * (B + 2)].view(torch.int32)
+  else:
+    tiles = torch.empty((4 * B + 2,), device=dev, dtype=torch.int32)
   rowmap = torch.empty((B * K,), device=dev, dtype=torch.int32)
   nrows = torch.empty((1,), device=dev, dtype=torch.int32)
   node_ids = torch.empty((B, N), device=dev, dtype=torch.int64)
@@ -269,7 +276,7 @@ def graph_prepare_sparse_packed(blob, B, N, E1, K, binarize=False, want_dense=Fa
   with torch.cuda.device(dev):
     _lib.check(_lib.load().lnb_graph_prepare_sparse_packed(
         _stream(blob), _ptr(blob), _ptr(_inv_sqrt_deg_table(dev)), int(B), int(N), int(E1), int(K),
-        1 if binarize else 0, _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max), _ptr(gext), _ptr(tiles),
+        (1 if binarize else 0) | (2 if host_tiles else 0), _ptr(ell_val), _ptr(ell_idx), _ptr(ell_max), _ptr(gext), _ptr(tiles),
         _ptr(rowmap), _ptr(nrows), _ptr(node_ids), _ptr(mask), _ptr(V), _ptr(L)),
                'lnb_graph_prepare_sparse_packed')
   prep = GraphPrep((ell_val, ell_idx, ell_max, gext, tiles))
@@ -357,7 +364,9 @@ def spectral_stack_forward(prep, Q, w_hi, w_lo, bias, dins, H, S, coeff=None, co
                                           b_att.data_ptr())
     d.score, d.P = score.data_ptr(), W_out.shape[0]
     if mask is not None:
-      mask = (mask != 0).to(torch.uint8).contiguous()
+      if mask.dtype != torch.uint8:            # any non-zero byte counts as 'real node' in the kernel
+        mask = (mask != 0).to(torch.uint8)
+      mask = mask.contiguous()
       d.mask = mask.data_ptr()
   for i, v in enumerate(dins):
     d.Din[i] = int(v)

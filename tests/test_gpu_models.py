@@ -521,6 +521,20 @@ def test_graph_prepare_sparse_is_bit_identical_to_collate_plus_prepare():
     for e in range(7):
       m = emax[b, e]
       assert np.array_equal(vs[b, e, :m], vd[b, e, :m]) and np.array_equal(js[b, e, :m], jd[b, e, :m])
+  # packed batch: one buffer, tile table and Ritz-row offsets computed on the HOST with the same rule
+  spn = data.sparse_collate(samples, 20)
+  pk = data.pack_sparse(spn)
+  prep_p, ids_p, mask_p, V_p, L_p = ops.graph_prepare_sparse_packed(_t(pk['blob']).to(dev()), B, N, 7, 20,
+                                                                    want_dense=True)
+  assert torch.equal(ids_p, ids) and torch.equal(mask_p, mask) and torch.equal(V_p, V) and torch.equal(L_p, L)
+  assert torch.equal(prep_p[2], prep_d[2]) and torch.equal(prep_p[3], prep_d[3])
+  assert torch.equal(prep_p[4][:T + 2], prep_d[4][:T + 2])                       # host tiles == device tiles
+  assert int(prep_p.nrows) == nr and torch.equal(prep_p.rowmap[:nr], prep_d.rowmap[:nr])
+  vp, jp = prep_p[0].cpu().numpy(), prep_p[1].cpu().numpy()
+  for b in range(0, B, 7):
+    for e in range(7):
+      m = emax[b, e]
+      assert np.array_equal(vp[b, e, :m], vd[b, e, :m]) and np.array_equal(jp[b, e, :m], jd[b, e, :m])
   # GCNFP's binarisation flag
   pb_s = ops.graph_prepare_sparse(sp['sizes'], sp['node_ptr'], sp['node_feat'], sp['edge_ptr'],
                                   sp['edges'], sp['V_rows'], N, 7, binarize=True)[0]
