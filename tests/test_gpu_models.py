@@ -618,3 +618,48 @@ def test_invalidate_caches_after_data_edit_and_graph_stats():
     assert not torch.equal(d, a)
     mod.use_cuda_graph = False
     assert torch.equal(mod(*args, mask=mask), d)
+
+
+def test_graph_prepare_sparse_random_multigraphs():
+  """GPU-side batch construction on adversarial inputs: random multigraphs (several bond types between
+  the same pair, self loops, duplicate records, isolated nodes, single-node graphs), N up to 96 and 1
+  to 15 bond types -- dense operators bit-identical to the host mirror of the reference's L4
+  (utils/data_helper.py:92-116,155-156) and ELL / extents identical to lnb_graph_prepare on them."""
+  from lanczosnetwork_b200 import ops
+  rng = np.random.RandomState(123)
+  for N, E, B in ((40, 3, 24), (96, 1, 9), (17, 15, 31), (128, 2, 4)):
+    samples = []
+    for b in range(B):
+      n = int(rng.randint(1, N + 1)) if b else N
+      adjs = np.zeros((n, n, E))
+      ne = int(rng.randint(0, 3 * n + 1))
+      recs = []
+      for _ in range(ne):
+        u, v, c = int(rng.randint(n)), int(rng.randint(n)), int(rng.randint(E))
+        adjs[u, v, c] = adjs[v, u, c] = 1.0
+        recs.append((min(u, v), max(u, v), c))
+      rec = data.prepare_graph(adjs, rng.randint(0, 70, size=n), label=rng.randn(1, 4))
+      if recs and b % 3 == 0:                      # ship the raw records, duplicates and order included
+        rec['edges'] = np.array(recs + recs[:2], np.uint8).reshape(-1, 3)
+      samples.append(rec)
+    dense = data.collate(samples, 12)
+    sp = _sparse_tensors(data.sparse_collate(samples, 12), dev())
+    prep_s, ids, mask, V, L = ops.graph_prepare_sparse(sp['sizes'], sp['node_ptr'], sp['node_feat'],
+                                                       sp['edge_ptr'], sp['edges'], sp['V_rows'], N, E + 1,
+                                                       want_dense=True)
+    assert torch.equal(L.cpu(), _t(dense['L'])), (N, E)
+    assert torch.equal(mask.cpu(), _t(dense['node_mask'])) and torch.equal(V.cpu(), _t(dense['V']))
+    prep_d = ops.graph_prepare(_t(dense['L']).to(dev()), _t(dense['V']).to(dev()))
+    assert torch.equal(prep_s[2], prep_d[2]) and torch.equal(prep_s[3], prep_d[3])
+    T = int(prep_d[4][0])
+    assert torch.equal(prep_s[4][:T + 2], prep_d[4][:T + 2])
+    emax = prep_d[2].cpu().numpy()
+    vs, vd = prep_s[0].cpu().numpy(), prep_d[0].cpu().numpy()
+    js, jd = prep_s[1].cpu().numpy(), prep_d[1].cpu().numpy()
+    for b in range(B):
+      for e in range(E + 1):
+        m = emax[b, e]
+        assert np.array_equal(vs[b, e, :m], vd[b, e, :m]) and np.array_equal(js[b, e, :m], jd[b, e, :m])
+    pk = data.pack_sparse(data.sparse_collate(samples, 12))
+    prep_p = ops.graph_prepare_sparse_packed(_t(pk['blob']).to(dev()), B, N, E + 1, 12)[0]
+    assert torch.equal(prep_p[4][:T + 2], prep_d[4][:T + 2]) and torch.equal(prep_p[3], prep_d[3])
