@@ -345,7 +345,12 @@ def test_ada_full_qm8_config_vs_oracle():
   # comparison depend on the host CPU's summation order in the oracle
   lz_ref = orc.lanczos_tridiagonalise(Le, _t(batch['node_mask']), q1[:, :, 0], spec['K'])
   np.testing.assert_allclose(lz['T'].cpu().numpy(), lz_ref['T'].numpy(), atol=5e-5)
-  np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4)
+  # final scores (O(0.16) here): rtol 5e-4 / atol 5e-5 against the fp32 oracle (round 1: 2e-3 / 2e-4) and a budget
+  # against the fp64 oracle -- measured (tools/exp_ada_error.py): |ours - fp64| = 1.2e-6, fp32 oracle 1.4e-7
+  np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=5e-4, atol=5e-5)
+  ref64 = orc.ada_lanczos_net_forward(params, spec, batch['node_feat'], batch['L'], batch['node_mask'],
+                                      q1[:, :, 0].double(), dtype=torch.float64).numpy()
+  assert np.abs(out.cpu().numpy() - ref64).max() <= 2e-5
 
 
 def test_lanczosnet_bench_shape_b1024_both_graph_paths():
