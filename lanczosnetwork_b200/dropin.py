@@ -33,7 +33,7 @@ def register_native_op():
 def patch_namespace(module, training=False):
   """Rebind the class names in ``module``'s globals to the B200 drop-ins.  ``training=True`` (a
   run without ``-t``) rebinds only the classes that have a differentiable training path
-  (every class but AdaLanczosNet); the others keep the reference's trainable class
+  (currently every class); one without it would keep the reference's trainable class
   instead of failing on the first ``loss.backward()``."""
   for name in DROPIN_CLASSES:
     if hasattr(module, name):

@@ -48,14 +48,21 @@ class AdaLanczosNet(SpectralNetBase):
       The Lanczos start vector is drawn exactly like the reference: torch.randn(B, N, 1) on
       the CPU generator (ada_lanczos_net.py:161), then copied to the device.
     """
-    self._check_mode()
     dev = self._device()
     B, N = node_feat.shape[0], node_feat.shape[1]
+    if self._check_mode():
+      q1 = torch.randn(B, N, 1)
+      score = self._train_impl(self._to(dev, node_feat), self._to(dev, L), self._to(dev, mask), q1)
+      return self._finish(score, self._to(dev, label))
     # drawn exactly like the reference (CPU generator, ada_lanczos_net.py:161); it enters the captured
     # CUDA graph as an input buffer
     q1 = torch.randn(B, N, 1) if self.num_scale_long > 0 else None
     score = self._graph_forward(self._forward_impl, (node_feat, L, mask, q1))
     return self._finish(score, self._to(dev, label))
+
+  def _train_impl(self, node_feat, L, mask, q1):
+    from ..train import ada_train
+    return ada_train(self, node_feat, L, mask, q1)
 
   def _forward_impl(self, node_feat, L, mask, q1):
     dev = L.device

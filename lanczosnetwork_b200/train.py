@@ -25,7 +25,7 @@ import torch
 from . import ops
 
 __all__ = ['dense', 'operator_messages', 'spectral_messages', 'embedding', 'ritz_stack_train',
-           'dcnn_train', 'cheby_train', 'gated_readout']
+           'dcnn_train', 'cheby_train', 'gated_readout', 'bmm', 'ada_train']
 
 
 def _pad_cols(x, mult=4):
@@ -265,6 +265,161 @@ def cheby_train(model, node_ids, L, mask):
     for kk in range(1, order):
       scale[kk] = 2.0 * operator_messages(L, scale[kk - 1], 0, 1) - scale[kk - 2]
     msgs = ([operator_messages(L, state, 1, E1 - 1)] if E1 > 1 else []) + scale
+    lin = model.filter[t]
+    state = dense(torch.cat(msgs, dim=2).reshape(B * N, -1), lin.weight, lin.bias, True).reshape(B, N, -1)
+    if model.training and model.dropout > 0.0:
+      state = torch.nn.functional.dropout(state, model.dropout, True)
+  return gated_readout(model, state, mask)
+
+
+class _BMM(torch.autograd.Function):
+  """C[b] = A[b] @ Bm[b] on the strided batched GEMM, differentiable in both operands
+  (gA = g Bm^T, gB = A^T g through swapped strides -- no transposed copies)."""
+
+  @staticmethod
+  def forward(ctx, A, Bm):
+    A, Bm = A.contiguous(), Bm.contiguous()
+    nb, M, K = A.shape
+    N = Bm.shape[2]
+    C = torch.empty((nb, M, N), device=A.device, dtype=torch.float32)
+    ops.bgemm(A, (M * K, 0, K, 1), Bm, (K * N, 0, N, 1), C, (M * N, 0, N, 1), nb, 1, M, N, K)
+    ctx.save_for_backward(A, Bm)
+    return C
+
+  @staticmethod
+  def backward(ctx, g):
+    A, Bm = ctx.saved_tensors
+    nb, M, K = A.shape
+    N = Bm.shape[2]
+    g = g.contiguous()
+    gA = gB = None
+    if ctx.needs_input_grad[0]:            # [M,N] @ [N,K]: B operand = Bm^T via (k stride 1, n stride N)
+      gA = torch.empty_like(A)
+      ops.bgemm(g, (M * N, 0, N, 1), Bm, (K * N, 0, 1, N), gA, (M * K, 0, K, 1), nb, 1, M, K, N)
+    if ctx.needs_input_grad[1]:            # [K,M] @ [M,N]: A operand = A^T via (m stride 1, k stride K)
+      gB = torch.empty_like(Bm)
+      ops.bgemm(A, (M * K, 0, 1, K), g, (M * N, 0, N, 1), gB, (K * N, 0, N, 1), nb, 1, K, N, M)
+    return gA, gB
+
+
+def bmm(A, Bm):
+  return _BMM.apply(A.float(), Bm.float())
+
+
+_EPS = 1.1920928955078125e-07       # np.finfo(np.float32).eps (ada_lanczos_net.py:8)
+
+
+def _gaussian_laplacian_train(x, adj):
+  """Learned operator of model/ada_lanczos_net.py:101-137 on the autograd tape: Gaussian kernel of the
+  embedding distances (sigma^2 = mean over all N^2 pairs, padded ones included), masked by the
+  adjacency, symmetrically normalised."""
+  diff = x.unsqueeze(1) - x.unsqueeze(2)
+  dist2 = (diff * diff).sum(dim=3)
+  sigma2 = dist2.reshape(dist2.shape[0], -1).mean(dim=1).reshape(-1, 1, 1)
+  A = torch.exp(-dist2 / sigma2) * adj
+  rs = A.sum(dim=2, keepdim=True)
+  d = (rs + (rs == 0).to(A.dtype)).pow(-0.5)
+  return d * A * d.transpose(1, 2)
+
+
+def _lanczos_train(A, mask, q1, K):
+  """Differentiable K-step Lanczos with the reference's rules (model/ada_lanczos_net.py:139-247);
+  operator products through ``bmm``, re-orthogonalisation as two block Gram-Schmidt passes (the
+  formulation of the inference kernel), the acceptance / masking logic as data (no gradient)."""
+  B, N = A.shape[0], A.shape[1]
+  iters = min(N, K)
+  q = q1.reshape(B, N, 1).to(A.dtype)
+  nreal = torch.full((B,), N, device=A.device, dtype=torch.long)
+  if mask is not None:
+    fm = (mask != 0).reshape(B, N, 1).to(A.dtype)
+    q = q * fm
+    nreal = fm.sum(dim=1).reshape(B).long()
+  q = q / q.norm(dim=1, keepdim=True)
+  basis, alphas, betas, valids = [q], [], [], []
+  prev, beta_prev = torch.zeros_like(q), torch.zeros((B, 1, 1), device=A.device, dtype=A.dtype)
+  ok = torch.ones((B, 1, 1), device=A.device, dtype=A.dtype)
+  for i in range(iters):
+    cur = basis[i]
+    z = bmm(A, cur)
+    a = (cur * z).sum(dim=1, keepdim=True)
+    z = z - a * cur - beta_prev * prev
+    if i > 0:
+      Qb = torch.cat(basis[:i], dim=2)                               # [B,N,i]
+      scale = 1.0 / ((Qb * Qb).sum(dim=1, keepdim=True) + _EPS)       # [B,1,i]
+      for _ in range(2):
+        c = bmm(Qb.transpose(1, 2), z) * scale.transpose(1, 2)       # [B,i,1]
+        z = z - bmm(Qb, c)
+    b = z.norm(dim=1, keepdim=True)
+    ok = ok * (b.detach() >= 1.0e-4).to(A.dtype)
+    valids.append(ok)
+    alphas.append(a)
+    betas.append(b)
+    basis.append(z * ok / (b + _EPS))
+    prev, beta_prev = cur, b
+  alpha = torch.cat(alphas, dim=1).squeeze(2)
+  valid = torch.cat(valids, dim=1).squeeze(2)
+  idx = torch.minimum(valid.sum(dim=1).long(), nreal)
+  col = torch.arange(iters, device=A.device).unsqueeze(0)
+  valid = valid * (col < idx.unsqueeze(1)).to(A.dtype)
+  alpha = alpha * valid
+  T = torch.diag_embed(alpha)
+  if iters > 1:
+    beta = torch.cat(betas[:-1], dim=1).squeeze(2) * valid[:, :-1]
+    T = T + torch.diag_embed(beta, offset=1) + torch.diag_embed(beta, offset=-1)
+  Q = torch.cat(basis[:iters], dim=2)
+  row = torch.arange(N, device=A.device).reshape(1, N, 1)
+  Q = Q * (valid.unsqueeze(1) * (row < idx.reshape(B, 1, 1)).to(A.dtype))
+  if iters < K:
+    T = torch.nn.functional.pad(T, (0, K - iters, 0, K - iters))
+    Q = torch.nn.functional.pad(Q, (0, K - iters))
+  return T, Q
+
+
+def ada_train(model, node_ids, L, mask, q1):
+  """Differentiable AdaLanczosNet (model/ada_lanczos_net.py:288-368): embedding -> learned Gaussian
+  Laplacian -> Lanczos -> learned filter on the powers of T (the 4096-wide MLP on the tcgen05 dense
+  kernel) -> graph convolutions with [short walk | Q G_s Q^T X | L_e X] messages -> gated readout."""
+  L = L.float().contiguous()
+  state = embedding(node_ids, model.embedding.weight)
+  B, N = state.shape[0], state.shape[1]
+  K, S = model.num_eig_vec, model.num_scale_long
+  short = list(model.short_diffusion_dist)
+  powers = Q = None
+  if S > 0:
+    adj = (L[:, :, :, 0] != 0).to(torch.float32)                    # ada_lanczos_net.py:310-311
+    Le = _gaussian_laplacian_train(state, adj)
+    T, Q = _lanczos_train(Le, mask, q1.to(L.device), K)
+    plist, cur = [], T
+    for p in range(1, max(model.long_diffusion_dist) + 1):          # T^p by repeated products (:262-270)
+      if p in model.long_diffusion_dist:
+        plist.append(cur)
+      if p < max(model.long_diffusion_dist):
+        cur = bmm(cur, T)
+    powers = torch.cat(plist, dim=2)                                # [B,K,S*K]: index r, s*K + c (:274)
+  for t in range(model.num_layer):
+    msgs = []
+    if short:
+      walk = state
+      for step in range(1, max(short) + 1):
+        walk = operator_messages(L, walk, 0, 1)
+        if step in short:
+          msgs.append(walk)
+    if S > 0:
+      if model.spectral_filter_kind == 'MLP':
+        h = powers.reshape(B, K * S * K)
+        seq = model.spectral_filter[t]
+        for i in (0, 2, 4, 6):
+          h = dense(h, seq[i].weight, seq[i].bias, i != 6)
+        G = h.reshape(B, K, K, S)                                   # index r, c, s (:275)
+        G = ((G + G.transpose(1, 2)) * 0.5).permute(0, 3, 1, 2)     # [B,S,K,K]
+      else:
+        G = torch.stack(plist, dim=1)
+      D = state.shape[2]
+      U = bmm(Q.transpose(1, 2), state)                             # [B,K,D]
+      W = bmm(G.reshape(B * S, K, K), U.unsqueeze(1).expand(B, S, K, D).reshape(B * S, K, D))
+      M = bmm(Q.unsqueeze(1).expand(B, S, N, K).reshape(B * S, N, K), W)      # [B*S,N,D]
+      msgs.append(M.reshape(B, S, N, D).permute(0, 2, 1, 3).reshape(B, N, S * D))
+    msgs.append(operator_messages(L, state))
     lin = model.filter[t]
     state = dense(torch.cat(msgs, dim=2).reshape(B * N, -1), lin.weight, lin.bias, True).reshape(B, N, -1)
     if model.training and model.dropout > 0.0:

@@ -7,7 +7,7 @@ import torch
 
 from helpers import deterministic_state_dict, load_golden, oracle_spec
 from lanczosnetwork_b200 import configs, data
-from lanczosnetwork_b200.model import ChebyNet, DCNN, GCN, LanczosNet, LanczosNetGeneral
+from lanczosnetwork_b200.model import AdaLanczosNet, ChebyNet, DCNN, GCN, LanczosNet, LanczosNetGeneral
 from oracle import lanczos_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -167,3 +167,36 @@ def test_dcnn_and_cheby_gradients_match_oracle(monkeypatch):
                   mask=_t(g['node_mask']).to(dev()))
     loss.backward()
     _compare(mod, grads_ref)
+
+
+def test_ada_lanczos_net_gradients_match_oracle(monkeypatch):
+  """AdaLanczosNet end to end on the tape: embedding -> learned Gaussian Laplacian -> K-step Lanczos
+  -> learned filter on the powers of T -> graph convolutions -> readout.  Gradients against autograd
+  over the fp64 oracle (which runs the reference's sequential Gram-Schmidt): the Lanczos recurrence
+  amplifies rounding, so the bound is 2e-2 of each gradient's largest entry; the forward agrees with
+  the fused inference path."""
+  g = load_golden('ada_forward_small.npz')
+  cfg = configs.qm8_ada_lanczos_net(num_layer=2, hidden_dim=[32, 32], num_eig_vec=8,
+                                    long_diffusion_dist=[2, 5], short_diffusion_dist=[1, 3])
+  mod = AdaLanczosNet(cfg)
+  params = deterministic_state_dict(mod, int(g['weight_seed']))
+  mod.load_state_dict(params)
+  mod = mod.to(dev()).train()
+  spec = oracle_spec(mod, 'AdaLanczosNet')
+  B, N = g['node_feat'].shape
+  torch.manual_seed(int(g['torch_seed']))
+  q1 = torch.randn(B, N, 1)
+  label = torch.from_numpy(np.random.RandomState(0).randn(B, g['score'].shape[1]).astype(np.float32))
+
+  def fwd(p64):
+    s = orc.ada_lanczos_net_forward(p64, spec, g['node_feat'], g['L'], g['node_mask'], q1[:, :, 0].double(),
+                                    dtype=torch.float64)
+    return torch.nn.functional.mse_loss(s, label.double())
+
+  _, grads_ref = _oracle_grads(fwd, params, monkeypatch)
+  torch.manual_seed(int(g['torch_seed']))
+  score, loss = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), label=label.to(dev()),
+                    mask=_t(g['node_mask']).to(dev()))
+  loss.backward()
+  _compare(mod, grads_ref, rel=2e-2)
+  np.testing.assert_allclose(score.detach().cpu().numpy(), g['score'], rtol=1e-3, atol=5e-5)

@@ -127,7 +127,7 @@ def test_modules_mirror_reference_surface():
   assert float(m1.filter[0].bias.abs().sum()) == 0.0
 
 
-def test_dropin_rebinds_names_in_a_runner_namespace():
+def test_dropin_rebinds_names_in_a_runner_namespace(monkeypatch):
   import types
   from lanczosnetwork_b200 import dropin
   fake_runner = types.ModuleType('fake_runner')
@@ -141,9 +141,11 @@ def test_dropin_rebinds_names_in_a_runner_namespace():
   # a training run (no -t): classes without a differentiable path keep the reference's class
   train_ns = types.ModuleType('fake_train_runner')
   train_ns.LanczosNet, train_ns.AdaLanczosNet, train_ns.DCNN = 'ref', 'ref', 'ref'
+  from lanczosnetwork_b200.model import AdaLanczosNet, DCNN
+  monkeypatch.delattr(DCNN, '_train_impl')
   dropin.patch_namespace(train_ns, training=True)
-  from lanczosnetwork_b200.model import DCNN
-  assert train_ns.LanczosNet is LanczosNet and train_ns.DCNN is DCNN and train_ns.AdaLanczosNet == 'ref'
+  assert train_ns.LanczosNet is LanczosNet and train_ns.AdaLanczosNet is AdaLanczosNet and train_ns.DCNN == 'ref'
+  monkeypatch.undo()
   dropin.register_native_op()
   import importlib
   sr = importlib.import_module('operators._ext.segment_reduction')
