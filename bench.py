@@ -325,7 +325,91 @@ def run_workloads(dev, peaks):
                     'bound': 'weight stream of the 4096-wide learned-filter MLP at small batch'}
   del ada
   torch.cuda.empty_cache()
+  out['train_qm8'] = train_workload(dev)
   return out
+
+
+def train_workload(dev, B=64, N=27):
+  """one optimisation step (forward, MSE loss, backward, Adam) of config #2's LanczosNet at the
+  reference's training batch size (config/qm8_lanczos_net.yaml:33), every batch padded to N nodes.  Three
+  timings: eager loop body of the reference's runner on this library's autograd Functions, the same step
+  replayed from one CUDA graph (train.GraphedStep; inputs copied device-to-device into the captured
+  buffers), and autograd over the CPU oracle port (fp32, 2 steps)."""
+  from helpers import deterministic_state_dict, oracle_spec
+  from lanczosnetwork_b200 import configs, data
+  from lanczosnetwork_b200.model import LanczosNet
+  from lanczosnetwork_b200.train import GraphedStep
+  batches = []
+  for i in range(4):
+    b = data.collate(data.synthetic_qm8_samples(B, seed=900 + i), 20, num_nodes=N)
+    b['label'] = np.random.RandomState(i).randn(B, 16).astype(np.float32)
+    batches.append(b)
+  dbatches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in batches]
+
+  def make():
+    m = LanczosNet(configs.qm8_lanczos_net())
+    params = deterministic_state_dict(m, WEIGHT_SEED)
+    m.load_state_dict(params)
+    return m, params
+
+  def call(b):
+    return (b['node_feat'], b['L'], b['D'], b['V']), {'label': b['label'], 'mask': b['node_mask']}
+
+  mod, params = make()
+  mod = mod.to(dev).train()
+  opt = torch.optim.Adam(mod.parameters(), lr=1e-4)
+  it = [0]
+
+  def eager():
+    a, kw = call(dbatches[it[0] % 4])
+    it[0] += 1
+    opt.zero_grad()
+    _, loss = mod(*a, **kw)
+    loss.backward()
+    opt.step()
+
+  t_eager = time_events(eager, 20, 5)
+  mod2 = make()[0].to(dev).train()
+  opt2 = torch.optim.Adam(mod2.parameters(), lr=1e-4)
+  a0, kw0 = call(dbatches[0])
+  step = GraphedStep(mod2, opt2, a0, kw0)
+
+  def graphed():
+    a, kw = call(dbatches[it[0] % 4])
+    it[0] += 1
+    step(*a, **kw)
+
+  t_graph = time_events(graphed, 50, 5)
+  nodes = step.graph  # keep alive
+  # CPU: autograd over the oracle port, Adam on leaf copies of the same weights
+  from oracle import lanczos_oracle as orc
+  spec = oracle_spec(mod, 'LanczosNet')
+  leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in params.items()}
+  copt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-4)
+  cast = orc._cast
+  orc._cast = lambda p_, dtype: p_                 # the oracle detaches its parameters; keep the tape
+  ts = []
+  try:
+    for i in range(3):
+      b = batches[i % 4]
+      t0 = time.perf_counter()
+      copt.zero_grad()
+      score = orc.lanczos_net_forward(leaves, spec, b['node_feat'], b['L'], b['D'], b['V'], b['node_mask'])
+      loss = torch.nn.functional.mse_loss(score, torch.from_numpy(b['label']))
+      loss.backward()
+      copt.step()
+      ts.append(time.perf_counter() - t0)
+  finally:
+    orc._cast = cast
+  t_cpu = float(np.median(ts[1:])) * 1e3
+  del nodes
+  return {'config': 'QM8 LanczosNet (config/qm8_lanczos_net.yaml) training step: B=%d, N padded to %d, K=20, Adam lr 1e-4, '
+                    'MSE; inputs device resident' % (B, N),
+          'ms_eager': t_eager, 'ms_graphed': t_graph, 'molecules_per_s_eager': B / (t_eager * 1e-3),
+          'molecules_per_s_graphed': B / (t_graph * 1e-3),
+          'cpu_port': {'ms': t_cpu, 'molecules_per_s': B / (t_cpu * 1e-3), 'threads': torch.get_num_threads(),
+                       'kind': 'port', 'sample': '2 timed steps of autograd over the oracle port (fp32)'},
+          'graph_replays': step.replays}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -90,13 +90,14 @@ def prepare_graph(adjs, node_feat, label=None):
   return rec
 
 
-def collate(samples, num_eigs):
-  """Zero-pad a list of ``prepare_graph`` records to the batch-max node count.
+def collate(samples, num_eigs, num_nodes=None):
+  """Zero-pad a list of ``prepare_graph`` records to the batch-max node count (or to ``num_nodes`` if
+  that is larger: fixed shapes for a captured training step, train.GraphedStep).
 
   Returns numpy arrays: node_feat (B,N) int64 or (B,N,D) float32, node_mask (B,N) uint8,
   L (B,N,N,E+1) float32 with channel 0 the simple-graph operator, D (B,K), V (B,N,K)."""
   sizes = np.array([s['L_simple_4'].shape[0] for s in samples])
-  B, N = len(samples), int(sizes.max())
+  B, N = len(samples), max(int(sizes.max()), int(num_nodes or 0))
   E = samples[0]['L_multi'].shape[2]
   nf0 = np.asarray(samples[0]['node_feat'])
   node_feat = (np.zeros((B, N), np.int64) if nf0.ndim == 1

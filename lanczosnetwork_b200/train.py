@@ -25,7 +25,7 @@ import torch
 from . import ops
 
 __all__ = ['dense', 'operator_messages', 'spectral_messages', 'embedding', 'ritz_stack_train',
-           'dcnn_train', 'cheby_train', 'gated_readout', 'bmm', 'ada_train']
+           'dcnn_train', 'cheby_train', 'gated_readout', 'bmm', 'ada_train', 'GraphedStep']
 
 
 def _pad_cols(x, mult=4):
@@ -425,3 +425,88 @@ def ada_train(model, node_ids, L, mask, q1):
     if model.training and model.dropout > 0.0:
       state = torch.nn.functional.dropout(state, model.dropout, True)
   return gated_readout(model, state, mask)
+
+
+class GraphedStep:
+  """One optimisation step -- forward, loss, backward, optimizer update -- of a drop-in module captured
+  in ONE CUDA graph and replayed per batch (the loop body of runner/qm8_runner.py:226-259:
+  ``optimizer.zero_grad(); _, loss = model(...); loss.backward(); optimizer.step()``).
+
+  At the reference's batch size (64 molecules, config/qm8_lanczos_net.yaml:33) a training step is a few
+  hundred small launches and launch-bound in eager mode; the replayed graph removes the host from the
+  loop.  Inputs are copied into static device buffers (shapes are fixed at capture: pad every batch to
+  the same node count -- padded nodes are masked and have zero operator rows, so the padding does not
+  change a real node's value).  The optimizer must support capture (``torch.optim.Adam`` /
+  ``AdamW`` get ``capturable=True`` here; plain SGD needs nothing).  The warm-up iterations torch needs
+  before capture are rolled back (parameters and optimizer state restored in place), so constructing
+  the object does not advance training.  Not for AdaLanczosNet (its start vector is drawn on the
+  host each call)."""
+
+  def __init__(self, model, optimizer, args, kwargs=None, warmup=3):
+    kwargs = dict(kwargs or {})
+    if not hasattr(type(model), '_train_impl') or type(model).__name__ == 'AdaLanczosNet':
+      raise TypeError('GraphedStep needs a drop-in module with a host-free training forward')
+    if kwargs.get('label') is None:
+      raise ValueError('GraphedStep captures the loss: pass label=')
+    dev = model._device()
+    if dev.type != 'cuda':
+      raise RuntimeError('GraphedStep needs the module on a CUDA device')
+    model.train()
+    self.model, self.optimizer = model, optimizer
+    self._args = [self._static(a, dev) for a in args]
+    self._kwargs = {k: self._static(v, dev) for k, v in kwargs.items()}
+    for group in optimizer.param_groups:
+      if 'capturable' in group:
+        group['capturable'] = True
+    for st in optimizer.state.values():                      # a resumed Adam keeps ``step`` on the host
+      if torch.is_tensor(st.get('step')) and st['step'].device != dev:
+        st['step'] = st['step'].to(dev)
+    params = [p for g in optimizer.param_groups for p in g['params']]
+    saved_p = [p.detach().clone() for p in params]
+    saved_s = {id(p): {k: v.detach().clone() for k, v in optimizer.state.get(p, {}).items() if torch.is_tensor(v)}
+               for p in params}
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      for _ in range(max(int(warmup), 1)):
+        self._body()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    self.graph = torch.cuda.CUDAGraph()
+    optimizer.zero_grad(set_to_none=True)
+    with torch.cuda.graph(self.graph):
+      self.score, self.loss = self._body(zero=False)
+    with torch.no_grad():                                    # roll the warm-up steps back, in place
+      for p, sp in zip(params, saved_p):
+        p.copy_(sp)
+        for k, v in optimizer.state.get(p, {}).items():
+          if torch.is_tensor(v):
+            old = saved_s[id(p)].get(k)
+            v.copy_(old) if old is not None else v.zero_()
+    self.replays = 0
+
+  @staticmethod
+  def _static(x, dev):
+    return x.detach().to(dev).clone() if torch.is_tensor(x) else x
+
+  def _body(self, zero=True):
+    if zero:
+      self.optimizer.zero_grad(set_to_none=True)
+    score, loss = self.model(*self._args, **self._kwargs)
+    loss.backward()
+    self.optimizer.step()
+    return score, loss
+
+  def __call__(self, *args, **kwargs):
+    """Copy this batch into the captured buffers and replay.  Returns (score, loss): static device
+    tensors that the next call overwrites."""
+    for dst, src in zip(self._args, args):
+      if torch.is_tensor(dst):
+        if dst.shape != src.shape:
+          raise ValueError('GraphedStep was captured for %s, got %s' % (tuple(dst.shape), tuple(src.shape)))
+        dst.copy_(src, non_blocking=True)
+    for k, dst in self._kwargs.items():
+      if torch.is_tensor(dst):
+        dst.copy_(kwargs[k], non_blocking=True)
+    self.graph.replay()
+    self.replays += 1
+    return self.score, self.loss
