@@ -1,8 +1,8 @@
 // Batched Lanczos tridiagonalisation for DENSE operators (two-launch path: lnb_lanczos_tridiag, then
-// lnb_tridiag_ritz), tridiagonal QL eigensolve (Ritz pairs) and tridiagonal powers.  One CTA per
-// graph: operator resident in registers / shared memory for 32 < N <= 256, streamed above; N <= 32
-// goes through the fused kernel of lanczos_fused.cu (the product path for every size is
-// lnb_lanczos_ritz: operator packed on chip, one launch).
+// lnb_tridiag_ritz), tridiagonal QL eigensolve (Ritz pairs) and tridiagonal powers.  lnb_lanczos_tridiag
+// is the fused kernel of lanczos_fused.cu without its QL stage wherever that kernel fits (N <= 1024,
+// K <= 64, basis in shared memory); the CTA-per-graph kernel below is the fallback for everything else
+// (operator staged in shared memory when it fits, streamed otherwise).
 //
 // Reference behaviour reproduced (model/ada_lanczos_net.py:139-247), including its masking
 // rules: cumulative validity from beta >= 1e-4 (:193-199), idx = min(#valid, #real nodes)
@@ -199,212 +199,6 @@ lanczos_cta_kernel(const float* __restrict__ A, const uint8_t* __restrict__ mask
 }
 
 // ------------------------------------------------------------------------------------------
-// Resident-operator kernel, 32 < N <= 256: the whole operator lives ON CHIP for all K
-// iterations (read from HBM exactly once), so the kernel's DRAM traffic is the compulsory
-// 4N^2 bytes per graph instead of K times that.
-//   NP = 64 / 128 / 256 padded size, TPG threads per graph (128 / 512 / 512), TPR = TPG / NP
-//   threads per operator row, each holding CW = NP / TPR consecutive columns of its row: in
-//   registers (CW <= 64) or 64 in registers + 64 in padded shared memory (NP = 256).
-//   matvec = register FMAs against q (shared memory, LDS.128) + a TPR-wide shuffle reduce.
-// Re-orthogonalisation: two block Gram-Schmidt passes (projections of a pass from the same z).
-// ------------------------------------------------------------------------------------------
-template <int TPG>
-__device__ __forceinline__ void group_bar(int grp) {
-  if (TPG == 512) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(TPG) : "memory");
-}
-
-// sum over the TPG threads of a graph group; red = [2][16] floats per group (double buffered:
-// one barrier per reduction)
-template <int TPG>
-__device__ __forceinline__ float group_sum(float v, float* red, int& flip, int grp, int wg, int lane) {
-  v = lnb::warp_sum(v);
-  float* buf = red + flip * 16;
-  flip ^= 1;
-  if (lane == 0) buf[wg] = v;
-  group_bar<TPG>(grp);
-  float t = 0.f;
-#pragma unroll
-  for (int w = 0; w < TPG / 32; ++w) t += buf[w];
-  return t;
-}
-
-template <int NP, int TPG>
-__global__ void __launch_bounds__(512)
-lanczos_resident_kernel(const float* __restrict__ A, const uint8_t* __restrict__ mask,
-                        const float* __restrict__ q1, int B, int N, int K,
-                        float* __restrict__ T, float* __restrict__ Q, float* __restrict__ alpha_out,
-                        float* __restrict__ beta_out, int32_t* __restrict__ idx_out) {
-  constexpr int GPC = 512 / TPG;               // graphs per CTA
-  constexpr int TPR = TPG / NP;                // threads per operator row
-  constexpr int CW = NP / TPR;                 // columns per thread
-  constexpr int CR = CW > 64 ? 64 : CW;        // ... of which in registers
-  constexpr int CS = CW - CR;                  // ... in shared memory (NP = 256: 64)
-  constexpr int ASP = CS ? CS + 4 : 0;         // padded per-thread stride of the smem part
-  extern __shared__ __align__(16) float smem_l[];
-  const int tid = threadIdx.x, grp = tid / TPG, t = tid % TPG;
-  const int lane = tid & 31, wg = t >> 5;
-  const int g = blockIdx.x * GPC + grp;
-  const int iters = N < K ? N : K;
-  // per-graph shared layout
-  const int per_graph = ((iters + 1) * NP + 2 * NP + 3 * K + (K + 1) + 32 + TPG * ASP + 3) & ~3;
-  float* base = smem_l + (size_t)grp * per_graph;
-  float* Qs = base;                            // (iters+1) x NP   Krylov basis
-  float* qs = Qs + (size_t)(iters + 1) * NP;   // NP               current q (matvec operand)
-  float* zs = qs + NP;                         // NP               z for the projection pass
-  float* As = zs + NP;                         // TPG x ASP        (16-byte aligned: float4 reads)
-  float* al = As + (size_t)TPG * ASP;          // K
-  float* be = al + K;                          // K
-  float* cs = be + K;                          // K                projection coefficients
-  float* qq = cs + K;                          // K+1
-  float* red = qq + (K + 1);                   // 32
-  const bool live = g < B;                     // whole groups are live or dead together
-  const int r = t / TPR, p = t % TPR;          // operator row, column part
-  int flip = 0;
-
-  // ---- operator -> registers (+ shared memory), read from HBM once -------------------------
-  float a[CR];
-  {
-    const float* Ag = A + (int64_t)(live ? g : 0) * N * N;
-#pragma unroll
-    for (int c = 0; c < CR; ++c) {
-      const int col = p * CW + c;
-      a[c] = (live && r < N && col < N) ? __ldg(Ag + (int64_t)r * N + col) : 0.f;
-    }
-    if (CS) {
-#pragma unroll 8
-      for (int c = 0; c < CS; ++c) {
-        const int col = p * CW + CR + c;
-        As[(size_t)t * ASP + c] = (live && r < N && col < N) ? __ldg(Ag + (int64_t)r * N + col) : 0.f;
-      }
-    }
-  }
-  // ---- start vector ------------------------------------------------------------------------
-  float mk = 0.f, qr = 0.f;                    // row-owner values (valid in every p-lane of the row)
-  if (live && r < N) {
-    mk = mask ? (mask[(int64_t)g * N + r] ? 1.f : 0.f) : 1.f;
-    qr = q1[(int64_t)g * N + r] * mk;
-  }
-  const float own = (p == 0) ? 1.f : 0.f;      // count each row once in reductions
-  const float nrm = sqrtf(group_sum<TPG>(own * qr * qr, red, flip, grp, wg, lane));
-  const int nreal = (int)(group_sum<TPG>(own * mk, red, flip, grp, wg, lane) + 0.5f);
-  qr = qr / nrm;
-  if (r >= N) qr = 0.f;
-  if (p == 0) { Qs[r] = qr; qs[r] = qr; }
-  const float qq0 = group_sum<TPG>(own * qr * qr, red, flip, grp, wg, lane);
-  if (t == 0) qq[0] = qq0;
-  group_bar<TPG>(grp);
-
-  float q_prev = 0.f, beta_prev = 0.f, valid = 1.f;
-  int count = 0;
-  for (int i = 0; i < iters; ++i) {
-    // z_r = sum_c A[r][c] q[c]
-    float z = 0.f;
-    {
-      // four independent partial sums: one accumulator would be a 128-deep dependent FMA chain
-      float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
-      const float4* q4 = reinterpret_cast<const float4*>(qs + p * CW);
-#pragma unroll
-      for (int c = 0; c < CR / 4; ++c) {
-        const float4 v = q4[c];
-        z0 = fmaf(a[4 * c + 0], v.x, z0); z1 = fmaf(a[4 * c + 1], v.y, z1);
-        z2 = fmaf(a[4 * c + 2], v.z, z2); z3 = fmaf(a[4 * c + 3], v.w, z3);
-      }
-      if (CS) {
-        const float4* a4 = reinterpret_cast<const float4*>(As + (size_t)t * ASP);
-#pragma unroll 4
-        for (int c = 0; c < CS / 4; ++c) {
-          const float4 v = q4[CR / 4 + c], w = a4[c];
-          z0 = fmaf(w.x, v.x, z0); z1 = fmaf(w.y, v.y, z1); z2 = fmaf(w.z, v.z, z2); z3 = fmaf(w.w, v.w, z3);
-        }
-      }
-      z = (z0 + z1) + (z2 + z3);
-#pragma unroll
-      for (int o = 1; o < TPR; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-    }
-    const float alpha = group_sum<TPG>(own * qr * z, red, flip, grp, wg, lane);
-    z = z - alpha * qr - beta_prev * q_prev;
-    if (i > 0) {
-      for (int pass = 0; pass < 2; ++pass) {
-        if (p == 0) zs[r] = z;
-        group_bar<TPG>(grp);
-        for (int j = wg; j < i; j += TPG / 32) {
-          const float* qj = Qs + (size_t)j * NP;
-          float sdot = 0.f;
-#pragma unroll
-          for (int n = 0; n < NP / 32; ++n) sdot = fmaf(zs[lane + 32 * n], qj[lane + 32 * n], sdot);
-          sdot = lnb::warp_sum(sdot);
-          if (lane == 0) cs[j] = sdot / (qq[j] + kEps);
-        }
-        group_bar<TPG>(grp);
-        {
-          float d0 = 0.f, d1 = 0.f;                  // two chains instead of one of length i
-          int j = 0;
-          for (; j + 1 < i; j += 2) {
-            d0 = fmaf(cs[j], Qs[(size_t)j * NP + r], d0);
-            d1 = fmaf(cs[j + 1], Qs[(size_t)(j + 1) * NP + r], d1);
-          }
-          if (j < i) d0 = fmaf(cs[j], Qs[(size_t)j * NP + r], d0);
-          z -= d0 + d1;
-        }
-      }
-    }
-    const float beta = sqrtf(group_sum<TPG>(own * z * z, red, flip, grp, wg, lane));
-    valid = (beta >= kBetaLowerBound) ? valid : 0.f;
-    count += (valid != 0.f) ? 1 : 0;
-    const float qn = (z * valid) / (beta + kEps);
-    const float qqn = group_sum<TPG>(own * qn * qn, red, flip, grp, wg, lane);
-    if (p == 0) { Qs[(size_t)(i + 1) * NP + r] = qn; qs[r] = qn; }
-    if (t == 0) { al[i] = alpha; be[i] = beta; qq[i + 1] = qqn; }
-    group_bar<TPG>(grp);
-    q_prev = qr; qr = qn; beta_prev = beta;
-  }
-
-  if (!live) return;
-  const int idx = count < nreal ? count : nreal;
-  if (t == 0) idx_out[g] = idx;
-  for (int k = t; k < K; k += TPG) {
-    alpha_out[(int64_t)g * K + k] = (k < iters && k < idx) ? al[k] : 0.f;
-    beta_out[(int64_t)g * K + k] = (k < iters - 1 && k < idx) ? be[k] : 0.f;
-  }
-  float* Tg = T + (int64_t)g * K * K;
-  for (int e = t; e < K * K; e += TPG) {
-    const int rr = e / K, c = e % K;
-    float v = 0.f;
-    if (rr == c) v = (rr < iters && rr < idx) ? al[rr] : 0.f;
-    else if (c == rr + 1) v = (rr < iters - 1 && rr < idx) ? be[rr] : 0.f;
-    else if (rr == c + 1) v = (c < iters - 1 && c < idx) ? be[c] : 0.f;
-    Tg[e] = v;
-  }
-  float* Qg = Q + (int64_t)g * N * K;
-  for (int e = t; e < N * K; e += TPG) {
-    const int n = e / K, k = e % K;
-    float v = 0.f;
-    if (k < iters && k < idx && n < idx) v = Qs[(size_t)k * NP + n];
-    Qg[e] = v;
-  }
-}
-
-template <int NP, int TPG>
-size_t resident_smem(int N, int K) {
-  const int iters = N < K ? N : K;
-  constexpr int TPR = TPG / NP, CW = NP / TPR, CS = CW > 64 ? CW - 64 : 0, ASP = CS ? CS + 4 : 0;
-  const size_t per_graph = ((size_t)(iters + 1) * NP + 2 * NP + 3 * K + (K + 1) + 32 + (size_t)TPG * ASP + 3) & ~size_t(3);
-  return per_graph * (512 / TPG) * sizeof(float);
-}
-
-template <int NP, int TPG>
-int launch_resident(cudaStream_t s, const float* A, const uint8_t* mask, const float* q1, int B,
-                    int N, int K, float* T, float* Q, float* alpha, float* beta, int32_t* idx) {
-  const size_t shm = resident_smem<NP, TPG>(N, K);
-  if (shm > 227 * 1024) return 0;
-  auto kern = lanczos_resident_kernel<NP, TPG>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-  kern<<<lnb::ceil_div(B, 512 / TPG), 512, shm, s>>>(A, mask, q1, B, N, K, T, Q, alpha, beta, idx);
-  return 1;
-}
-
-// ------------------------------------------------------------------------------------------
 // Ritz pairs: implicit-shift QL on the symmetric tridiagonal (alpha, beta), Givens rotations
 // applied to the rows of Z (initialised to Q) so the result is V = Q S directly.
 // One group of GW warps per graph; every warp redundantly carries the (tiny) scalar
@@ -458,33 +252,36 @@ tridiag_ritz_kernel(const float* __restrict__ alpha, const float* __restrict__ b
       int i = m - 1;
       bool underflow = false;
       for (; i >= l; --i) {
-        float f = s * e[i];
-        float b = c * e[i];
+        // every lane carries the recurrence; lane 0 alone stores, after all lanes have read this row
+        const float ei = e[i], di1 = d[i + 1], di = d[i];
+        __syncwarp();
+        float f = s * ei;
+        float b = c * ei;
         r = sqrtf(f * f + gq * gq);
-        e[i + 1] = r;
         if (r == 0.f) {
-          d[i + 1] -= p;
-          e[m] = 0.f;
+          if (lane == 0) { e[i + 1] = r; d[i + 1] = di1 - p; e[m] = 0.f; }
           underflow = true;
           break;
         }
         s = f / r;
         c = gq / r;
-        gq = d[i + 1] - p;
-        r = (d[i] - gq) * s + 2.f * c * b;
-        p = s * r;
-        d[i + 1] = gq + p;
-        gq = c * r - b;
+        gq = di1 - p;
+        const float rr = (di - gq) * s + 2.f * c * b;
+        p = s * rr;
+        if (lane == 0) { e[i + 1] = r; d[i + 1] = gq + p; }
+        gq = c * rr - b;
         for (int n = tg; n < N; n += gthreads) {
           float z1 = Zs[n * KP + i + 1], z0 = Zs[n * KP + i];
           Zs[n * KP + i + 1] = s * z0 + c * z1;
           Zs[n * KP + i] = c * z0 - s * z1;
         }
       }
-      if (underflow) continue;
-      d[l] -= p;
-      e[l] = gq;
-      e[m] = 0.f;
+      if (!underflow) {
+        const float dl = d[l];
+        __syncwarp();
+        if (lane == 0) { d[l] = dl - p; e[l] = gq; e[m] = 0.f; }
+      }
+      __syncwarp();
     }
     if (fail) break;
   }
@@ -584,14 +381,13 @@ int lnb_lanczos_tridiag(lnb_stream_t stream, const float* A, const uint8_t* mask
   if (B == 0) return LNB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int iters = N < K ? N : K;
-  if (N <= 32 && K <= 64) {
-    // small graphs: the fused kernel without its QL stage (operator rows loaded coalesced and packed
-    // on chip -- a dense 32 x 32 operator fits its pool --, butterfly projections)
-    return lnb_lanczos_ritz(stream, A, mask, q1, B, N, K, 0, T, Q, alpha, beta, idx, nullptr, nullptr, nullptr);
-  } else if (N <= 64 && launch_resident<64, 128>(s, A, mask, q1, B, N, K, T, Q, alpha, beta, idx)) {
-  } else if (N <= 128 && launch_resident<128, 512>(s, A, mask, q1, B, N, K, T, Q, alpha, beta, idx)) {
-  } else if (N <= 256 && launch_resident<256, 512>(s, A, mask, q1, B, N, K, T, Q, alpha, beta, idx)) {
-  } else {
+  if (N <= 1024 && K <= 64) {
+    // the fused kernel without its QL stage: operator rows loaded coalesced ONCE and packed on chip,
+    // butterfly projections (it replaced the round-1 warp / resident-operator kernels at every size)
+    const int rc = lnb_lanczos_ritz(stream, A, mask, q1, B, N, K, 0, T, Q, alpha, beta, idx, nullptr, nullptr, nullptr);
+    if (rc != LNB_ERR_UNSUPPORTED) return rc;
+  }
+  {
     const int NP = (N + 3) & ~3;
     size_t base = ((size_t)(iters + 1) * NP + NP + 4 * (size_t)K + 1 + 32) * sizeof(float);
     size_t stage = (size_t)N * (N + 1) * sizeof(float);

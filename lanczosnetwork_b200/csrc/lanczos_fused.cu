@@ -490,8 +490,13 @@ lanczos_ritz_kernel(const FusedParams P) {
     // The dependent chain of one rotation is kept to ~8 instructions: rsqrt + one Newton step
     // instead of sqrt and two divisions, d / e of the next rotation prefetched, the search for the
     // small sub-diagonal done by the whole warp at once.
+    // Within a sweep every read of d / e is of a value from BEFORE the sweep, so lane 0 stores the new
+    // values into shadow rows (the dead projection scratch) and the warp commits them after the sweep:
+    // no lane can ever read an entry another lane has already overwritten, without a barrier per rotation.
     float* d = al;
     float* e = be;                               // e[K-1] = 0 by construction
+    float* d2 = cs;
+    float* e2 = iq;
     const bool act0 = lane < K, act1 = lane + 32 < K;
     for (int l = 0; l < K; ++l) {
       int sweeps = 0;
@@ -525,7 +530,7 @@ lanczos_ritz_kernel(const FusedParams P) {
           const float b = c * e_i;
           const float r2 = fmaf(f, f, gq * gq);
           if (r2 < 1.0e-36f) {                   // f = g = 0 up to underflow: the reference QL's r == 0 exit
-            if (lane == 0) { e[i + 1] = 0.f; d[i + 1] = d_ip1 - p; e[m] = 0.f; }
+            if (lane == 0) { e2[i + 1] = 0.f; d2[i + 1] = d_ip1 - p; e2[m] = 0.f; }
             underflow = true;
             break;
           }
@@ -538,7 +543,7 @@ lanczos_ritz_kernel(const FusedParams P) {
           const float rr = fmaf(2.f * c, b, (d_i - g2) * s);
           p = s * rr;
           gq = fmaf(c, rr, -b);
-          if (lane == 0) { e[i + 1] = r2 * rinv; d[i + 1] = g2 + p; }
+          if (lane == 0) { e2[i + 1] = r2 * rinv; d2[i + 1] = g2 + p; }
           {
             const float lo0 = act0 ? Zt[(size_t)i * KR + lane] : 0.f;
             if (act0) Zt[(size_t)(i + 1) * KR + lane] = fmaf(s, lo0, c * hi0);
@@ -554,7 +559,9 @@ lanczos_ritz_kernel(const FusedParams P) {
         // column i+1 (= l after a complete sweep) still lives in the register
         if (act0) Zt[(size_t)(i + 1) * KR + lane] = hi0;
         if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = hi1;
-        if (!underflow && lane == 0) { d[l] = d_ip1 - p; e[l] = gq; e[m] = 0.f; }
+        if (!underflow && lane == 0) { d2[l] = d_ip1 - p; e2[l] = gq; e2[m] = 0.f; }
+        __syncwarp();
+        for (int j = i + 1 + lane; j <= m; j += 32) { d[j] = d2[j]; e[j] = e2[j]; }   // rows [i+1, m] changed
         __syncwarp();
       }
       if (fail) break;

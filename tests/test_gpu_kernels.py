@@ -685,10 +685,11 @@ def test_filter_mlp_chain_matches_fp64():
       assert torch.equal(out2[l][b, :kk], out[l][b, :kk])
 
 
-@pytest.mark.parametrize('N,K,B', [(200, 40, 5), (256, 40, 3), (129, 20, 4), (33, 40, 9)])
-def test_lanczos_resident_operator_vs_oracle(N, K, B):
-  """Resident-operator kernel (32 < N <= 256) against the fp64 oracle with the fp32 oracle's own
-  error as the yardstick (no reference output exists at these sizes in the goldens)."""
+@pytest.mark.parametrize('N,K,B', [(200, 40, 5), (256, 40, 3), (129, 20, 4), (33, 40, 9), (100, 70, 3)])
+def test_lanczos_tridiag_mid_sizes_and_fallback_vs_oracle(N, K, B):
+  """lnb_lanczos_tridiag above the QM8 size (the fused kernel without its QL stage; K = 70 > 64 takes
+  the CTA-per-graph fallback) against the fp64 oracle with the fp32 oracle's own error as the
+  yardstick (no reference output exists at these sizes in the goldens)."""
   import networkx as nx
   from lanczosnetwork_b200 import data
   rng = np.random.RandomState(N + K)

@@ -12,7 +12,7 @@ timeout 900 $CS --tool memcheck --error-exitcode 9 \
   python -m pytest tests/test_gpu_models.py -m gpu -x -q -k "sparse or online or golden" > gpurun_out/r2u_memcheck_models.log 2>&1
 echo "memcheck models rc=$?" | tee -a gpurun_out/r2u_rc.txt
 tail -4 gpurun_out/r2u_memcheck_models.log
-timeout 1200 $CS --tool racecheck --racecheck-report all --error-exitcode 9 \
+timeout 1200 $CS --tool racecheck --racecheck-report all --print-limit 200000 --error-exitcode 9 \
   python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "fused_lanczos_ritz_matches or fused_lanczos_ritz_edges or graph_messages or operator_chain" > gpurun_out/r2u_racecheck.log 2>&1
 echo "racecheck rc=$?" | tee -a gpurun_out/r2u_rc.txt
 grep -c "Race reported" gpurun_out/r2u_racecheck.log; tail -4 gpurun_out/r2u_racecheck.log
