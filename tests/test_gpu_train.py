@@ -27,7 +27,7 @@ def _oracle_grads(forward, params, monkeypatch):
   monkeypatch.setattr(orc, '_cast', lambda p, dtype: p)
   loss = forward(p64)
   loss.backward()
-  return float(loss), {k: v.grad for k, v in p64.items() if v.grad is not None}
+  return float(loss.detach()), {k: v.grad for k, v in p64.items() if v.grad is not None}
 
 
 def _compare(mod, grads_ref, rel=2e-3):
