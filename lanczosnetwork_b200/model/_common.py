@@ -139,12 +139,22 @@ class SpectralNetBase(nn.Module):
     return dict(st, live=len(self.__dict__.get('_graphs', {})),
                 live_resident=len(self.__dict__.get('_graphs_resident', {})))
 
+  def _has_trainable_parameters(self):
+    """nn.DataParallel replicas hold their parameter copies as plain attributes (``parameters()`` is
+    empty there, the copies are listed in ``_former_parameters``): look at both."""
+    for m in self.modules():
+      for group in (m._parameters, getattr(m, '_former_parameters', None) or {}):
+        for p in group.values():
+          if p is not None and p.requires_grad:
+            return True
+    return False
+
   def _check_mode(self):
     """Returns True when this call has to be differentiable (autograd on, trainable parameters):
     the forward then runs the training path of lanczosnetwork_b200.train (unfused, every
     contraction and its adjoint in this library's kernels) instead of the fused inference kernels.
     Models without a training path raise."""
-    if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+    if torch.is_grad_enabled() and self._has_trainable_parameters():
       if not hasattr(self, '_train_impl'):
         raise NotImplementedError(
             '%s has no training path in this build: call it under torch.no_grad() (as '

@@ -254,3 +254,42 @@ def test_graphed_training_step_matches_eager_steps(opt_name):
     for (n, p), (_, q) in zip(graphed.named_parameters(), eager.named_parameters()):
       np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=n)
   assert step.replays == 6
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (the reference runner\'s gpus: [0, 1])')
+def test_data_parallel_two_gpus_inference_and_training():
+  """How the reference goes multi-GPU (runner/qm8_runner.py:64-66,291-292): nn.DataParallel over the module,
+  scatter of the batch, per-replica forward in threads, gather of (score, loss).  Scores of the two halves
+  equal the single-GPU forward; the gradients that flow back through the replicas to the master
+  parameters equal the single-GPU gradients of the same batch (equal halves: mean of the two MSEs)."""
+  g = load_golden('lanczosnet_qm8.npz')
+  cfg = configs.qm8_lanczos_net()
+  base = LanczosNet(cfg)
+  params = deterministic_state_dict(base, 21)
+  base.load_state_dict(params)
+  base = base.cuda(0)
+  args = [_t(g[k]).cuda(0) for k in ('node_feat', 'L', 'D', 'V')]
+  label, mask = _t(g['label']).cuda(0), _t(g['node_mask']).cuda(0)
+  base.eval()
+  with torch.no_grad():
+    ref = base(*args, mask=mask)
+  base.train()
+  _, loss1 = base(*args, label=label, mask=mask)
+  loss1.backward()
+  grads1 = {n: p.grad.detach().clone() for n, p in base.named_parameters()}
+  base.zero_grad()
+
+  dp = torch.nn.DataParallel(base, device_ids=[0, 1])
+  dp.eval()
+  with torch.no_grad():
+    score, loss = dp(*args, label=label, mask=mask)
+  assert score.shape == ref.shape and loss.numel() == 2           # one loss per replica
+  torch.testing.assert_close(score, ref, rtol=1e-5, atol=1e-6)
+  dp.train()
+  _, loss2 = dp(*args, label=label, mask=mask)
+  loss2.float().mean().backward()                                   # runner/qm8_runner.py:243-247
+  assert abs(float(loss2.mean().detach()) - float(loss1.detach())) <= 1e-5 * max(1.0, abs(float(loss1.detach())))
+  for n, p in base.named_parameters():
+    assert p.grad is not None, n
+    scale = float(grads1[n].abs().max()) + 1e-12
+    assert float((p.grad - grads1[n]).abs().max()) / scale <= 1e-4, n
