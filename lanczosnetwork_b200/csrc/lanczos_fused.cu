@@ -47,6 +47,10 @@ __device__ __forceinline__ void gbar(int grp) {
   else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(TPG) : "memory");
 }
 
+// producer / consumer hand-over between the two QL warps of a group (named barriers, 64 threads)
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
 // sums of two values over the TPG threads of a graph; identical result (same order) in every thread
 template <int TPG>
 __device__ __forceinline__ float2 gsum2(float a, float b, float* red, int& flip, int grp, int wg,
@@ -478,7 +482,13 @@ lanczos_ritz_kernel(const FusedParams P) {
   float* Zt = pval;                              // K x KR
   const int KR = K | 1;
   float* Zr = Zt + (((size_t)K * KR + 3) & ~(size_t)3);   // K x K4, 16-byte aligned rows
-  int* rank = reinterpret_cast<int*>(Zr + (size_t)K * K4);   // K
+  int* rank = reinterpret_cast<int*>(Zr + (size_t)K * K4);   // K4
+  // groups of >= 2 warps split the eigensolve: warp 0 carries the scalar recurrence and publishes the
+  // rotations (s, c) of a sweep; warp 1 applies them to Z one sweep behind (double-buffered ring)
+  constexpr bool kSplitQL = TPG >= 64;
+  float2* scr = reinterpret_cast<float2*>(rank + K4);         // [2][K] rotations of a sweep, indexed by row
+  int* sdesc = reinterpret_cast<int*>(scr + 2 * (size_t)K);   // [2][2] {m, first rotated row}; m < 0: done
+  const int bar0 = 4 + 4 * grp;                               // FULL[0..1] = bar0 + b, EMPTY[0..1] = bar0 + 2 + b
   for (int e = t; e < K * KR; e += TPG) {
     const int i = e / KR, k = e - i * KR;
     Zt[e] = (i == k) ? 1.f : 0.f;
@@ -498,6 +508,7 @@ lanczos_ritz_kernel(const FusedParams P) {
     float* d2 = cs;
     float* e2 = iq;
     const bool act0 = lane < K, act1 = lane + 32 < K;
+    int nsw = 0;                                 // sweeps published so far (split mode)
     for (int l = 0; l < K; ++l) {
       int sweeps = 0;
       while (true) {
@@ -521,8 +532,14 @@ lanczos_ritz_kernel(const FusedParams P) {
         bool underflow = false;
         float d_ip1 = d[m], d_i = d[m - 1], e_i = e[m - 1];
         // rows k = lane (+32) of Z: the value of column i+1 travels in a register between rotations
-        float hi0 = act0 ? Zt[(size_t)m * KR + lane] : 0.f;
-        float hi1 = act1 ? Zt[(size_t)m * KR + lane + 32] : 0.f;
+        float hi0 = 0.f, hi1 = 0.f;
+        const int buf = nsw & 1;
+        if constexpr (kSplitQL) {
+          if (nsw >= 2) pair_sync(bar0 + 2 + buf);            // the consumer is done with sweep nsw - 2
+        } else {
+          hi0 = act0 ? Zt[(size_t)m * KR + lane] : 0.f;
+          hi1 = act1 ? Zt[(size_t)m * KR + lane + 32] : 0.f;
+        }
         for (; i >= l; --i) {
           const float d_n = (i > l) ? d[i - 1] : 0.f;       // prefetch for rotation i-1
           const float e_n = (i > l) ? e[i - 1] : 0.f;
@@ -544,7 +561,9 @@ lanczos_ritz_kernel(const FusedParams P) {
           p = s * rr;
           gq = fmaf(c, rr, -b);
           if (lane == 0) { e2[i + 1] = r2 * rinv; d2[i + 1] = g2 + p; }
-          {
+          if constexpr (kSplitQL) {
+            if (lane == 0) scr[(size_t)buf * K + i] = make_float2(s, c);
+          } else {
             const float lo0 = act0 ? Zt[(size_t)i * KR + lane] : 0.f;
             if (act0) Zt[(size_t)(i + 1) * KR + lane] = fmaf(s, lo0, c * hi0);
             hi0 = fmaf(c, lo0, -s * hi0);
@@ -556,15 +575,28 @@ lanczos_ritz_kernel(const FusedParams P) {
           }
           d_ip1 = d_i; d_i = d_n; e_i = e_n;
         }
-        // column i+1 (= l after a complete sweep) still lives in the register
-        if (act0) Zt[(size_t)(i + 1) * KR + lane] = hi0;
-        if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = hi1;
+        if constexpr (kSplitQL) {
+          if (lane == 0) { sdesc[2 * buf] = m; sdesc[2 * buf + 1] = i + 1; }
+          pair_arrive(bar0 + buf);               // sweep nsw is published (rows i+1 .. m-1 were rotated)
+          ++nsw;
+        } else {
+          // column i+1 (= l after a complete sweep) still lives in the register
+          if (act0) Zt[(size_t)(i + 1) * KR + lane] = hi0;
+          if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = hi1;
+        }
         if (!underflow && lane == 0) { d2[l] = d_ip1 - p; e2[l] = gq; e2[m] = 0.f; }
         __syncwarp();
         for (int j = i + 1 + lane; j <= m; j += 32) { d[j] = d2[j]; e[j] = e2[j]; }   // rows [i+1, m] changed
         __syncwarp();
       }
       if (fail) break;
+    }
+    if constexpr (kSplitQL) {
+      const int buf = nsw & 1;
+      if (nsw >= 2) pair_sync(bar0 + 2 + buf);
+      if (lane == 0) sdesc[2 * buf] = -1;
+      pair_arrive(bar0 + buf);                   // "done"
+      if (nsw >= 1) pair_sync(bar0 + 2 + (buf ^ 1));          // the last sweep's release
     }
     __syncwarp();
     // rank by descending |theta|; ties: ascending signed value, then ascending index
@@ -579,6 +611,32 @@ lanczos_ritz_kernel(const FusedParams P) {
       P.theta[(size_t)g * K + rk] = dj;
     }
     if (lane == 0) P.status[g] = fail | (dense ? 2 : 0);
+  } else if (kSplitQL && wg == 1) {
+    // consumer: the rotations of sweep n on the rows of Z (column k = lane, lane + 32), one sweep behind
+    const bool act0 = lane < K, act1 = lane + 32 < K;
+    for (int n = 0;; ++n) {
+      const int buf = n & 1;
+      pair_sync(bar0 + buf);
+      const int m = sdesc[2 * buf], i_end = sdesc[2 * buf + 1];
+      if (m < 0) break;
+      float hi0 = act0 ? Zt[(size_t)m * KR + lane] : 0.f;
+      float hi1 = act1 ? Zt[(size_t)m * KR + lane + 32] : 0.f;
+      const float2* sc = scr + (size_t)buf * K;
+      for (int i = m - 1; i >= i_end; --i) {
+        const float2 r = sc[i];
+        const float lo0 = act0 ? Zt[(size_t)i * KR + lane] : 0.f;
+        if (act0) Zt[(size_t)(i + 1) * KR + lane] = fmaf(r.x, lo0, r.y * hi0);
+        hi0 = fmaf(r.y, lo0, -r.x * hi0);
+        if (K > 32) {
+          const float lo1 = act1 ? Zt[(size_t)i * KR + lane + 32] : 0.f;
+          if (act1) Zt[(size_t)(i + 1) * KR + lane + 32] = fmaf(r.x, lo1, r.y * hi1);
+          hi1 = fmaf(r.y, lo1, -r.x * hi1);
+        }
+      }
+      if (act0) Zt[(size_t)i_end * KR + lane] = hi0;
+      if (act1) Zt[(size_t)i_end * KR + lane + 32] = hi1;
+      pair_arrive(bar0 + 2 + buf);
+    }
   }
   gbar<TPG>(grp);
   LNB_PHASE(4)
@@ -645,7 +703,7 @@ static bool plan_fused(int N, int K, int tpg, int npt, FusedPlan& pl) {
   int zw = nwg * K4 > NP ? nwg * K4 : NP;
   zw = (zw + 3) & ~3;
   const int fixed = K * NS + NP + zw + 4 * K4 + 4 + 128 + 4;
-  const int ql_words = ((K * (K | 1) + 3) & ~3) + K * K4 + K + 4;
+  const int ql_words = ((K * (K | 1) + 3) & ~3) + K * K4 + K4 + 4 * K + 8;   // Zt, Zr, rank, rotation ring, descriptors
   const int smem_max = 227 * 1024;
   // target capacity: every entry of a dense operator while that is cheap (N <= 48: <= 13.5 KB),
   // else 12 non-zeros per row
