@@ -143,8 +143,20 @@ lanczos_ritz_kernel(const FusedParams P) {
     constexpr int NC4 = NCH >= 4 ? NCH / 4 : 1;
     constexpr int RB = NC4 >= 4 ? 2 : 4;
     int cursor = 0;
+    // rows of the iterations after next are pulled into L2 while this one is packed (one bulk prefetch
+    // per row, no registers): the 16-byte loads below then wait for L2, not for HBM
+    constexpr int PF = 2;
+    const unsigned row_bytes = (unsigned)N * 4u;
+    if (NC4 >= 2 && lane < RB * PF) {
+      const int r = wg + (lane / RB) * NWG * RB + (lane % RB) * NWG;
+      if (r < N) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Ag + (size_t)r * N), "r"(row_bytes) : "memory");
+    }
     for (int r0 = wg; r0 < N; r0 += NWG * RB) {
       float4 v[RB][NC4];
+      if (NC4 >= 2 && lane < RB) {
+        const int r = r0 + PF * NWG * RB + lane * NWG;
+        if (r < N) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Ag + (size_t)r * N), "r"(row_bytes) : "memory");
+      }
 #pragma unroll
       for (int b = 0; b < RB; ++b) {
         const int r = r0 + b * NWG;
