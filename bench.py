@@ -392,27 +392,36 @@ def train_workload(dev, B=64, N=27):
   copt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-4)
   cast = orc._cast
   orc._cast = lambda p_, dtype: p_                 # the oracle detaches its parameters; keep the tape
-  ts = []
+  def cpu_step(b):
+    t0 = time.perf_counter()
+    copt.zero_grad()
+    score = orc.lanczos_net_forward(leaves, spec, b['node_feat'], b['L'], b['D'], b['V'], b['node_mask'])
+    loss = torch.nn.functional.mse_loss(score, torch.from_numpy(b['label']))
+    loss.backward()
+    copt.step()
+    return time.perf_counter() - t0
+
+  # thousands of tiny CPU ops: all cores is far from the best setting, so probe a few thread counts
+  threads_before, cores = torch.get_num_threads(), os.cpu_count() or 1
+  best_t, best_nt = None, threads_before
   try:
-    for i in range(3):
-      b = batches[i % 4]
-      t0 = time.perf_counter()
-      copt.zero_grad()
-      score = orc.lanczos_net_forward(leaves, spec, b['node_feat'], b['L'], b['D'], b['V'], b['node_mask'])
-      loss = torch.nn.functional.mse_loss(score, torch.from_numpy(b['label']))
-      loss.backward()
-      copt.step()
-      ts.append(time.perf_counter() - t0)
+    for nt in sorted(set(min(n, cores) for n in (4, 8, 16, 32))):
+      torch.set_num_threads(nt)
+      cpu_step(batches[0])
+      t = min(cpu_step(batches[1]), cpu_step(batches[2]))
+      if best_t is None or t < best_t:
+        best_t, best_nt = t, nt
   finally:
     orc._cast = cast
-  t_cpu = float(np.median(ts[1:])) * 1e3
+    torch.set_num_threads(threads_before)
+  t_cpu = best_t * 1e3
   del nodes
   return {'config': 'QM8 LanczosNet (config/qm8_lanczos_net.yaml) training step: B=%d, N padded to %d, K=20, Adam lr 1e-4, '
                     'MSE; inputs device resident' % (B, N),
           'ms_eager': t_eager, 'ms_graphed': t_graph, 'molecules_per_s_eager': B / (t_eager * 1e-3),
           'molecules_per_s_graphed': B / (t_graph * 1e-3),
-          'cpu_port': {'ms': t_cpu, 'molecules_per_s': B / (t_cpu * 1e-3), 'threads': torch.get_num_threads(),
-                       'kind': 'port', 'sample': '2 timed steps of autograd over the oracle port (fp32)'},
+          'cpu_port': {'ms': t_cpu, 'molecules_per_s': B / (t_cpu * 1e-3), 'threads': best_nt,
+                       'kind': 'port', 'sample': 'best of 2 timed steps of autograd over the oracle port (fp32) at the best of {4,8,16,32} threads'},
           'graph_replays': step.replays}
 
 

@@ -64,7 +64,7 @@ def test_lanczosnet_gradients_match_fp64_oracle_autograd(monkeypatch):
   loss_ref, grads_ref = _oracle_grads(fwd, params, monkeypatch)
   score, loss = mod(_t(g['node_feat']).to(dev()), _t(g['L']).to(dev()), _t(g['D']).to(dev()),
                     _t(g['V']).to(dev()), label=label.to(dev()), mask=_t(g['node_mask']).to(dev()))
-  assert score.requires_grad and abs(float(loss) - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
+  assert score.requires_grad and abs(float(loss.detach()) - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
   loss.backward()
   _compare(mod, grads_ref)
   # the differentiable forward agrees with the fused inference kernels
