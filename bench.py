@@ -333,6 +333,40 @@ def run_workloads(dev, peaks):
   return out
 
 
+def train_cpu_port(batches, params, spec):
+  """One optimisation step of autograd over the CPU oracle port (fp32, Adam on leaf copies of the same
+  weights): best of 2 timed steps at the best of {4, 8, 16, 32} threads (thousands of tiny CPU ops: all
+  cores is far from the best setting).  Returns (ms per step, threads)."""
+  from oracle import lanczos_oracle as orc
+  leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in params.items()}
+  copt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-4)
+  cast = orc._cast
+  orc._cast = lambda p_, dtype: p_                 # the oracle detaches its parameters; keep the tape
+
+  def cpu_step(b):
+    t0 = time.perf_counter()
+    copt.zero_grad()
+    score = orc.lanczos_net_forward(leaves, spec, b['node_feat'], b['L'], b['D'], b['V'], b['node_mask'])
+    loss = torch.nn.functional.mse_loss(score, torch.from_numpy(b['label']))
+    loss.backward()
+    copt.step()
+    return time.perf_counter() - t0
+
+  threads_before, cores = torch.get_num_threads(), os.cpu_count() or 1
+  best_t, best_nt = None, threads_before
+  try:
+    for nt in sorted(set(min(n, cores) for n in (4, 8, 16, 32))):
+      torch.set_num_threads(nt)
+      cpu_step(batches[0])
+      t = min(cpu_step(batches[1]), cpu_step(batches[2]))
+      if best_t is None or t < best_t:
+        best_t, best_nt = t, nt
+  finally:
+    orc._cast = cast
+    torch.set_num_threads(threads_before)
+  return best_t * 1e3, best_nt
+
+
 def train_workload(dev, B=64, N=27):
   """one optimisation step (forward, MSE loss, backward, Adam) of config #2's LanczosNet at the
   reference's training batch size (config/qm8_lanczos_net.yaml:33), every batch padded to N nodes.  Three
@@ -385,36 +419,7 @@ def train_workload(dev, B=64, N=27):
 
   t_graph = time_events(graphed, 50, 5)
   nodes = step.graph  # keep alive
-  # CPU: autograd over the oracle port, Adam on leaf copies of the same weights
-  from oracle import lanczos_oracle as orc
-  spec = oracle_spec(mod, 'LanczosNet')
-  leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in params.items()}
-  copt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-4)
-  cast = orc._cast
-  orc._cast = lambda p_, dtype: p_                 # the oracle detaches its parameters; keep the tape
-  def cpu_step(b):
-    t0 = time.perf_counter()
-    copt.zero_grad()
-    score = orc.lanczos_net_forward(leaves, spec, b['node_feat'], b['L'], b['D'], b['V'], b['node_mask'])
-    loss = torch.nn.functional.mse_loss(score, torch.from_numpy(b['label']))
-    loss.backward()
-    copt.step()
-    return time.perf_counter() - t0
-
-  # thousands of tiny CPU ops: all cores is far from the best setting, so probe a few thread counts
-  threads_before, cores = torch.get_num_threads(), os.cpu_count() or 1
-  best_t, best_nt = None, threads_before
-  try:
-    for nt in sorted(set(min(n, cores) for n in (4, 8, 16, 32))):
-      torch.set_num_threads(nt)
-      cpu_step(batches[0])
-      t = min(cpu_step(batches[1]), cpu_step(batches[2]))
-      if best_t is None or t < best_t:
-        best_t, best_nt = t, nt
-  finally:
-    orc._cast = cast
-    torch.set_num_threads(threads_before)
-  t_cpu = best_t * 1e3
+  t_cpu, best_nt = train_cpu_port(batches, params, oracle_spec(mod, 'LanczosNet'))
   del nodes
   return {'config': 'QM8 LanczosNet (config/qm8_lanczos_net.yaml) training step: B=%d, N padded to %d, K=20, Adam lr 1e-4, '
                     'MSE; inputs device resident' % (B, N),
