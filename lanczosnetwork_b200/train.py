@@ -7,7 +7,8 @@ forward and of its adjoint goes through the C ABI:
 
   * dense layers ``act(x W^T + b)`` and their two adjoint products (``g W`` and ``g^T x``): the
     tcgen05 3xTF32 kernel (lnb_linear_tf32x3) -- the big Linear of the graph-conv layer is 97 % of
-    the flops of a training step;
+    the flops of a training step -- or, for layers too small to amortise that kernel's set-up, the
+    strided fp32 GEMM reading W / W^T / g^T in place;
   * operator products ``L_e X``, ``L_e^T G`` (channel-innermost operators read in place through
     their strides), ``V^T X``, ``V diag(f) U`` and their adjoints: the strided batched GEMM
     (lnb_batched_gemm);
@@ -42,14 +43,34 @@ def _matmul_nt(a, w):
   return ops.linear_tf32x3(a, w_hi, w_lo, None, False)
 
 
+# Below this many flops (2 M N K) a dense layer is launch bound on the persistent tcgen05 kernel (TMEM
+# allocation, barrier set-up, operand splits, padded / transposed copies for its two adjoint products):
+# the strided fp32 GEMM reads W, W^T, g^T in place and is exact fp32.  At the reference's batch size (64
+# molecules) this is every layer but the graph-conv Linear, which keeps 95 % of the flops on the tensor cores.
+_SMALL_DENSE_FLOPS = 1.5e8
+
+
+def _small_gemm(A, a_str, Bm, b_str, M, N, K, bias=None, relu=False):
+  C = torch.empty((M, N), device=A.device, dtype=torch.float32)
+  ops.bgemm(A, (0, 0) + a_str, Bm, (0, 0) + b_str, C, (0, 0, N, 1), 1, 1, M, N, K, bias=bias, relu=relu)
+  return C
+
+
 class _Dense(torch.autograd.Function):
   """y = act(x W^T + b): nn.Linear (+ ReLU) of model/lanczos_net.py:109-113,180-181,188-189."""
 
   @staticmethod
   def forward(ctx, x, weight, bias, relu):
-    xp, wp = _pad_cols(x.float()), _pad_cols(weight.float())
-    w_hi, w_lo = ops.split_tf32(wp)
-    y = ops.linear_tf32x3(xp, w_hi, w_lo, bias, relu)
+    M, K = x.shape
+    N = weight.shape[0]
+    ctx.small = 2.0 * M * N * K < _SMALL_DENSE_FLOPS
+    if ctx.small:
+      x, weight = x.float().contiguous(), weight.float().contiguous()
+      y = _small_gemm(x, (K, 1), weight, (1, K), M, N, K, bias.float().contiguous() if bias is not None else None, relu)
+    else:
+      xp, wp = _pad_cols(x.float()), _pad_cols(weight.float())
+      w_hi, w_lo = ops.split_tf32(wp)
+      y = ops.linear_tf32x3(xp, w_hi, w_lo, bias, relu)
     ctx.relu = bool(relu)
     ctx.save_for_backward(x, weight, y if relu else None)
     ctx.has_bias = bias is not None
@@ -62,10 +83,14 @@ class _Dense(torch.autograd.Function):
     if ctx.relu:
       gy = gy * (y > 0).to(gy.dtype)
     gx = gw = gb = None
-    if ctx.needs_input_grad[0]:
-      gx = _matmul_nt(gy, weight.t())[:, :x.shape[1]]               # g W
-    if ctx.needs_input_grad[1]:
-      gw = _matmul_nt(gy.t(), x.t())[:, :weight.shape[1]]           # g^T x
+    M, K = x.shape
+    N = weight.shape[0]
+    if ctx.needs_input_grad[0]:                                     # g W
+      gx = (_small_gemm(gy, (N, 1), weight, (K, 1), M, K, N) if ctx.small
+            else _matmul_nt(gy, weight.t())[:, :K])
+    if ctx.needs_input_grad[1]:                                     # g^T x
+      # few output tiles, long contraction over the rows: the tensor-core kernel wins at every size
+      gw = _matmul_nt(gy.t(), x.t())[:, :K]
     if ctx.has_bias and ctx.needs_input_grad[2]:
       gb = gy.sum(dim=0)
     return gx, gw, gb, None
