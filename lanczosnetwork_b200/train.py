@@ -498,8 +498,8 @@ class GraphedStep:
     torch.cuda.current_stream(dev).wait_stream(side)
     self.graph = torch.cuda.CUDAGraph()
     optimizer.zero_grad(set_to_none=True)
-    with torch.cuda.graph(self.graph):
-      self.score, self.loss = self._body(zero=False)
+    with torch.cuda.graph(self.graph, stream=side):          # same stream as the warm-up: the parameters'
+      self.score, self.loss = self._body(zero=False)         # AccumulateGrad nodes were created on it
     with torch.no_grad():                                    # roll the warm-up steps back, in place
       for p, sp in zip(params, saved_p):
         p.copy_(sp)
