@@ -220,3 +220,77 @@ def test_sparse_collate_and_pack_describe_the_same_batch():
   # the fp64 table the device kernel multiplies with is numpy's own deg ** -0.5
   deg = np.arange(1, 12, dtype=np.float64)
   assert np.array_equal(np.power(deg, -0.5), deg ** -0.5)
+
+
+def test_graphed_step_refuses_what_it_cannot_capture():
+  """train.GraphedStep argument checks (no GPU needed): a module without a host-free training forward,
+  a missing label, a module that is not on CUDA."""
+  import torch
+  from lanczosnetwork_b200 import configs
+  from lanczosnetwork_b200.model import AdaLanczosNet, LanczosNet
+  from lanczosnetwork_b200.train import GraphedStep
+  small = dict(num_layer=1, hidden_dim=[16])
+  ln = LanczosNet(configs.qm8_lanczos_net(**small))
+  opt = torch.optim.SGD(ln.parameters(), lr=0.1)
+  x = (torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 3, 3, 7), torch.zeros(2, 20), torch.zeros(2, 3, 20))
+  with pytest.raises(TypeError):
+    GraphedStep(torch.nn.Linear(2, 2), opt, x, {'label': torch.zeros(2, 16)})
+  ada = AdaLanczosNet(configs.qm8_ada_lanczos_net(num_eig_vec=4, long_diffusion_dist=[1], short_diffusion_dist=[], **small))
+  with pytest.raises(TypeError):
+    GraphedStep(ada, opt, x[:2], {'label': torch.zeros(2, 16)})
+  with pytest.raises(ValueError):
+    GraphedStep(ln, opt, x, {'mask': torch.ones(2, 3)})
+  with pytest.raises(RuntimeError):            # CPU module: no CPU fallback anywhere
+    GraphedStep(ln, opt, x, {'label': torch.zeros(2, 16)})
+
+
+def test_trainable_parameter_detection_sees_data_parallel_replicas():
+  """nn.DataParallel replicas keep their parameter copies in ``_former_parameters`` (``parameters()`` is
+  empty there): the training path must still be selected for them (regression: two-GPU training through
+  the reference runner's DataParallel took the inference path)."""
+  import torch
+  from lanczosnetwork_b200 import configs
+  from lanczosnetwork_b200.model import LanczosNet
+  mod = LanczosNet(configs.qm8_lanczos_net(num_layer=1, hidden_dim=[16]))
+  assert mod._has_trainable_parameters()
+  # build the replica tree the way torch.nn.parallel.replicate does: children replicated, parameters demoted
+  def demote(m):
+    r = m._replicate_for_data_parallel()                       # empties r._parameters
+    r._former_parameters = {}
+    for k, c in m._modules.items():
+      r._modules[k] = None if c is None else demote(c)
+    for k, p in m._parameters.items():
+      if p is None:
+        r._parameters[k] = None
+      else:
+        cp = p.detach().clone().requires_grad_(p.requires_grad)   # stand-in for the Broadcast output
+        setattr(r, k, cp)
+        r._former_parameters[k] = cp
+    return r
+  rep = demote(mod)
+  assert list(rep.parameters()) == [] and rep._has_trainable_parameters()
+  for p in mod.parameters():
+    p.requires_grad_(False)
+  assert not demote(mod)._has_trainable_parameters() and not mod._has_trainable_parameters()
+
+
+def test_bench_cpu_training_port_steps_and_restores_threads():
+  """bench.train_cpu_port (the CPU leg of the train_qm8 workload) on a tiny model: returns a positive
+  time and a thread count, leaves torch's thread setting and the oracle's cast hook as they were."""
+  import torch
+  import bench
+  from helpers import deterministic_state_dict, oracle_spec
+  from lanczosnetwork_b200 import configs
+  from lanczosnetwork_b200.model import LanczosNet
+  from oracle import lanczos_oracle as orc
+  mod = LanczosNet(configs.qm8_lanczos_net(num_layer=1, hidden_dim=[16]))
+  params = deterministic_state_dict(mod, 1)
+  batches = []
+  for i in range(3):
+    b = data.collate(data.synthetic_qm8_samples(4, seed=i), 20, num_nodes=27)
+    b['label'] = np.random.RandomState(i).randn(4, 16).astype(np.float32)
+    batches.append(b)
+  nt, cast = torch.get_num_threads(), orc._cast
+  ms, threads = bench.train_cpu_port(batches, params, oracle_spec(mod, 'LanczosNet'))
+  assert ms > 0 and threads >= 1 and torch.get_num_threads() == nt and orc._cast is cast
+  assert batches[0]['L'].shape[1] == 27                      # collate(num_nodes=) pads to the fixed node count
