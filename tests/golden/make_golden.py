@@ -299,10 +299,60 @@ def golden_ada_forward(weight_seed=999):
        torch_seed=np.array(seed))
 
 
+def golden_train_grads():
+  """Gradients of the REFERENCE classes' own autograd (runner/qm8_runner.py:226-247: train mode, MSE
+  loss, ``train_loss.backward()``) on the inputs of the forward goldens: pins the oracle's differentiable
+  use (tests/test_oracle_golden.py), which in turn is what the GPU training tests are checked against.
+  Only the loss and a digest per parameter (sum, sum of squares, the first 8 entries) are stored."""
+  out = {}
+
+  def digest(prefix, model, loss):
+    out[prefix + '_loss'] = np.array(float(loss))
+    for name, p in model.named_parameters():
+      g = p.grad.detach().double().numpy().reshape(-1)
+      out['%s|%s' % (prefix, name)] = np.concatenate([[g.sum(), (g * g).sum()], g[:8]])
+
+  g = np.load(os.path.join(HERE, 'lanczosnet_qm8.npz'))
+  nf, L, D, V = [torch.from_numpy(g[k]) for k in ('node_feat', 'L', 'D', 'V')]
+  label, mask = torch.from_numpy(g['label']), torch.from_numpy(g['node_mask'])
+  cfg = configs.qm8_lanczos_net(num_layer=2, hidden_dim=[64, 64])
+  model = LanczosNet(cfg)
+  model.load_state_dict(deterministic_state_dict(model, 11))
+  model.train()
+  _, loss = model(nf, L, D, V, label=label, mask=mask)
+  loss.backward()
+  digest('lanczosnet', model, loss)
+
+  gcn = GCN(configs.qm8_gcn(num_layer=2, hidden_dim=[64, 64]))
+  gcn.load_state_dict(deterministic_state_dict(gcn, 9))
+  gcn.train()
+  _, loss = gcn(nf, L, label=label, mask=mask)
+  loss.backward()
+  digest('gcn', gcn, loss)
+
+  a = np.load(os.path.join(HERE, 'ada_forward_small.npz'))
+  cfg_a = configs.qm8_ada_lanczos_net(num_layer=2, hidden_dim=[32, 32], num_eig_vec=8,
+                                      long_diffusion_dist=[2, 5], short_diffusion_dist=[1, 3])
+  ada = AdaLanczosNet(cfg_a)
+  ada.load_state_dict(deterministic_state_dict(ada, int(a['weight_seed'])))
+  ada.train()
+  lab = torch.from_numpy(np.random.RandomState(0).randn(a['score'].shape[0], a['score'].shape[1]).astype(np.float32))
+  torch.manual_seed(int(a['torch_seed']))
+  _, loss = ada(torch.from_numpy(a['node_feat']), torch.from_numpy(a['L']), label=lab,
+                mask=torch.from_numpy(a['node_mask']))
+  loss.backward()
+  digest('ada', ada, loss)
+  save('train_grads.npz', **out)
+
+
 if __name__ == '__main__':
+  if 'grads-only' in sys.argv:                     # needs the forward goldens on disk
+    golden_train_grads()
+    sys.exit(0)
   golden_data_helper()
   golden_lanczosnet_qm8()
   golden_gcn_qm8()
   golden_general_synth()
   golden_lanczos_layer()
   golden_ada_forward()
+  golden_train_grads()

@@ -158,3 +158,75 @@ def test_tridiag_ritz_oracle_reconstructs_T():
   rec = np.einsum('bik,bk,bjk->bij', S, theta, S)
   np.testing.assert_allclose(rec, T, atol=1e-12)
   assert np.all(np.diff(np.abs(theta), axis=1) <= 1e-15)
+
+
+def _oracle_grad_digests(forward, params, monkeypatch):
+  p64 = {k: v.detach().double().requires_grad_(v.is_floating_point()) for k, v in params.items()}
+  monkeypatch.setattr(orc, '_cast', lambda p, dtype: p)      # the oracle detaches its parameters; keep the tape
+  loss = forward(p64)
+  loss.backward()
+  return float(loss.detach()), {k: v.grad.numpy().reshape(-1) for k, v in p64.items() if v.grad is not None}
+
+
+_WORST = {}
+
+
+def _check_digests(prefix, g, loss, grads, rel):
+  """tests/golden/train_grads.npz holds, per parameter of the reference's own backward, [sum, sum of
+  squares, first 8 entries] of the gradient; ``rel`` is relative to the gradient's largest entry."""
+  assert abs(loss - float(g[prefix + '_loss'])) <= 1e-5 * max(1.0, abs(loss))
+  seen = 0
+  for key in g:
+    if not key.startswith(prefix + '|'):
+      continue
+    name = key.split('|', 1)[1]
+    ours, ref = grads[name], g[key]
+    scale = float(np.abs(ours).max()) + 1e-12
+    assert np.abs(ours[:8] - ref[2:2 + min(8, ours.size)]).max() <= rel * scale, name
+    _WORST[prefix] = max(_WORST.get(prefix, 0.0), float(np.abs(ours[:8] - ref[2:2 + min(8, ours.size)]).max() / scale))
+    assert abs(ours.sum() - ref[0]) <= rel * scale * np.sqrt(ours.size) + 1e-12, name
+    assert abs((ours * ours).sum() - ref[1]) <= 4 * rel * max(ref[1], 1e-30), name
+    seen += 1
+  assert seen == len(grads) and seen > 0
+
+
+def test_oracle_autograd_matches_the_references_own_backward(monkeypatch):
+  """SURVEY 8(f1) pin: the GPU training tests compare against autograd over the oracle; here autograd
+  over the oracle (fp64) is compared with ``loss.backward()`` of the REFERENCE classes (fp32, train mode,
+  runner/qm8_runner.py:226-247) on the same inputs and weights."""
+  g = load_golden('train_grads.npz')
+  q = load_golden('lanczosnet_qm8.npz')
+  label = torch.from_numpy(q['label']).double()
+
+  mod = LanczosNet(configs.qm8_lanczos_net(num_layer=2, hidden_dim=[64, 64]))
+  params = deterministic_state_dict(mod, 11)
+  spec = oracle_spec(mod, 'LanczosNet')
+  loss, grads = _oracle_grad_digests(
+      lambda p: torch.nn.functional.mse_loss(
+          orc.lanczos_net_forward(p, spec, q['node_feat'], q['L'], q['D'], q['V'], q['node_mask'],
+                                  dtype=torch.float64), label), params, monkeypatch)
+  _check_digests('lanczosnet', g, loss, grads, 2e-5)        # measured 2.4e-7
+
+  gcn = GCN(configs.qm8_gcn(num_layer=2, hidden_dim=[64, 64]))
+  gp = deterministic_state_dict(gcn, 9)
+  gspec = oracle_spec(gcn, 'GCN')
+  loss, grads = _oracle_grad_digests(
+      lambda p: torch.nn.functional.mse_loss(
+          orc.gcn_forward(p, gspec, q['node_feat'], q['L'], q['node_mask'], dtype=torch.float64), label),
+      gp, monkeypatch)
+  _check_digests('gcn', g, loss, grads, 2e-5)               # measured 1.1e-7
+
+  a = load_golden('ada_forward_small.npz')
+  cfg = configs.qm8_ada_lanczos_net(num_layer=2, hidden_dim=[32, 32], num_eig_vec=8,
+                                    long_diffusion_dist=[2, 5], short_diffusion_dist=[1, 3])
+  ada = AdaLanczosNet(cfg)
+  ap = deterministic_state_dict(ada, int(a['weight_seed']))
+  aspec = oracle_spec(ada, 'AdaLanczosNet')
+  lab = torch.from_numpy(np.random.RandomState(0).randn(*a['score'].shape).astype(np.float32)).double()
+  loss, grads = _oracle_grad_digests(
+      lambda p: torch.nn.functional.mse_loss(
+          orc.ada_lanczos_net_forward(p, aspec, a['node_feat'], a['L'], a['node_mask'],
+                                      torch.from_numpy(a['q1']).double(), dtype=torch.float64), lab),
+      ap, monkeypatch)
+  _check_digests('ada', g, loss, grads, 5e-4)               # measured 5.6e-6 (the reference ran its Lanczos recurrence in fp32)
+  print('worst relative gradient-entry error vs the reference backward:', _WORST)
