@@ -342,6 +342,28 @@ def golden_train_grads():
                 mask=torch.from_numpy(a['node_mask']))
   loss.backward()
   digest('ada', ada, loss)
+
+  # the operator-chain models and the general (feature-input) model, configs of tests/test_gpu_train.py
+  dc = DCNN(configs.qm8_dcnn(num_layer=2, hidden_dim=[32, 32], diffusion_dist=[2, 5]))
+  dc.load_state_dict(deterministic_state_dict(dc, 3))
+  dc.train()
+  _, loss = dc(nf, L, label=label, mask=mask)
+  loss.backward()
+  digest('dcnn', dc, loss)
+  ch = ChebyNet(configs.qm8_cheby_net(num_layer=2, hidden_dim=[32, 32], polynomial_order=4))
+  ch.load_state_dict(deterministic_state_dict(ch, 3))
+  ch.train()
+  _, loss = ch(nf, L, label=label, mask=mask)
+  loss.backward()
+  digest('cheby', ch, loss)
+  gg = np.load(os.path.join(HERE, 'lanczosnet_general_synth.npz'))
+  gen = LanczosNetGeneral(configs.graph_lanczos_net())
+  gen.load_state_dict(deterministic_state_dict(gen, 5))
+  gen.train()
+  _, loss = gen(torch.from_numpy(gg['node_feat']), torch.from_numpy(gg['L']), torch.from_numpy(gg['D']),
+                torch.from_numpy(gg['V']), label=torch.zeros(gg['score'].shape), mask=torch.from_numpy(gg['node_mask']))
+  loss.backward()
+  digest('general', gen, loss)
   save('train_grads.npz', **out)
 
 

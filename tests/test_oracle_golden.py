@@ -229,4 +229,27 @@ def test_oracle_autograd_matches_the_references_own_backward(monkeypatch):
                                       torch.from_numpy(a['q1']).double(), dtype=torch.float64), lab),
       ap, monkeypatch)
   _check_digests('ada', g, loss, grads, 5e-4)               # measured 5.6e-6 (the reference ran its Lanczos recurrence in fp32)
+  dc_cfg = configs.qm8_dcnn(num_layer=2, hidden_dim=[32, 32], diffusion_dist=[2, 5])
+  dp = deterministic_state_dict(DCNN(dc_cfg), 3)
+  loss, grads = _oracle_grad_digests(
+      lambda p: torch.nn.functional.mse_loss(
+          orc.dcnn_forward(p, dc_cfg.model.diffusion_dist, 6, 2, q['node_feat'], q['L'], q['node_mask'],
+                           dtype=torch.float64), label), dp, monkeypatch)
+  _check_digests('dcnn', g, loss, grads, 2e-5)
+  cp = deterministic_state_dict(ChebyNet(configs.qm8_cheby_net(num_layer=2, hidden_dim=[32, 32], polynomial_order=4)), 3)
+  loss, grads = _oracle_grad_digests(
+      lambda p: torch.nn.functional.mse_loss(
+          orc.cheby_net_forward(p, 4, 6, 2, q['node_feat'], q['L'], q['node_mask'], dtype=torch.float64), label),
+      cp, monkeypatch)
+  _check_digests('cheby', g, loss, grads, 2e-5)
+  gg = load_golden('lanczosnet_general_synth.npz')
+  gen = LanczosNetGeneral(configs.graph_lanczos_net())
+  gnp = deterministic_state_dict(gen, 5)
+  gen_spec = oracle_spec(gen, 'LanczosNetGeneral')
+  loss, grads = _oracle_grad_digests(
+      lambda p: torch.nn.functional.mse_loss(
+          orc.lanczos_net_forward(p, gen_spec, gg['node_feat'], gg['L'], gg['D'], gg['V'], gg['node_mask'],
+                                  dtype=torch.float64), torch.zeros(gg['score'].shape, dtype=torch.float64)),
+      gnp, monkeypatch)
+  _check_digests('general', g, loss, grads, 2e-5)
   print('worst relative gradient-entry error vs the reference backward:', _WORST)
