@@ -135,3 +135,25 @@ def test_sparse_records_rebuild_the_padded_batch(B, seed):
   sparse_bytes = sum(np.asarray(sp[k]).nbytes for k in ('sizes', 'node_ptr', 'node_feat', 'edge_ptr', 'edges', 'V_rows', 'D'))
   dense_bytes = sum(dense[k].nbytes for k in ('node_feat', 'node_mask', 'L', 'D', 'V'))
   assert sparse_bytes < dense_bytes
+
+
+@settings(max_examples=15, deadline=None)
+@given(st.integers(0, 10 ** 6), st.lists(st.integers(0, 59), min_size=1, max_size=40), st.sampled_from([4, 20]))
+def test_packed_molecules_batches_are_pack_sparse_byte_for_byte(seed, idx, K):
+  """data.PackedMolecules flattens a split once and assembles a batch by vectorised gathers; the blob is
+  the one pack_sparse(sparse_collate(...)) builds molecule by molecule -- same bytes, same header -- for
+  any index list (repeats and any order included), also into a reused buffer full of stale bytes."""
+  samples = data.synthetic_qm8_samples(60, seed=seed % 7)       # a few distinct pools, cached below
+  pool = _POOLS.setdefault((seed % 7, K), data.PackedMolecules(samples, K))
+  ref = data.pack_sparse(data.sparse_collate([samples[i] for i in idx], K))
+  got = pool.batch(idx)
+  assert np.array_equal(got['blob'], ref['blob'])
+  assert (got['B'], got['N'], got['K'], got['num_edgetype']) == (ref['B'], ref['N'], ref['K'], ref['num_edgetype'])
+  assert np.array_equal(got['label'], ref['label'])
+  stale = np.full(pool.max_bytes(len(idx)) + 64, 0xAB, np.uint8)
+  again = pool.batch(idx, out=stale)
+  assert again['blob'].base is stale and np.array_equal(again['blob'], ref['blob'])
+  assert pool.max_bytes(len(idx)) >= ref['blob'].size
+
+
+_POOLS = {}
